@@ -1,0 +1,155 @@
+/*
+ * kbo.h — C ABI of libkbo.so, the B200 (sm_100a) GP-suggestion engine.
+ *
+ * This is the drop-in boundary (SURVEY.md §8(b) "B-inner").  The reference platform repo
+ * (/root/reference = kubeflow/kubeflow @ 6d6b78bc) reaches the suggestion service only through
+ * Kubernetes (testing/katib_studyjob_test.py:155-161, testing/kfctl/kf_is_ready_test.py:65-70) and
+ * holds no FFI for it; the arithmetic these entry points replace is the one Katib's
+ * `bayesianoptimization` service executes (upstream kubeflow/katib
+ * pkg/suggestion/v1beta1/skopt/base_service.py -> skopt.Optimizer.tell/ask ->
+ * sklearn.gaussian_process.GaussianProcessRegressor).  Each entry point cites the
+ * scikit-learn 1.9.0 lines ($SK = sklearn/gaussian_process) or the skopt function it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - every call returns KBO_OK (0) or a negative kbo_status; kbo_last_error(h) gives the text.
+ *   - "dev" pointers are device memory owned by the caller (e.g. torch tensors), row-major,
+ *     contiguous, 16-byte aligned.  The library never frees caller memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous on that stream unless the name ends in _host or the doc says "synchronises".
+ *   - one handle per device per thread; a handle owns its workspace (grow-only device buffers).
+ *   - there is NO CPU fallback: without a CUDA device kbo_create fails with KBO_ERR_CUDA.
+ */
+#ifndef KBO_H_
+#define KBO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KBO_VERSION 100 /* 0.1.0 */
+
+typedef struct kbo_handle kbo_handle;
+
+typedef enum kbo_status {
+  KBO_OK = 0,
+  KBO_ERR_INVALID = -1, /* bad argument (maps to gRPC INVALID_ARGUMENT)            */
+  KBO_ERR_CUDA = -2,    /* CUDA runtime/driver error (maps to gRPC INTERNAL)       */
+  KBO_ERR_NOT_PD = -3,  /* Cholesky met a non-positive pivot ($SK/_gpr.py:353-362) */
+  KBO_ERR_NOMEM = -4,
+  KBO_ERR_STATE = -5    /* sweep before fit, etc.                                   */
+} kbo_status;
+
+typedef enum kbo_kernel_kind {
+  KBO_KERNEL_RBF = 0,     /* $SK/kernels.py:1559-1570 */
+  KBO_KERNEL_MATERN52 = 1 /* $SK/kernels.py:1713-1729 (nu = 2.5; skopt's default GP kernel) */
+} kbo_kernel_kind;
+
+typedef enum kbo_acq_kind {
+  KBO_ACQ_EI = 0,  /* skopt.acquisition.gaussian_ei  */
+  KBO_ACQ_LCB = 1, /* skopt.acquisition.gaussian_lcb (value reported is -(mu - kappa*sigma)) */
+  KBO_ACQ_PI = 2   /* skopt.acquisition.gaussian_pi  */
+} kbo_acq_kind;
+
+typedef enum kbo_var_mode {
+  KBO_VAR_F64 = 0,     /* variance contraction V = K* W^T on the FP64 SIMT pipe (checker precision) */
+  KBO_VAR_TC_F16X3 = 1 /* tcgen05 tensor cores, fp16 hi/lo split (3 MMAs per product), fp32 accum  */
+} kbo_var_mode;
+
+typedef enum kbo_dtype { KBO_F64 = 0, KBO_F32 = 1 } kbo_dtype;
+
+/* Fixed hyper-parameters θ and acquisition settings of one tell/ask (SURVEY.md §7 "parity at fixed θ"). */
+typedef struct kbo_params {
+  int32_t kernel;          /* kbo_kernel_kind */
+  int32_t acq;             /* kbo_acq_kind */
+  int32_t normalize_y;     /* 1 = $SK/_gpr.py:275-280 */
+  int32_t var_mode;        /* kbo_var_mode */
+  double amplitude;        /* ConstantKernel value ($SK/kernels.py:1278) */
+  double noise;            /* GaussianProcessRegressor.alpha, added to diag(K) ($SK/_gpr.py:350) */
+  double xi;               /* EI / PI offset (skopt default 0.01) */
+  double kappa;            /* LCB weight (skopt default 1.96) */
+  const double* length_scale; /* HOST pointer, n_length_scale entries */
+  int32_t n_length_scale;  /* 1 (isotropic) or D (anisotropic) */
+  int32_t tc_k_span;       /* TC mode: trials accumulated in TMEM before a drain to fp32 registers; 0 = default */
+} kbo_params;
+
+/* Result of one sweep: best acquisition value and its GLOBAL candidate index (lowest index wins ties,
+ * = np.argmin(-values) in skopt Optimizer._tell), with the posterior at that point (raw y scale). */
+typedef struct kbo_best {
+  double value;
+  int64_t index;
+  double mu;
+  double std;
+} kbo_best;
+
+/* Timings of the last kbo_suggest_host call, milliseconds (CUDA events on the call's stream). */
+typedef struct kbo_timings {
+  float h2d_ms, fit_ms, sweep_ms, d2h_ms, total_ms;
+  float var_kernel_ms;   /* sum over chunks of the variance-contraction kernel */
+  float cross_kernel_ms; /* sum over chunks of the K* / mean kernel           */
+  float acq_kernel_ms;   /* acquisition + argmax kernels                      */
+  int32_t launches;      /* kernels launched by the call                      */
+  int32_t chunks;
+} kbo_timings;
+
+int kbo_version(void);
+int kbo_create(kbo_handle** out, int device);
+void kbo_destroy(kbo_handle* h);
+const char* kbo_last_error(const kbo_handle* h);
+/* cap (bytes) on the per-sweep K* scratch; default 2 GiB.  Determines the candidate chunk size. */
+int kbo_set_scratch_limit(kbo_handle* h, uint64_t bytes);
+
+/* ---- tell: GaussianProcessRegressor.fit at fixed θ ($SK/_gpr.py:275-280, 349-368) ---------------
+ * X: N×D fp64, y: N fp64, device pointers (x_on_host = 0) or host pointers (x_on_host = 1).
+ * Computes X/ℓ, normalised y, K = amp·k(X,X)+noise·I, L = chol(K), W = L^-1, alpha = W^T W y, LML, and
+ * (TC mode) the fp16 hi/lo split of W.  All on the device; asynchronous on `stream` except that a
+ * non-positive pivot is reported by the next synchronising call (kbo_fit_info / kbo_best_to_host). */
+int kbo_fit(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, const kbo_params* p,
+            int x_on_host, void* stream);
+/* synchronises; any out pointer may be NULL.  info = 0 or 1-based index of the failed pivot. */
+int kbo_fit_info(kbo_handle* h, double* lml, double* y_mean, double* y_std, double* y_opt, int32_t* info,
+                 void* stream);
+/* copies the fit state into caller-owned DEVICE buffers (any may be NULL): L_out, W_out are N×N row-major
+ * (L: lower Cholesky factor, strict upper part zeroed; W = L^-1), alpha_out has N entries. For parity tests. */
+int kbo_fit_state(kbo_handle* h, double* L_out, double* W_out, double* alpha_out, void* stream);
+
+/* ---- ask: predict(return_std) + acquisition + first-index argmax over M candidates ---------------
+ * ($SK/_gpr.py:445-500; skopt gaussian_ei/lcb/pi; Optimizer._tell `X_cand[np.argmin(values)]`).
+ * Xc: M×D, dtype xc_dtype, device (xc_on_host=0) or host.  global_offset is added to reported indices
+ * (the rank's row offset when the grid is sharded).
+ * Optional device outputs (NULL to skip): mu_out, std_out, acq_out — fp64, M entries each.
+ * best_dev: device kbo_best written at the end of the stream work. */
+int kbo_sweep(kbo_handle* h, const void* Xc, int32_t xc_dtype, int64_t M, int64_t global_offset, int xc_on_host,
+              double* mu_out, double* std_out, double* acq_out, kbo_best* best_dev, void* stream);
+/* synchronises `stream`, copies *best_dev to host, and returns KBO_ERR_NOT_PD if the fit failed. */
+int kbo_best_to_host(kbo_handle* h, const kbo_best* best_dev, kbo_best* best_host, void* stream);
+
+/* ---- one call, HOST buffers in, host result out (tell + ask); synchronises -----------------------
+ * The end-to-end entry: H2D of X, y, Xc and D2H of the result are inside the call. */
+int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, const void* Xc,
+                     int32_t xc_dtype, int64_t M, int64_t global_offset, const kbo_params* p,
+                     kbo_best* best_host, kbo_timings* timings /* may be NULL */);
+int kbo_last_timings(kbo_handle* h, kbo_timings* out);
+
+/* ---- building blocks, caller-owned device memory (used by the parity tests one kernel at a time) --
+ * kbo_gram:  K (N×ldk, fp64) = amplitude·k(Xs,Xs) + noise·I, Xs already divided by ℓ. ($SK/kernels.py:1561,1716)
+ * kbo_potrf: in-place lower Cholesky of A (N×lda); upper triangle untouched; info_dev = 0 or failed pivot. ($SK/_gpr.py:352)
+ * kbo_trtri: W (N×ldw, zero upper) = L^-1 for lower-triangular L.  Needs the potrf of the same handle just before
+ *            (reuses its inverted diagonal blocks).
+ * kbo_acq_argmax: standalone acquisition + argmax pass over (mu, var) in the NORMALISED y scale:
+ *            mu_n, var_n fp32 (8 B/candidate read) -> optional acq fp32 (4 B write) + best. The HBM-bound kernel
+ *            whose GB/s the headline metric asks for. */
+int kbo_gram(kbo_handle* h, const double* Xs, int32_t N, int32_t D, int32_t kernel, double amplitude, double noise,
+             double* K, int32_t ldk, void* stream);
+int kbo_potrf(kbo_handle* h, double* A, int32_t N, int32_t lda, int32_t* info_dev, void* stream);
+int kbo_trtri(kbo_handle* h, const double* L, int32_t N, int32_t ldl, double* W, int32_t ldw, void* stream);
+int kbo_acq_argmax(kbo_handle* h, const float* mu_n, const float* var_n, int64_t M, int64_t global_offset,
+                   int32_t acq, double y_mean, double y_std, double y_opt, double xi, double kappa,
+                   float* acq_out, kbo_best* best_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KBO_H_ */

@@ -1,0 +1,230 @@
+// extern "C" surface of libkbo.so (include/kbo.h).  No exceptions cross this boundary; every failure is a
+// negative kbo_status plus kbo_last_error() text.  There is no CPU path: without a device kbo_create fails.
+#include "kbo_internal.cuh"
+
+static const char* kNoHandle = "kbo: null handle";
+
+extern "C" {
+
+int kbo_version(void) { return KBO_VERSION; }
+
+int kbo_create(kbo_handle** out, int device) {
+  if (!out) return KBO_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return KBO_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return KBO_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return KBO_ERR_CUDA;
+  kbo_handle* h = new (std::nothrow) kbo_handle();
+  if (!h) return KBO_ERR_NOMEM;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    // sm_100a cubin only: refuse politely instead of failing at the first launch
+    h->err = "libkbo is built for sm_100a (B200) only";
+  }
+  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  *out = h;
+  return KBO_OK;
+}
+
+void kbo_destroy(kbo_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  DevBuf* bufs[] = {&h->d_inv_ls, &h->Xs, &h->nx, &h->yraw, &h->yn, &h->K, &h->W, &h->Linv, &h->T, &h->alpha, &h->z, &h->Wh, &h->Wl,
+                    &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
+                    &h->blockbest, &h->best};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto* v : {&h->ev_var, &h->ev_cross, &h->ev_acq})
+    for (auto& p : *v) {
+      cudaEventDestroy(p.first);
+      cudaEventDestroy(p.second);
+    }
+  delete h;
+}
+
+const char* kbo_last_error(const kbo_handle* h) { return h ? h->err.c_str() : kNoHandle; }
+
+int kbo_set_scratch_limit(kbo_handle* h, uint64_t bytes) {
+  if (!h) return KBO_ERR_INVALID;
+  if (bytes < (64ull << 20)) KBO_FAIL(h, KBO_ERR_INVALID, "scratch limit must be >= 64 MiB");
+  h->scratch_limit = bytes;
+  return KBO_OK;
+}
+
+int kbo_fit(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, const kbo_params* p, int x_on_host, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!X || !y || !p || !p->length_scale) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: null argument");
+  if (N < 1 || D < 1) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: need N >= 1 and D >= 1 (got N=%d D=%d)", N, D);
+  cudaStream_t s = (cudaStream_t)stream;
+  KBO_CUDA(h, cudaSetDevice(h->device));
+  if (x_on_host) {
+    KBO_TRY(kbo_reserve(h, h->stage_X, sizeof(double) * (size_t)N * D));
+    KBO_TRY(kbo_reserve(h, h->stage_y, sizeof(double) * (size_t)N));
+    KBO_CUDA(h, cudaMemcpyAsync(h->stage_X.p, X, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, s));
+    KBO_CUDA(h, cudaMemcpyAsync(h->stage_y.p, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+    X = (const double*)h->stage_X.p;
+    y = (const double*)h->stage_y.p;
+  }
+  return kbo_i_fit(h, X, y, N, D, p, s);
+}
+
+int kbo_fit_info(kbo_handle* h, double* lml, double* y_mean, double* y_std, double* y_opt, int32_t* info, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_info: call kbo_fit first");
+  cudaStream_t s = (cudaStream_t)stream;
+  double sc[S_COUNT];
+  int inf = 0;
+  KBO_CUDA(h, cudaMemcpyAsync(sc, h->scal.p, sizeof sc, cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaMemcpyAsync(&inf, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaStreamSynchronize(s));
+  if (lml) *lml = sc[S_LML];
+  if (y_mean) *y_mean = sc[S_YMEAN];
+  if (y_std) *y_std = sc[S_YSTD];
+  if (y_opt) *y_opt = sc[S_YOPT];
+  if (info) *info = inf;
+  if (inf != 0) KBO_FAIL(h, KBO_ERR_NOT_PD, "kernel matrix is not positive definite (pivot %d); increase `noise` ($SK/_gpr.py:353-362)", inf);
+  return KBO_OK;
+}
+
+int kbo_fit_state(kbo_handle* h, double* L_out, double* W_out, double* alpha_out, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_state: call kbo_fit first");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t N = h->N, ld = h->ld;
+  if (L_out) {
+    KBO_CUDA(h, cudaMemcpy2DAsync(L_out, N * 8, h->K.p, ld * 8, N * 8, N, cudaMemcpyDeviceToDevice, s));
+    KBO_TRY(kbo_i_zero_upper(h, L_out, (int)N, (int)N, s));
+  }
+  if (W_out) KBO_CUDA(h, cudaMemcpy2DAsync(W_out, N * 8, h->W.p, ld * 8, N * 8, N, cudaMemcpyDeviceToDevice, s));
+  if (alpha_out) KBO_CUDA(h, cudaMemcpyAsync(alpha_out, h->alpha.p, N * 8, cudaMemcpyDeviceToDevice, s));
+  return KBO_OK;
+}
+
+int kbo_sweep(kbo_handle* h, const void* Xc, int32_t xc_dtype, int64_t M, int64_t global_offset, int xc_on_host, double* mu_out,
+              double* std_out, double* acq_out, kbo_best* best_dev, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!Xc || !best_dev) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: null argument");
+  if (M < 1) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: M must be >= 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  KBO_CUDA(h, cudaSetDevice(h->device));
+  if (xc_on_host) {
+    const size_t bytes = (size_t)M * h->D * (xc_dtype == KBO_F64 ? 8 : 4);
+    KBO_TRY(kbo_reserve(h, h->stage_Xc, bytes));
+    KBO_CUDA(h, cudaMemcpyAsync(h->stage_Xc.p, Xc, bytes, cudaMemcpyHostToDevice, s));
+    Xc = h->stage_Xc.p;
+  }
+  return kbo_i_sweep(h, Xc, xc_dtype, M, global_offset, mu_out, std_out, acq_out, best_dev, s);
+}
+
+int kbo_best_to_host(kbo_handle* h, const kbo_best* best_dev, kbo_best* best_host, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!best_dev || !best_host) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_best_to_host: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int inf = 0;
+  KBO_CUDA(h, cudaMemcpyAsync(best_host, best_dev, sizeof(kbo_best), cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaMemcpyAsync(&inf, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaStreamSynchronize(s));
+  if (inf != 0) KBO_FAIL(h, KBO_ERR_NOT_PD, "kernel matrix is not positive definite (pivot %d); increase `noise`", inf);
+  return KBO_OK;
+}
+
+static float sum_pairs(std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, size_t used) {
+  float t = 0.f;
+  for (size_t i = 0; i < used; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, v[i].first, v[i].second);
+    t += ms;
+  }
+  return t;
+}
+
+int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, const void* Xc, int32_t xc_dtype, int64_t M,
+                     int64_t global_offset, const kbo_params* p, kbo_best* best_host, kbo_timings* timings) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!X || !y || !Xc || !p || !best_host) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_suggest_host: null argument");
+  cudaStream_t s = 0;
+  KBO_CUDA(h, cudaSetDevice(h->device));
+  KBO_TRY(kbo_reserve(h, h->best, sizeof(kbo_best)));
+  h->launches = 0;
+  h->time_kernels = true;
+  h->ev_var_used = h->ev_cross_used = h->ev_acq_used = 0;
+  cudaEventRecord(h->ev[0], s);
+  // H2D of everything up front (X, y, Xc), then tell + ask, then the 32-byte result back
+  int r = kbo_fit(h, X, y, N, D, p, 1, s);
+  cudaEventRecord(h->ev[1], s);
+  if (r == KBO_OK) {
+    const size_t bytes = (size_t)M * D * (xc_dtype == KBO_F64 ? 8 : 4);
+    r = kbo_reserve(h, h->stage_Xc, bytes);
+    if (r == KBO_OK) {
+      cudaError_t e = cudaMemcpyAsync(h->stage_Xc.p, Xc, bytes, cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) {
+        h->err = std::string("H2D of candidates failed: ") + cudaGetErrorString(e);
+        r = KBO_ERR_CUDA;
+      }
+    }
+  }
+  cudaEventRecord(h->ev[2], s);
+  if (r == KBO_OK) r = kbo_i_sweep(h, h->stage_Xc.p, xc_dtype, M, global_offset, nullptr, nullptr, nullptr, (kbo_best*)h->best.p, s);
+  cudaEventRecord(h->ev[3], s);
+  if (r == KBO_OK) r = kbo_best_to_host(h, (const kbo_best*)h->best.p, best_host, s);
+  cudaEventRecord(h->ev[4], s);
+  cudaEventSynchronize(h->ev[4]);
+  h->time_kernels = false;
+  kbo_timings t{};
+  cudaEventElapsedTime(&t.fit_ms, h->ev[0], h->ev[1]);    // includes H2D of X, y
+  cudaEventElapsedTime(&t.h2d_ms, h->ev[1], h->ev[2]);    // H2D of the candidate grid
+  cudaEventElapsedTime(&t.sweep_ms, h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&t.d2h_ms, h->ev[3], h->ev[4]);
+  cudaEventElapsedTime(&t.total_ms, h->ev[0], h->ev[4]);
+  t.var_kernel_ms = sum_pairs(h->ev_var, h->ev_var_used);
+  t.cross_kernel_ms = sum_pairs(h->ev_cross, h->ev_cross_used);
+  t.acq_kernel_ms = sum_pairs(h->ev_acq, h->ev_acq_used);
+  t.launches = h->launches;
+  t.chunks = h->tim.chunks;
+  h->tim = t;
+  if (timings) *timings = t;
+  return r;
+}
+
+int kbo_last_timings(kbo_handle* h, kbo_timings* out) {
+  if (!h || !out) return KBO_ERR_INVALID;
+  *out = h->tim;
+  return KBO_OK;
+}
+
+int kbo_gram(kbo_handle* h, const double* Xs, int32_t N, int32_t D, int32_t kernel, double amplitude, double noise, double* K, int32_t ldk,
+             void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!Xs || !K || N < 1 || D < 1 || ldk < N) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_gram: bad argument");
+  if (kernel != KBO_KERNEL_RBF && kernel != KBO_KERNEL_MATERN52) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_gram: unknown kernel %d", kernel);
+  return kbo_i_gram(h, Xs, N, D, kernel, amplitude, noise, K, ldk, (cudaStream_t)stream);
+}
+
+int kbo_potrf(kbo_handle* h, double* A, int32_t N, int32_t lda, int32_t* info_dev, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!A || !info_dev || N < 1 || lda < N) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_potrf: bad argument");
+  return kbo_i_potrf(h, A, N, lda, info_dev, (cudaStream_t)stream);
+}
+
+int kbo_trtri(kbo_handle* h, const double* L, int32_t N, int32_t ldl, double* W, int32_t ldw, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!L || !W || N < 1 || ldl < N || ldw < N) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_trtri: bad argument");
+  return kbo_i_trtri(h, L, N, ldl, W, ldw, (cudaStream_t)stream);
+}
+
+int kbo_acq_argmax(kbo_handle* h, const float* mu_n, const float* var_n, int64_t M, int64_t global_offset, int32_t acq, double y_mean,
+                   double y_std, double y_opt, double xi, double kappa, float* acq_out, kbo_best* best_dev, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!mu_n || !var_n || !best_dev) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_acq_argmax: null argument");
+  if (acq < KBO_ACQ_EI || acq > KBO_ACQ_PI) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_acq_argmax: unknown acquisition %d", acq);
+  return kbo_i_acq_argmax_f32(h, mu_n, var_n, M, global_offset, acq, y_mean, y_std, y_opt, xi, kappa, 1.0, acq_out, best_dev,
+                              (cudaStream_t)stream);
+}
+
+}  // extern "C"

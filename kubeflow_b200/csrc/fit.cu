@@ -1,0 +1,491 @@
+// tell(): GaussianProcessRegressor.fit at fixed θ on the device, FP64 throughout.
+//   $SK/_gpr.py:275-280 normalise y | :349-350 K = k(X,X)+alpha·I | :352 L = cholesky(K) | :363 alpha_ = cho_solve
+//   $SK/kernels.py:1559-1570 RBF, :1713-1729 Matern(nu=2.5)
+// Why FP64 here (not fp32/tensor cores): the posterior mean is K*·alpha with |alpha|₂ up to ~3e3 for the
+// workloads of record; fp32 L/alpha moves EI by 1e-4 (measured) against a 1e-5 contract.
+// B200 has a full FP64 pipe, and the fit is O(N³/3) once per suggestion next to the O(M·N²) sweep.
+#include "kbo_internal.cuh"
+#include "dgemm.cuh"
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double kbo_kernel_eval(double d2, int kind) {
+  d2 = d2 < 0.0 ? 0.0 : d2;
+  if (kind == KBO_KERNEL_RBF) return exp(-0.5 * d2);
+  const double s = sqrt(5.0 * d2);
+  return (1.0 + s + s * s * (1.0 / 3.0)) * exp(-s);
+}
+
+// Xs = X / ℓ, nx = |Xs|² (one thread per trial row)
+__global__ void prep_x_kernel(const double* __restrict__ X, int N, int D, const double* __restrict__ inv_ls, int n_ls,
+                              double* __restrict__ Xs, double* __restrict__ nx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double s = 0.0;
+  for (int d = 0; d < D; d++) {
+    const double v = X[(size_t)i * D + d] * inv_ls[n_ls == 1 ? 0 : d];
+    Xs[(size_t)i * D + d] = v;
+    s = fma(v, v, s);
+  }
+  nx[i] = s;
+}
+
+// mean / population std / min of y and the normalised yn — one CTA, fixed-order tree reductions.
+__global__ void __launch_bounds__(1024) prep_y_kernel(const double* __restrict__ y, int N, int normalize, double* __restrict__ yn,
+                                                      double* __restrict__ scal) {
+  __shared__ double red[1024];
+  __shared__ double s_mean, s_std;
+  const int t = threadIdx.x;
+  double a = 0.0, mn = INFINITY;
+  for (int i = t; i < N; i += 1024) {
+    a += y[i];
+    mn = fmin(mn, y[i]);
+  }
+  red[t] = a;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  if (t == 0) s_mean = red[0] / N;
+  __syncthreads();
+  red[t] = mn;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) red[t] = fmin(red[t], red[t + o]);
+    __syncthreads();
+  }
+  const double ymin = red[0];
+  __syncthreads();
+  const double mean = s_mean;
+  a = 0.0;
+  for (int i = t; i < N; i += 1024) {
+    const double d = y[i] - mean;
+    a = fma(d, d, a);
+  }
+  red[t] = a;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  if (t == 0) {
+    double sd = sqrt(red[0] / N);
+    if (sd < 10.0 * 2.220446049250313e-16) sd = 1.0;  // sklearn _handle_zeros_in_scale
+    s_std = sd;
+  }
+  __syncthreads();
+  const double m = normalize ? s_mean : 0.0, sd = normalize ? s_std : 1.0;
+  for (int i = t; i < N; i += 1024) yn[i] = (y[i] - m) / sd;
+  if (t == 0) {
+    scal[S_YMEAN] = m;
+    scal[S_YSTD] = sd;
+    scal[S_YOPT] = ymin;
+  }
+}
+
+// K = amp·k(Xs,Xs) + noise·I.  Exact pairwise differences (as scipy cdist does), lower tiles computed
+// and mirrored.  64×64 tile, 4×4 per thread, D consumed in chunks of 16 through shared memory.
+__global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs, int N, int D, int kind, double amp, double noise,
+                                                   double* __restrict__ K, int ldk) {
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (n0 > m0) return;
+  __shared__ double Xi[16][66], Xj[16][66];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[4][4] = {};
+  for (int d0 = 0; d0 < D; d0 += 16) {
+    const int d = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = (tid >> 4) + 16 * i;
+      Xi[d][r] = (m0 + r < N && d0 + d < D) ? Xs[(size_t)(m0 + r) * D + d0 + d] : 0.0;
+      Xj[d][r] = (n0 + r < N && d0 + d < D) ? Xs[(size_t)(n0 + r) * D + d0 + d] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int dd = 0; dd < 16; dd++) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = Xi[dd][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Xj[dd][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const double df = a[i] - b[j];
+          acc[i][j] = fma(df, df, acc[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int gm = m0 + ty + 16 * i;
+    if (gm >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int gn = n0 + tx + 16 * j;
+      if (gn >= N) continue;
+      double v = amp * kbo_kernel_eval(acc[i][j], kind);
+      if (gm == gn) v += noise;
+      K[(size_t)gm * ldk + gn] = v;
+      if (m0 != n0) K[(size_t)gn * ldk + gm] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked right-looking Cholesky (lower), NB = 64.
+// potf2_inv: factor one diagonal block in shared memory and invert it (for the panel solve).
+__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, int lda, int jb, int k_global,
+                                                        double* __restrict__ Linv, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double(*S)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm);
+  double(*T)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm + KBO_NB * (KBO_NB + 1));
+  __shared__ int bad;
+  const int t = threadIdx.x;
+  if (*info != 0) return;  // an earlier panel already failed
+  if (t == 0) bad = 0;
+  for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    S[r][c] = (r < jb && c <= r) ? A[(size_t)r * lda + c] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  for (int j = 0; j < jb; j++) {
+    const double djj = S[j][j];
+    if (!(djj > 0.0)) {
+      if (t == 0) {
+        bad = 1;
+        *info = k_global + j + 1;
+      }
+    }
+    __syncthreads();
+    if (bad) return;
+    const double d = sqrt(djj);
+    const double rd = 1.0 / d;
+    __syncthreads();
+    if (t == 0) S[j][j] = d;
+    for (int i = j + 1 + t; i < jb; i += 256) S[i][j] *= rd;
+    __syncthreads();
+    // trailing update of the lower triangle: S[i][c] -= S[i][j]·S[c][j], j < c <= i < jb
+    const int rem = jb - j - 1;
+    for (int e = t; e < rem * rem; e += 256) {
+      const int i = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= i) S[i][c] = fma(-S[i][j], S[c][j], S[i][c]);
+    }
+    __syncthreads();
+  }
+  // inverse of the lower-triangular block by forward substitution, 4 threads per column
+  {
+    const int c = t >> 2, q = t & 3;
+    for (int i = 0; i < KBO_NB; i++) {
+      double s = 0.0;
+      if (i > c)
+        for (int k = c + q; k < i; k += 4) s = fma(S[i][k], T[k][c], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0) T[i][c] = (i < c) ? 0.0 : (i == c ? 1.0 / S[i][i] : -s / S[i][i]);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    if (r < jb && c <= r) A[(size_t)r * lda + c] = S[r][c];
+    Linv[e] = T[r][c];
+  }
+}
+
+// batched inverse of the 64×64 diagonal blocks of a lower-triangular L (for kbo_trtri); one CTA per block
+__global__ void __launch_bounds__(256) diag_inv_kernel(const double* __restrict__ L, int N, int ldl, double* __restrict__ W, int ldw) {
+  extern __shared__ double sm[];
+  double(*S)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm);
+  double(*T)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm + KBO_NB * (KBO_NB + 1));
+  const int t = threadIdx.x, k0 = blockIdx.x * KBO_NB, jb = min(KBO_NB, N - k0);
+  for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    S[r][c] = (r < jb && c <= r) ? L[(size_t)(k0 + r) * ldl + k0 + c] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  const int c = t >> 2, q = t & 3;
+  for (int i = 0; i < KBO_NB; i++) {
+    double s = 0.0;
+    if (i > c)
+      for (int k = c + q; k < i; k += 4) s = fma(S[i][k], T[k][c], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (q == 0) T[i][c] = (i < c) ? 0.0 : (i == c ? 1.0 / S[i][i] : -s / S[i][i]);
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    if (r < jb && c < jb) W[(size_t)(k0 + r) * ldw + k0 + c] = T[r][c];
+  }
+}
+
+// panel solve: P ← P · Linvᵀ for a 64-row slab of the panel below the diagonal block (in place, rows owned by the CTA)
+__global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ P, int lda, int rows, int jb,
+                                                         const double* __restrict__ Linv, const int* __restrict__ info) {
+  if (*info != 0) return;
+  extern __shared__ double sm[];
+  double(*Ps)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm);
+  double(*Ls)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm + KBO_NB * (KBO_NB + 1));
+  const int t = threadIdx.x, r0 = blockIdx.x * 64;
+  for (int e = t; e < 64 * 64; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    Ps[r][c] = (r0 + r < rows && c < jb) ? P[(size_t)(r0 + r) * lda + c] : 0.0;
+    Ls[r][c] = Linv[e];
+  }
+  __syncthreads();
+  const int tx = t & 15, ty = t >> 4;
+  double acc[4][4] = {};
+  for (int k = 0; k < jb; k++) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = Ps[ty + 16 * i][k];
+#pragma unroll
+    for (int j = 0; j < 4; j++) b[j] = Ls[tx + 16 * j][k];  // (P·Linvᵀ)[r,c] = Σ_k P[r,k]·Linv[c,k]
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = r0 + ty + 16 * i;
+    if (r >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = tx + 16 * j;
+      if (c < jb) P[(size_t)r * lda + c] = acc[i][j];
+    }
+  }
+}
+
+int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s) {
+  KBO_TRY(kbo_reserve(h, h->Linv, sizeof(double) * KBO_NB * KBO_NB));
+  static bool attr_set = false;
+  const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
+  if (!attr_set) {
+    KBO_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KBO_CUDA(h, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+  double* Linv = (double*)h->Linv.p;
+  for (int k = 0; k < N; k += KBO_NB) {
+    const int jb = min(KBO_NB, N - k);
+    double* Akk = A + (size_t)k * lda + k;
+    potf2_inv_kernel<<<1, 256, smem, s>>>(Akk, lda, jb, k, Linv, info_dev);
+    KBO_LAUNCH_CHECK(h);
+    const int rows = N - k - jb;
+    if (rows > 0) {
+      double* P = A + (size_t)(k + jb) * lda + k;
+      trsm_panel_kernel<<<(rows + 63) / 64, 256, smem, s>>>(P, lda, rows, jb, Linv, info_dev);
+      KBO_LAUNCH_CHECK(h);
+      double* C = A + (size_t)(k + jb) * lda + (k + jb);
+      dgemm64_launch<true, EPI_STORE>(s, rows, rows, jb, P, lda, P, lda, C, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+      KBO_LAUNCH_CHECK(h);
+    }
+  }
+  return KBO_OK;
+}
+
+// W = L^-1 by recursive doubling: [[W11,0],[−W22·L21·W11, W22]] — log2(N/64) levels of two batched GEMMs.
+int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int ldw, cudaStream_t s) {
+  static bool attr_set = false;
+  const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
+  if (!attr_set) {
+    KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
+  double* T = (double*)h->T.p;
+  KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));
+  diag_inv_kernel<<<(N + KBO_NB - 1) / KBO_NB, 256, smem, s>>>(L, N, ldl, W, ldw);
+  KBO_LAUNCH_CHECK(h);
+  for (long long b = KBO_NB; b < N; b *= 2) {
+    const int full = (int)(N / (2 * b));
+    const long long sL = 2 * b * (long long)ldl + 2 * b, sW = 2 * b * (long long)ldw + 2 * b;
+    if (full > 0) {
+      // T21 = L21 · W11   (W11 lower-triangular: k >= n)
+      dgemm64_launch<false, EPI_STORE>(s, (int)b, (int)b, (int)b, L + b * ldl, ldl, W, ldw, T + b * ldw, ldw, 1.0, 0.0, KM_FROM_N, 0,
+                                       TS_NONE, full, sL, sW, sW);
+      KBO_LAUNCH_CHECK(h);
+      // W21 = −W22 · T21  (W22 lower-triangular: k <= m)
+      dgemm64_launch<false, EPI_STORE>(s, (int)b, (int)b, (int)b, W + b * ldw + b, ldw, T + b * ldw, ldw, W + b * ldw, ldw, -1.0, 0.0,
+                                       KM_UPTO_M, 0, TS_NONE, full, sW, sW, sW);
+      KBO_LAUNCH_CHECK(h);
+    }
+    const long long r0 = (long long)full * 2 * b;
+    if (r0 + b < N) {  // ragged last pair: second half has rows2 < b rows
+      const int rows2 = (int)(N - (r0 + b));
+      const double* L21 = L + (r0 + b) * ldl + r0;
+      const double* W11 = W + r0 * ldw + r0;
+      double* T21 = T + (r0 + b) * ldw + r0;
+      double* W21 = W + (r0 + b) * ldw + r0;
+      const double* W22 = W + (r0 + b) * ldw + (r0 + b);
+      dgemm64_launch<false, EPI_STORE>(s, rows2, (int)b, (int)b, L21, ldl, W11, ldw, T21, ldw, 1.0, 0.0, KM_FROM_N, 0, TS_NONE);
+      KBO_LAUNCH_CHECK(h);
+      dgemm64_launch<false, EPI_STORE>(s, rows2, (int)b, rows2, W22, ldw, T21, ldw, W21, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+      KBO_LAUNCH_CHECK(h);
+    }
+  }
+  return KBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// z = W·yn (one warp per row, lower triangle only) ; alpha = Wᵀ·z (one thread per column, coalesced across k)
+__global__ void trmv_lower_kernel(const double* __restrict__ W, int N, int ldw, const double* __restrict__ x, double* __restrict__ z) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  double s = 0.0;
+  for (int k = lane; k <= row; k += 32) s = fma(W[(size_t)row * ldw + k], x[k], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) z[row] = s;
+}
+__global__ void trmv_lower_t_kernel(const double* __restrict__ W, int N, int ldw, const double* __restrict__ z, double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  double s = 0.0;
+  for (int i = k; i < N; i++) s = fma(W[(size_t)i * ldw + k], z[i], s);
+  out[k] = s;
+}
+// LML = −½ ynᵀalpha − Σ log L_ii − N/2 log 2π  ($SK/_gpr.py:604-618)
+__global__ void __launch_bounds__(1024) lml_kernel(const double* __restrict__ L, int N, int ldl, const double* __restrict__ yn,
+                                                   const double* __restrict__ alpha, double* __restrict__ scal) {
+  __shared__ double r1[1024], r2[1024];
+  const int t = threadIdx.x;
+  double q = 0.0, ld = 0.0;
+  for (int i = t; i < N; i += 1024) {
+    q = fma(yn[i], alpha[i], q);
+    ld += log(L[(size_t)i * ldl + i]);
+  }
+  r1[t] = q;
+  r2[t] = ld;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) {
+      r1[t] += r1[t + o];
+      r2[t] += r2[t + o];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    scal[S_QUAD] = r1[0];
+    scal[S_LOGDET] = r2[0];
+    scal[S_LML] = -0.5 * r1[0] - r2[0] - 0.5 * N * 1.8378770664093453;
+  }
+}
+
+// max |W| (order-independent: bit pattern of a non-negative double is monotone as uint64)
+__global__ void absmax_kernel(const double* __restrict__ W, int N, int ldw, unsigned long long* __restrict__ out) {
+  double m = 0.0;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)N * N; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / N), c = (int)(e % N);
+    if (c <= r) m = fmax(m, fabs(W[(size_t)r * ldw + c]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+// fp16 hi/lo planes of 2^s·W (s chosen so max|2^s W| ∈ [2^13, 2^14)); zero above the diagonal and in the padding.
+__global__ void split_w_kernel(const double* __restrict__ W, int N, int ldw, int Npad, const unsigned long long* __restrict__ amax,
+                               __half* __restrict__ Wh, __half* __restrict__ Wl, double* __restrict__ scale_out) {
+  const double mx = __longlong_as_double((long long)*amax);
+  int e;
+  frexp(mx > 0.0 ? mx : 1.0, &e);  // mx = f·2^e, f ∈ [0.5,1)
+  const double sc = ldexp(1.0, 14 - e);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    scale_out[0] = sc;
+    scale_out[1] = 1.0 / sc;
+  }
+  const int r = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Npad; c += gridDim.x * blockDim.x) {
+    double v = (r < N && c <= r) ? W[(size_t)r * ldw + c] * sc : 0.0;
+    const __half hi = __double2half(v);
+    const __half lo = __double2half(v - (double)__half2float(hi));
+    Wh[(size_t)r * Npad + c] = hi;
+    Wl[(size_t)r * Npad + c] = lo;
+  }
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ A, int N, int lda) {
+  const int r = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < N && c > r) A[(size_t)r * lda + c] = 0.0;
+}
+int kbo_i_zero_upper(kbo_handle* h, double* A, int N, int lda, cudaStream_t s) {
+  dim3 g((N + 255) / 256, N);
+  zero_upper_kernel<<<g, 256, 0, s>>>(A, N, lda);
+  KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
+
+int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double amp, double noise, double* K, int ldk, cudaStream_t s) {
+  dim3 grid((N + 63) / 64, (N + 63) / 64);
+  gram_kernel<<<grid, 256, 0, s>>>(Xs, N, D, kernel, amp, noise, K, ldk);
+  KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
+
+int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, const kbo_params* p, cudaStream_t s) {
+  if (N < 1 || D < 1 || D > 512) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: need N >= 1 and 1 <= D <= 512 (got N=%d D=%d)", N, D);
+  if (p->n_length_scale != 1 && p->n_length_scale != D)
+    KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: n_length_scale must be 1 or D=%d (got %d)", D, p->n_length_scale);
+  if (!(p->noise >= 0.0) || !(p->amplitude > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: amplitude must be > 0 and noise >= 0");
+  if (p->kernel != KBO_KERNEL_RBF && p->kernel != KBO_KERNEL_MATERN52) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: unknown kernel %d", p->kernel);
+  for (int d = 0; d < p->n_length_scale; d++)
+    if (!(p->length_scale[d] > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: length_scale[%d] must be > 0", d);
+  h->fitted = false;
+  h->N = N;
+  h->D = D;
+  h->ld = round_up(N, 64);
+  h->Npad = round_up(N, 256);
+  h->prm = *p;
+  h->inv_ls.resize(p->n_length_scale);
+  for (int d = 0; d < p->n_length_scale; d++) h->inv_ls[d] = 1.0 / p->length_scale[d];
+  h->prm.length_scale = nullptr;
+  const int ld = h->ld;
+  KBO_TRY(kbo_reserve(h, h->d_inv_ls, sizeof(double) * 512));
+  KBO_TRY(kbo_reserve(h, h->Xs, sizeof(double) * (size_t)N * D));
+  KBO_TRY(kbo_reserve(h, h->nx, sizeof(double) * N));
+  KBO_TRY(kbo_reserve(h, h->yn, sizeof(double) * N));
+  KBO_TRY(kbo_reserve(h, h->K, sizeof(double) * (size_t)N * ld));
+  KBO_TRY(kbo_reserve(h, h->W, sizeof(double) * (size_t)N * ld));
+  KBO_TRY(kbo_reserve(h, h->alpha, sizeof(double) * N));
+  KBO_TRY(kbo_reserve(h, h->z, sizeof(double) * N));
+  KBO_TRY(kbo_reserve(h, h->scal, sizeof(double) * 16));
+  KBO_TRY(kbo_reserve(h, h->info, sizeof(int) * 4));
+  // inv_ls is tiny: stage through pageable memory is fine, but keep it async-safe by copying from the vector we own
+  KBO_CUDA(h, cudaMemcpyAsync(h->d_inv_ls.p, h->inv_ls.data(), sizeof(double) * h->inv_ls.size(), cudaMemcpyHostToDevice, s));
+  prep_x_kernel<<<(N + 127) / 128, 128, 0, s>>>(X, N, D, (const double*)h->d_inv_ls.p, p->n_length_scale, (double*)h->Xs.p, (double*)h->nx.p);
+  KBO_LAUNCH_CHECK(h);
+  prep_y_kernel<<<1, 1024, 0, s>>>(y, N, p->normalize_y, (double*)h->yn.p, (double*)h->scal.p);
+  KBO_LAUNCH_CHECK(h);
+  KBO_TRY(kbo_i_gram(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, s));
+  KBO_TRY(kbo_i_potrf(h, (double*)h->K.p, N, ld, (int*)h->info.p, s));
+  KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
+  trmv_lower_kernel<<<(N + 7) / 8, 256, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->yn.p, (double*)h->z.p);
+  KBO_LAUNCH_CHECK(h);
+  trmv_lower_t_kernel<<<(N + 127) / 128, 128, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->z.p, (double*)h->alpha.p);
+  KBO_LAUNCH_CHECK(h);
+  lml_kernel<<<1, 1024, 0, s>>>((const double*)h->K.p, N, ld, (const double*)h->yn.p, (const double*)h->alpha.p, (double*)h->scal.p);
+  KBO_LAUNCH_CHECK(h);
+  if (p->var_mode == KBO_VAR_TC_F16X3) {
+    const int Npad = h->Npad;
+    KBO_TRY(kbo_reserve(h, h->Wh, sizeof(__half) * (size_t)Npad * Npad));
+    KBO_TRY(kbo_reserve(h, h->Wl, sizeof(__half) * (size_t)Npad * Npad));
+    unsigned long long* amax = (unsigned long long*)((double*)h->scal.p + 8);
+    KBO_CUDA(h, cudaMemsetAsync(amax, 0, sizeof(unsigned long long), s));
+    absmax_kernel<<<h->sm_count * 4, 256, 0, s>>>((const double*)h->W.p, N, ld, amax);
+    KBO_LAUNCH_CHECK(h);
+    dim3 g((Npad + 255) / 256, Npad);
+    split_w_kernel<<<g, 256, 0, s>>>((const double*)h->W.p, N, ld, Npad, amax, (__half*)h->Wh.p, (__half*)h->Wl.p, (double*)h->scal.p + 6);
+    KBO_LAUNCH_CHECK(h);
+  }
+  h->fitted = true;
+  return KBO_OK;
+}

@@ -1,0 +1,114 @@
+// Internal declarations shared by the libkbo translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/kbo.h"
+
+#define KBO_NB 64  // Cholesky / trtri block size (one diagonal block = one CTA in shared memory)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct kbo_handle {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  uint64_t scratch_limit = 2ull << 30;
+
+  // ---- fit state -------------------------------------------------------------------------
+  bool fitted = false;
+  int N = 0, D = 0, ld = 0;  // ld = leading dimension of L / W (multiple of 64)
+  int Npad = 0;              // multiple of 256: extent of the fp16 W planes and of K* scratch rows
+  kbo_params prm{};
+  std::vector<double> inv_ls;  // 1/ℓ_d, host copy
+  DevBuf d_inv_ls;             // D doubles
+  DevBuf Xs, nx, yraw, yn, K, W, Linv, T, alpha, z;
+  DevBuf Wh, Wl;        // fp16 planes Npad×Npad (TC mode)
+  DevBuf scal;          // device scalars, see ScalIdx
+  DevBuf info;          // int32: potrf info
+  DevBuf stage_X, stage_y, stage_Xc;  // H2D staging for host-pointer entry points
+  // ---- sweep workspace ---------------------------------------------------------------------
+  DevBuf Ks64;          // chunk × ldks fp64 (F64 mode)
+  DevBuf Ksh, Ksl;      // chunk × Npad fp16 planes (TC mode)
+  DevBuf mun;           // M (fp64 in F64 mode, fp32 in TC mode)
+  DevBuf part;          // chunk × n_jtiles partial Σv² (fp64) — F64 mode
+  DevBuf varn;          // M (same dtype as mun)
+  DevBuf blockbest;     // per-block argmax partials
+  DevBuf best;          // one kbo_best for suggest_host
+  kbo_timings tim{};
+  cudaEvent_t ev[8] = {};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_var, ev_cross, ev_acq;
+  size_t ev_var_used = 0, ev_cross_used = 0, ev_acq_used = 0;
+  int launches = 0;
+  bool time_kernels = false;
+};
+
+enum ScalIdx { S_YMEAN = 0, S_YSTD = 1, S_YOPT = 2, S_LML = 3, S_LOGDET = 4, S_QUAD = 5, S_COUNT = 8 };
+
+#define KBO_FAIL(h, code, ...)                         \
+  do {                                                 \
+    char _b[512];                                      \
+    snprintf(_b, sizeof _b, __VA_ARGS__);              \
+    (h)->err = _b;                                     \
+    return (code);                                     \
+  } while (0)
+
+#define KBO_CUDA(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      KBO_FAIL(h, KBO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define KBO_LAUNCH_CHECK(h)                                                                        \
+  do {                                                                                             \
+    (h)->launches++;                                                                               \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess)                                                                         \
+      KBO_FAIL(h, KBO_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int kbo_reserve(kbo_handle* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return KBO_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) KBO_FAIL(h, KBO_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  b.cap = bytes;
+  return KBO_OK;
+}
+#define KBO_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != KBO_OK) return _r; \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- fit.cu ------------------------------------------------------------------------------------
+int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double amp, double noise, double* K, int ldk,
+               cudaStream_t s);
+int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s);
+int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int ldw, cudaStream_t s);
+int kbo_i_zero_upper(kbo_handle* h, double* A, int N, int lda, cudaStream_t s);
+int kbo_i_fit(kbo_handle* h, const double* X_dev, const double* y_dev, int N, int D, const kbo_params* p, cudaStream_t s);
+// ---- sweep.cu ----------------------------------------------------------------------------------
+int kbo_i_sweep(kbo_handle* h, const void* Xc_dev, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out,
+                double* acq_out, kbo_best* best_dev, cudaStream_t s);
+int kbo_i_acq_argmax_f32(kbo_handle* h, const float* mu_n, const float* var_n, int64_t M, int64_t goff, int acq, double y_mean,
+                         double y_std, double y_opt, double xi, double kappa, double amp, float* acq_out, kbo_best* best_dev,
+                         cudaStream_t s);
+// ---- tc_var.cu ---------------------------------------------------------------------------------
+// var_n[m] = amp − Σ_j (Σ_k K*[m,k] W[j,k])²  for the rows of one chunk, on tcgen05 tensor cores.
+int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl,
+                      int Npad, double w_scale_inv, double amp, float* var_n_out, int k_span, cudaStream_t s);
+int kbo_i_tc_selftest(kbo_handle* h);

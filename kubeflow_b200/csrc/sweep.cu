@@ -1,0 +1,448 @@
+// ask(): predict(return_std=True) + acquisition + first-index argmax over the candidate grid.
+//   $SK/_gpr.py:446 K* = k(Xc,X) | :447-450 mean | :460 V = L⁻¹K*ᵀ (here V = K*·Wᵀ, W = L⁻¹) | :480-500 variance
+//   skopt.acquisition.gaussian_ei / gaussian_lcb / gaussian_pi ; Optimizer._tell: X_cand[np.argmin(values)]
+// Per candidate chunk:  cross_mean_kernel (FP64: K*, μ = K*·alpha)  →  variance contraction (FP64 SIMT GEMM with a
+// fused Σv² epilogue, or the tcgen05 kernel in tc_var.cu)  →  once per sweep: acquisition + argmax.
+#include "kbo_internal.cuh"
+#include "dgemm.cuh"
+
+__device__ __forceinline__ double kbo_kernel_eval2(double d2, int kind) {
+  d2 = d2 < 0.0 ? 0.0 : d2;
+  if (kind == KBO_KERNEL_RBF) return exp(-0.5 * d2);
+  const double s = sqrt(5.0 * d2);
+  return (1.0 + s + s * s * (1.0 / 3.0)) * exp(-s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K* tile = 64 candidates × 64 trials per step, the CTA walks all trial tiles so μ needs no atomics.
+// MODE 0: K* written as fp64 (chunk × ldks).  MODE 1: K* written as fp16 hi/lo planes (chunk_pad × Npad),
+// hi = fp16(k), lo = fp16(k − hi): |k − hi − lo| ≤ 2⁻²⁴ for k ∈ [0, amp≈1].
+template <typename XT, typename MT, int MODE>
+__global__ void __launch_bounds__(256)
+cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* __restrict__ inv_ls, int n_ls,
+                  const double* __restrict__ Xs, const double* __restrict__ nx, int N, const double* __restrict__ alpha, int kind,
+                  double amp, double* __restrict__ Ks64, int ldks, __half* __restrict__ Ksh, __half* __restrict__ Ksl, int Npad,
+                  MT* __restrict__ mun) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int Dp = (D + 15) & ~15;
+  double* As = reinterpret_cast<double*>(smraw);  // [Dp][66]
+  double* Bs = As + (size_t)Dp * 66;              // [16][66]
+  double* nc = Bs + 16 * 66;                      // [64]
+  double* nxs = nc + 64;                          // [64]
+  double* als = nxs + 64;                         // [64]
+  __half* hs = reinterpret_cast<__half*>(als + 64);  // [64][72] (MODE 1)
+  __half* ls = hs + 64 * 72;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * 64;
+
+  for (int e = tid; e < 64 * Dp; e += 256) {
+    const int r = e / Dp, d = e % Dp;
+    double v = 0.0;
+    if (m0 + r < rows && d < D) v = (double)Xc[(m0 + r) * D + d] * inv_ls[n_ls == 1 ? 0 : d];
+    As[d * 66 + r] = v;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    double s = 0.0;
+    for (int d = 0; d < D; d++) s = fma(As[d * 66 + tid], As[d * 66 + tid], s);
+    nc[tid] = s;
+  }
+  double musum[4] = {0.0, 0.0, 0.0, 0.0};
+  const int n_end = (MODE == 1) ? Npad : ((N + 63) & ~63);
+  for (int n0 = 0; n0 < n_end; n0 += 64) {
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    if (n0 < N) {
+      if (tid < 64) {
+        const bool ok = n0 + tid < N;
+        nxs[tid] = ok ? nx[n0 + tid] : 0.0;
+        als[tid] = ok ? alpha[n0 + tid] : 0.0;
+      }
+      for (int d0 = 0; d0 < D; d0 += 16) {
+        const int d = tid & 15;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int r = (tid >> 4) + 16 * i;
+          Bs[d * 66 + r] = (n0 + r < N && d0 + d < D) ? Xs[(size_t)(n0 + r) * D + d0 + d] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int dd = 0; dd < 16; dd++) {
+          double a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) a[i] = As[(d0 + dd) * 66 + ty + 16 * i];
+#pragma unroll
+          for (int j = 0; j < 4; j++) b[j] = Bs[dd * 66 + tx + 16 * j];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = ty + 16 * i;
+      const bool rok = m0 + r < rows;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = tx + 16 * j;
+        double kv = 0.0;
+        if (rok && n0 + c < N) {
+          const double d2 = nc[r] + nxs[c] - 2.0 * acc[i][j];
+          kv = amp * kbo_kernel_eval2(d2, kind);
+          musum[i] = fma(kv, als[c], musum[i]);
+        }
+        if (MODE == 0) {
+          if (rok && n0 + c < N) Ks64[(size_t)(m0 + r) * ldks + n0 + c] = kv;
+        } else {
+          const __half hi = __double2half(kv);
+          hs[r * 72 + c] = hi;
+          ls[r * 72 + c] = __double2half(kv - (double)__half2float(hi));
+        }
+      }
+    }
+    if (MODE == 1) {
+      __syncthreads();
+      // 64 rows × 128 B per plane, 16 B per thread-store: fully coalesced rows
+      for (int e = tid; e < 64 * 8; e += 256) {
+        const int r = e >> 3, sgm = e & 7;
+        const size_t g = (size_t)(m0 + r) * Npad + n0 + sgm * 8;
+        *reinterpret_cast<uint4*>(Ksh + g) = *reinterpret_cast<const uint4*>(hs + r * 72 + sgm * 8);
+        *reinterpret_cast<uint4*>(Ksl + g) = *reinterpret_cast<const uint4*>(ls + r * 72 + sgm * 8);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double s = musum[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int64_t gm = m0 + ty + 16 * i;
+    if (tx == 0 && gm < rows) mun[gm] = (MT)s;
+  }
+}
+
+__global__ void var_from_parts_kernel(const double* __restrict__ part, int64_t rows, int njt, double amp, double* __restrict__ varn) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  double s = 0.0;
+  for (int j = 0; j < njt; j++) s += part[m * njt + j];
+  varn[m] = amp - s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Acquisition + argmax.  T = double (checker precision) or float (8 B/candidate in, the HBM-bound pass).
+struct BlockBest {
+  double v;
+  long long i;
+};
+__device__ __forceinline__ bool better(double v, long long i, double bv, long long bi) { return v > bv || (v == bv && i < bi); }
+
+template <typename T>
+__device__ __forceinline__ T acq_value(T mun, T varn, int acq, T ymean, T ystd, T yopt, T xi, T kappa, T* mu_o, T* sd_o) {
+  const T var = varn > (T)0 ? varn : (T)0;  // $SK/_gpr.py:485-491
+  const T mu = ystd * mun + ymean;          // :450
+  const T sd = sqrt(var * ystd * ystd);     // :494,:500
+  *mu_o = mu;
+  *sd_o = sd;
+  if (acq == KBO_ACQ_LCB) return -(mu - kappa * sd);
+  if (!(sd > (T)0)) return (T)0;
+  const T imp = yopt - xi - mu;
+  const T z = imp / sd;
+  const T cdf = (T)0.5 * erfc(-z * (T)0.70710678118654752440);
+  if (acq == KBO_ACQ_PI) return cdf;
+  const T pdf = exp((T)-0.5 * z * z) * (T)0.39894228040143267794;
+  return imp * cdf + sd * pdf;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int64_t goff, int acq, double ymean, double ystd,
+           double yopt, const double* __restrict__ scal_dev, double xi, double kappa, double* __restrict__ mu_out,
+           double* __restrict__ std_out, double* __restrict__ acq_out, float* __restrict__ acq_out32,
+           BlockBest* __restrict__ partial) {
+  if (scal_dev) {  // composed path: y statistics stay on the device, no host round trip
+    ymean = scal_dev[S_YMEAN];
+    ystd = scal_dev[S_YSTD];
+    yopt = scal_dev[S_YOPT];
+  }
+  double bv = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  const T ym = (T)ymean, ys = (T)ystd, yo = (T)yopt, x = (T)xi, kp = (T)kappa;
+  const int64_t stride = (int64_t)gridDim.x * 256 * 4;
+  for (int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; base < M; base += stride) {
+    T m4[4], v4[4];
+    const bool full = base + 3 < M;
+    if (full && sizeof(T) == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(mun + base);
+      const float4 b = *reinterpret_cast<const float4*>(varn + base);
+      m4[0] = a.x; m4[1] = a.y; m4[2] = a.z; m4[3] = a.w;
+      v4[0] = b.x; v4[1] = b.y; v4[2] = b.z; v4[3] = b.w;
+    } else if (full) {
+      const double2 a0 = *reinterpret_cast<const double2*>(mun + base), a1 = *reinterpret_cast<const double2*>(mun + base + 2);
+      const double2 b0 = *reinterpret_cast<const double2*>(varn + base), b1 = *reinterpret_cast<const double2*>(varn + base + 2);
+      m4[0] = a0.x; m4[1] = a0.y; m4[2] = a1.x; m4[3] = a1.y;
+      v4[0] = b0.x; v4[1] = b0.y; v4[2] = b1.x; v4[3] = b1.y;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        m4[q] = base + q < M ? mun[base + q] : (T)0;
+        v4[q] = base + q < M ? varn[base + q] : (T)0;
+      }
+    }
+    float o4[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      T mu, sd;
+      const T a = acq_value<T>(m4[q], v4[q], acq, ym, ys, yo, x, kp, &mu, &sd);
+      o4[q] = (float)a;
+      if (base + q < M) {
+        if (mu_out) mu_out[base + q] = (double)mu;
+        if (std_out) std_out[base + q] = (double)sd;
+        if (acq_out) acq_out[base + q] = (double)a;
+        const double av = (a == a) ? (double)a : -INFINITY;  // NaN never wins
+        if (better(av, goff + base + q, bv, bi)) {
+          bv = av;
+          bi = goff + base + q;
+        }
+      }
+    }
+    if (acq_out32) {
+      if (full) {
+        *reinterpret_cast<float4*>(acq_out32 + base) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      } else {
+        for (int q = 0; q < 4 && base + q < M; q++) acq_out32[base + q] = o4[q];
+      }
+    }
+  }
+  // warp-shuffle argmax (lowest index wins ties), then across the 8 warps through shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) {
+      bv = ov;
+      bi = oi;
+    }
+  }
+  __shared__ double sv[8];
+  __shared__ long long si[8];
+  if ((threadIdx.x & 31) == 0) {
+    sv[threadIdx.x >> 5] = bv;
+    si[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      if (better(sv[w], si[w], bv, bi)) {
+        bv = sv[w];
+        bi = si[w];
+      }
+    partial[blockIdx.x].v = bv;
+    partial[blockIdx.x].i = bi;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+argmax_final_kernel(const BlockBest* __restrict__ partial, int n, const T* __restrict__ mun, const T* __restrict__ varn, int64_t goff,
+                    int64_t M, double ymean, double ystd, const double* __restrict__ scal_dev, kbo_best* __restrict__ best) {
+  if (scal_dev) {
+    ymean = scal_dev[S_YMEAN];
+    ystd = scal_dev[S_YSTD];
+  }
+  __shared__ double sv[1024];
+  __shared__ long long si[1024];
+  double bv = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (int e = threadIdx.x; e < n; e += 1024)
+    if (better(partial[e].v, partial[e].i, bv, bi)) {
+      bv = partial[e].v;
+      bi = partial[e].i;
+    }
+  sv[threadIdx.x] = bv;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o && better(sv[threadIdx.x + o], si[threadIdx.x + o], sv[threadIdx.x], si[threadIdx.x])) {
+      sv[threadIdx.x] = sv[threadIdx.x + o];
+      si[threadIdx.x] = si[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    best->value = sv[0];
+    best->index = si[0];
+    const int64_t l = si[0] - goff;
+    if (l >= 0 && l < M) {
+      const double var = (double)varn[l] > 0.0 ? (double)varn[l] : 0.0;
+      best->mu = ystd * (double)mun[l] + ymean;
+      best->std = sqrt(var * ystd * ystd);
+    } else {
+      best->mu = 0.0;
+      best->std = 0.0;
+    }
+  }
+}
+
+static int acq_grid(kbo_handle* h, int64_t M) {
+  int64_t g = (M + 1023) / 1024;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <typename T>
+static int launch_acq(kbo_handle* h, const T* mun, const T* varn, int64_t M, int64_t goff, int acq, double ymean, double ystd, double yopt,
+                      const double* scal_dev, double xi, double kappa, double* mu_out, double* std_out, double* acq_out, float* acq_out32, kbo_best* best_dev,
+                      cudaStream_t s) {
+  const int g = acq_grid(h, M);
+  KBO_TRY(kbo_reserve(h, h->blockbest, sizeof(BlockBest) * (size_t)h->sm_count * 8));
+  acq_kernel<T><<<g, 256, 0, s>>>(mun, varn, M, goff, acq, ymean, ystd, yopt, scal_dev, xi, kappa, mu_out, std_out, acq_out, acq_out32,
+                                  (BlockBest*)h->blockbest.p);
+  KBO_LAUNCH_CHECK(h);
+  argmax_final_kernel<T><<<1, 1024, 0, s>>>((const BlockBest*)h->blockbest.p, g, mun, varn, goff, M, ymean, ystd, scal_dev, best_dev);
+  KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
+
+int kbo_i_acq_argmax_f32(kbo_handle* h, const float* mu_n, const float* var_n, int64_t M, int64_t goff, int acq, double y_mean,
+                         double y_std, double y_opt, double xi, double kappa, double amp, float* acq_out, kbo_best* best_dev,
+                         cudaStream_t s) {
+  (void)amp;
+  if (M < 1) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_acq_argmax: M must be >= 1");
+  if (((uintptr_t)mu_n | (uintptr_t)var_n | (uintptr_t)acq_out) & 15) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_acq_argmax: pointers must be 16-byte aligned");
+  return launch_acq<float>(h, mu_n, var_n, M, goff, acq, y_mean, y_std, y_opt, nullptr, xi, kappa, nullptr, nullptr, nullptr, acq_out, best_dev, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+static size_t cross_smem_bytes(int D, int mode) {
+  const int Dp = (D + 15) & ~15;
+  size_t b = sizeof(double) * ((size_t)Dp * 66 + 16 * 66 + 64 * 3);
+  if (mode == 1) b += sizeof(__half) * 2 * 64 * 72;
+  return b;
+}
+
+template <typename XT, typename MT, int MODE>
+static int launch_cross(kbo_handle* h, const XT* Xc, int64_t rows, int64_t rows_grid, double* Ks64, int ldks, __half* Ksh, __half* Ksl, MT* mun,
+                        cudaStream_t s) {
+  const size_t smem = cross_smem_bytes(h->D, MODE);
+  KBO_CUDA(h, cudaFuncSetAttribute(cross_mean_kernel<XT, MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cross_mean_kernel<XT, MT, MODE><<<(unsigned)((rows_grid + 63) / 64), 256, smem, s>>>(
+      Xc, rows, h->D, (const double*)h->d_inv_ls.p, (int)h->inv_ls.size(), (const double*)h->Xs.p, (const double*)h->nx.p, h->N,
+      (const double*)h->alpha.p, h->prm.kernel, h->prm.amplitude, Ks64, ldks, Ksh, Ksl, h->Npad, mun);
+  KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
+
+static cudaEvent_t* ev_pair(kbo_handle* h, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, size_t& used) {
+  if (used == v.size()) {
+    std::pair<cudaEvent_t, cudaEvent_t> p;
+    cudaEventCreate(&p.first);
+    cudaEventCreate(&p.second);
+    v.push_back(p);
+  }
+  return &v[used++].first;
+}
+#define KBO_TIME_BEGIN(vec, used)                      \
+  cudaEvent_t* _ev = nullptr;                          \
+  if (h->time_kernels) {                               \
+    _ev = ev_pair(h, h->vec, h->used);                 \
+    cudaEventRecord(_ev[0], s);                        \
+  }
+#define KBO_TIME_END()                                 \
+  if (_ev) cudaEventRecord((&_ev[0])[1], s);
+
+int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out, double* acq_out,
+                kbo_best* best_dev, cudaStream_t s) {
+  if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_sweep: call kbo_fit first");
+  if (M < 1) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: M must be >= 1 (got %lld)", (long long)M);
+  if (xc_dtype != KBO_F64 && xc_dtype != KBO_F32) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: xc_dtype must be KBO_F64 or KBO_F32");
+  if (h->D > 256) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: D <= 256 supported (got %d)", h->D);
+  const int N = h->N, D = h->D, ld = h->ld, Npad = h->Npad;
+  const bool tc = h->prm.var_mode == KBO_VAR_TC_F16X3;
+  const size_t esz = xc_dtype == KBO_F64 ? 8 : 4;
+  const double* scal = (const double*)h->scal.p;
+  int64_t chunk;
+  if (tc) {
+    chunk = (int64_t)(h->scratch_limit / ((size_t)Npad * 4)) / 128 * 128;
+    if (chunk < 128) chunk = 128;
+    if (chunk > round_up64(M, 128)) chunk = round_up64(M, 128);
+    KBO_TRY(kbo_reserve(h, h->Ksh, sizeof(__half) * (size_t)chunk * Npad));
+    KBO_TRY(kbo_reserve(h, h->Ksl, sizeof(__half) * (size_t)chunk * Npad));
+    KBO_TRY(kbo_reserve(h, h->mun, sizeof(float) * (size_t)round_up64(M, 128)));
+    KBO_TRY(kbo_reserve(h, h->varn, sizeof(float) * (size_t)round_up64(M, 128)));
+  } else {
+    chunk = (int64_t)(h->scratch_limit / ((size_t)ld * 8)) / 64 * 64;
+    if (chunk < 64) chunk = 64;
+    if (chunk > round_up64(M, 64)) chunk = round_up64(M, 64);
+    KBO_TRY(kbo_reserve(h, h->Ks64, sizeof(double) * (size_t)chunk * ld));
+    KBO_TRY(kbo_reserve(h, h->part, sizeof(double) * (size_t)chunk * ((N + 63) / 64)));
+    KBO_TRY(kbo_reserve(h, h->mun, sizeof(double) * (size_t)M));
+    KBO_TRY(kbo_reserve(h, h->varn, sizeof(double) * (size_t)M));
+  }
+  h->tim.chunks = 0;
+  for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+    const int64_t rows = (M - c0 < chunk) ? (M - c0) : chunk;
+    const unsigned char* xc = (const unsigned char*)Xc + (size_t)c0 * D * esz;
+    h->tim.chunks++;
+    if (tc) {
+      const int64_t rows_pad = round_up64(rows, 128);
+      float* mun = (float*)h->mun.p + c0;
+      {
+        KBO_TIME_BEGIN(ev_cross, ev_cross_used);
+        if (xc_dtype == KBO_F64)
+          KBO_TRY((launch_cross<double, float, 1>(h, (const double*)xc, rows, rows_pad, nullptr, 0, (__half*)h->Ksh.p, (__half*)h->Ksl.p, mun, s)));
+        else
+          KBO_TRY((launch_cross<float, float, 1>(h, (const float*)xc, rows, rows_pad, nullptr, 0, (__half*)h->Ksh.p, (__half*)h->Ksl.p, mun, s)));
+        KBO_TIME_END();
+      }
+      {
+        KBO_TIME_BEGIN(ev_var, ev_var_used);
+        KBO_TRY(kbo_i_tc_variance(h, (const __half*)h->Ksh.p, (const __half*)h->Ksl.p, rows_pad, (const __half*)h->Wh.p, (const __half*)h->Wl.p,
+                                  Npad, 0.0, h->prm.amplitude, (float*)h->varn.p + c0, h->prm.tc_k_span, s));
+        KBO_TIME_END();
+      }
+    } else {
+      double* mun = (double*)h->mun.p + c0;
+      {
+        KBO_TIME_BEGIN(ev_cross, ev_cross_used);
+        if (xc_dtype == KBO_F64)
+          KBO_TRY((launch_cross<double, double, 0>(h, (const double*)xc, rows, rows, (double*)h->Ks64.p, ld, nullptr, nullptr, mun, s)));
+        else
+          KBO_TRY((launch_cross<float, double, 0>(h, (const float*)xc, rows, rows, (double*)h->Ks64.p, ld, nullptr, nullptr, mun, s)));
+        KBO_TIME_END();
+      }
+      {
+        KBO_TIME_BEGIN(ev_var, ev_var_used);
+        const int njt = (N + 63) / 64;
+        dgemm64_launch<true, EPI_ROWSUMSQ>(s, (int)rows, N, N, (const double*)h->Ks64.p, ld, (const double*)h->W.p, ld, (double*)h->part.p, njt,
+                                           1.0, 0.0, KM_UPTO_N, 0, TS_NONE);
+        KBO_LAUNCH_CHECK(h);
+        var_from_parts_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>((const double*)h->part.p, rows, njt, h->prm.amplitude,
+                                                                            (double*)h->varn.p + c0);
+        KBO_LAUNCH_CHECK(h);
+        KBO_TIME_END();
+      }
+    }
+  }
+  // acquisition over the whole grid; y statistics are read from the fit's device scalars (no host sync)
+  {
+    KBO_TIME_BEGIN(ev_acq, ev_acq_used);
+    if (tc)
+      KBO_TRY(launch_acq<float>(h, (const float*)h->mun.p, (const float*)h->varn.p, M, goff, h->prm.acq, 0.0, 1.0, 0.0, scal, h->prm.xi,
+                                h->prm.kappa, mu_out, std_out, acq_out, nullptr, best_dev, s));
+    else
+      KBO_TRY(launch_acq<double>(h, (const double*)h->mun.p, (const double*)h->varn.p, M, goff, h->prm.acq, 0.0, 1.0, 0.0, scal, h->prm.xi,
+                                 h->prm.kappa, mu_out, std_out, acq_out, nullptr, best_dev, s));
+    KBO_TIME_END();
+  }
+  return KBO_OK;
+}

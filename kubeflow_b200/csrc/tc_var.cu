@@ -1,0 +1,336 @@
+// Variance contraction on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   var_n[m] = amp − Σ_j v[m,j]²,   v[m,j] = Σ_{k≤j} K*[m,k]·W[j,k]      ($SK/_gpr.py:460, :480-481 with W = L⁻¹)
+//
+// This is the M·N² term that sets the suggestion rate.  Operands are fp16 hi/lo splits
+// (x ≈ hi + lo, |x − hi − lo| ≤ 2⁻²²|x|) and each product is three MMAs  Ah·Bh + Ah·Bl + Al·Bh  into one
+// fp32 TMEM accumulator: bf16/fp16 single-pass moves σ² by 1e-2 and bf16×3 by 1e-5..1e-4 (measured,
+// DESIGN.md §numerics) — fp16×3 stays at ~3e-7.
+//
+// CTA = 128 candidate rows (TMEM lanes) × all j-tiles of 256 trial columns, walked in order; for j-tile t only
+// k < 256(t+1) is issued (W is lower triangular).  K is consumed in 32-wide chunks, 4-stage TMA→smem ring:
+//   warp 0     TMA producer (A hi/lo 128×32, B hi/lo 256×32 per stage, SWIZZLE_64B, mbarrier expect_tx)
+//   warp 1     MMA issuer  (single thread, tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16)
+//   warps 2-9  epilogue: TMEM → registers every `k_span` trials (two 256-column TMEM buffers ping-pong) and
+//              accumulate in fp32 registers with round-to-nearest — bounds the length of the in-TMEM
+//              accumulation chain — then Σv² per row at the end of each j-tile.
+#include <cuda.h>
+
+#include "kbo_internal.cuh"
+
+#define TC_BM 128
+#define TC_BN 256
+#define TC_BK 32
+#define TC_STAGES 4
+#define TC_A_BYTES (TC_BM * TC_BK * 2)        // 8 KB per plane
+#define TC_B_BYTES (TC_BN * TC_BK * 2)        // 16 KB per plane
+#define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)  // 48 KB
+#define TC_THREADS 320
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("kbo tc_variance: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
+// rows are 64 B (32 fp16), 8-row groups 512 B apart (SBO), LBO unused for swizzled K-major (canonical value 1).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                          // LBO            [16,30)
+  d |= (uint64_t)(512 >> 4) << 32;                 // SBO            [32,46)
+  d |= (uint64_t)1 << 46;                          // version        [46,48)
+  d |= (uint64_t)4 << 61;                          // SWIZZLE_64B    [61,64)
+  return d;
+}
+// kind::f16 instruction descriptor: D=F32, A=B=F16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f16_m128_n256() {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+struct TcSmem {
+  uint64_t full[TC_STAGES];
+  uint64_t empty[TC_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_variance_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int n_jtiles,
+                   int span_chunks, const double* __restrict__ w_scale /* [0]=2^s, [1]=2^-s */, double amp,
+                   float* __restrict__ var_out, double* __restrict__ sumsq_out /* optional raw Σv² (tests) */) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  // SWIZZLE_64B tiles need 512 B alignment of each plane; keep the whole ring 1024 B aligned.
+  unsigned char* ring = (unsigned char*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  TcSmem* S = (TcSmem*)(ring + TC_STAGES * TC_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+    for (int i = 0; i < TC_STAGES; i++) {
+      mbar_init(smem_u32(&S->full[i]), 1);
+      mbar_init(smem_u32(&S->empty[i]), 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(smem_u32(&S->tmem_full[i]), 1);
+      mbar_init(smem_u32(&S->tmem_empty[i]), 8);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // the MMA warp owns the TMEM allocation: all 512 columns = two 128×256 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S->tmem_base;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ===========================================
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int jt = 0; jt < n_jtiles; jt++) {
+        const int nch = (jt + 1) * (TC_BN / TC_BK);
+        for (int ch = 0; ch < nch; ch++, c++) {
+          const uint32_t st = c % TC_STAGES, use = c / TC_STAGES;
+          mbar_wait(smem_u32(&S->empty[st]), (use & 1) ^ 1, 1);
+          const uint32_t bar = smem_u32(&S->full[st]);
+          mbar_expect_tx(bar, TC_STAGE_BYTES);
+          const uint32_t base = smem_u32(ring + st * TC_STAGE_BYTES);
+          const int k0 = ch * TC_BK;
+          tma_load_2d(base, &tmAh, bar, k0, m0);
+          tma_load_2d(base + TC_A_BYTES, &tmAl, bar, k0, m0);
+          tma_load_2d(base + 2 * TC_A_BYTES, &tmBh, bar, k0, jt * TC_BN);
+          tma_load_2d(base + 2 * TC_A_BYTES + TC_B_BYTES, &tmBl, bar, k0, jt * TC_BN);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =============================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16_m128_n256();
+      uint32_t c = 0, span = 0;
+      for (int jt = 0; jt < n_jtiles; jt++) {
+        const int nch = (jt + 1) * (TC_BN / TC_BK);
+        for (int ch0 = 0; ch0 < nch; ch0 += span_chunks, span++) {
+          const uint32_t buf = span & 1, use = span >> 1;
+          mbar_wait(smem_u32(&S->tmem_empty[buf]), (use & 1) ^ 1, 2);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * TC_BN;
+          const int che = min(nch, ch0 + span_chunks);
+          for (int ch = ch0; ch < che; ch++, c++) {
+            const uint32_t st = c % TC_STAGES, suse = c / TC_STAGES;
+            mbar_wait(smem_u32(&S->full[st]), suse & 1, 3);
+            tc_fence_after();
+            const uint32_t base = smem_u32(ring + st * TC_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; k++) {
+              const uint32_t koff = k * 32;  // 16 fp16 = 32 B inside the 64 B swizzle row
+              const uint64_t ah = umma_desc_sw64(base + koff);
+              const uint64_t al = umma_desc_sw64(base + TC_A_BYTES + koff);
+              const uint64_t bh = umma_desc_sw64(base + 2 * TC_A_BYTES + koff);
+              const uint64_t bl = umma_desc_sw64(base + 2 * TC_A_BYTES + TC_B_BYTES + koff);
+              umma_f16(d_tmem, al, bh, idesc, (ch > ch0 || k > 0) ? 1u : 0u);  // small terms first
+              umma_f16(d_tmem, ah, bl, idesc, 1u);
+              umma_f16(d_tmem, ah, bh, idesc, 1u);
+            }
+            umma_commit(smem_u32(&S->empty[st]));  // frees the smem stage when these MMAs retire
+          }
+          umma_commit(smem_u32(&S->tmem_full[buf]));  // accumulator span complete → epilogue
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue warps =========================================
+    const int ew = warp - 2;             // 0..7
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;            // which 128 of the 256 accumulator columns
+    const int row = quarter * 32 + lane; // candidate row within the CTA tile (= TMEM lane)
+    float acc[128];
+#pragma unroll
+    for (int i = 0; i < 128; i++) acc[i] = 0.f;
+    double rowacc = 0.0;
+    uint32_t span = 0;
+    for (int jt = 0; jt < n_jtiles; jt++) {
+      const int nch = (jt + 1) * (TC_BN / TC_BK);
+      for (int ch0 = 0; ch0 < nch; ch0 += span_chunks, span++) {
+        const uint32_t buf = span & 1, use = span >> 1;
+        mbar_wait(smem_u32(&S->tmem_full[buf]), use & 1, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC_BN + half * 128;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          uint32_t r[32];
+          tmem_ld32(taddr + p * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) acc[p * 32 + i] += __uint_as_float(r[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&S->tmem_empty[buf]));
+      }
+      // j-tile complete: Σ v² over this thread's 128 columns (4 partial sums, then fp64 across tiles)
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        s0 = fmaf(acc[i], acc[i], s0);
+        s1 = fmaf(acc[i + 1], acc[i + 1], s1);
+        s2 = fmaf(acc[i + 2], acc[i + 2], s2);
+        s3 = fmaf(acc[i + 3], acc[i + 3], s3);
+        acc[i] = acc[i + 1] = acc[i + 2] = acc[i + 3] = 0.f;
+      }
+      rowacc += (double)((s0 + s1) + (s2 + s3));
+    }
+    const double sc = w_scale[1];
+    const double total_half = rowacc * sc * sc;
+    // combine the two column halves through shared memory (fixed order: half 0 + half 1)
+    __shared__ double halfsum[TC_BM];
+    if (half == 1) halfsum[row] = total_half;
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+    if (half == 0) {
+      const double tot = total_half + halfsum[row];
+      var_out[m0 + row] = (float)(amp - tot);
+      if (sumsq_out) sumsq_out[m0 + row] = tot;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_map(kbo_handle* h, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    KBO_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) KBO_FAIL(h, KBO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    fn = (PFN_encodeTiled)p;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {TC_BK, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) KBO_FAIL(h, KBO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return KBO_OK;
+}
+
+int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl, int Npad,
+              const double* w_scale_dev, double amp, float* var_out, double* sumsq_out, int k_span, cudaStream_t s) {
+  if (rows % TC_BM != 0 || Npad % TC_BN != 0) KBO_FAIL(h, KBO_ERR_INVALID, "tc_variance: rows %% 128 and Npad %% 256 must be 0");
+  if (k_span <= 0) k_span = 1024;
+  int span_chunks = k_span / TC_BK;
+  if (span_chunks < 1) span_chunks = 1;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  KBO_TRY(encode_map(h, &tmAh, Ksh, (uint64_t)Npad, (uint64_t)rows, TC_BM));
+  KBO_TRY(encode_map(h, &tmAl, Ksl, (uint64_t)Npad, (uint64_t)rows, TC_BM));
+  KBO_TRY(encode_map(h, &tmBh, Wh, (uint64_t)Npad, (uint64_t)Npad, TC_BN));
+  KBO_TRY(encode_map(h, &tmBl, Wl, (uint64_t)Npad, (uint64_t)Npad, TC_BN));
+  static bool attr = false;
+  if (!attr) {
+    KBO_CUDA(h, cudaFuncSetAttribute(tc_variance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr = true;
+  }
+  tc_variance_kernel<<<(unsigned)(rows / TC_BM), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh, tmAl, tmBh, tmBl, Npad / TC_BN, span_chunks, w_scale_dev,
+                                                                                amp, var_out, sumsq_out);
+  KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
+
+}  // namespace
+
+int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl, int Npad,
+                      double /*unused*/, double amp, float* var_n_out, int k_span, cudaStream_t s) {
+  return tc_launch(h, Ksh, Ksl, rows, Wh, Wl, Npad, (const double*)h->scal.p + 6, amp, var_n_out, nullptr, k_span, s);
+}
+
+// Raw entry for the kernel-level parity test: caller supplies fp16 planes and the scale pair on the device.
+extern "C" int kbo_tc_variance_raw(kbo_handle* h, const void* Ksh, const void* Ksl, int64_t rows, const void* Wh, const void* Wl, int32_t Npad,
+                                   const double* w_scale_dev, double amp, float* var_out, double* sumsq_out, int32_t k_span, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  return tc_launch(h, (const __half*)Ksh, (const __half*)Ksl, rows, (const __half*)Wh, (const __half*)Wl, Npad, w_scale_dev, amp, var_out,
+                   sumsq_out, k_span, (cudaStream_t)stream);
+}
