@@ -55,7 +55,8 @@ typedef enum kbo_acq_kind {
 
 typedef enum kbo_var_mode {
   KBO_VAR_F64 = 0,     /* variance contraction V = K* W^T on the FP64 SIMT pipe (checker precision) */
-  KBO_VAR_TC_F16X3 = 1 /* tcgen05 tensor cores, fp16 hi/lo split (3 MMAs per product), fp32 accum  */
+  KBO_VAR_TC_F16X3 = 1, /* tcgen05 tensor cores, fp16 hi/lo split (3 MMAs per product), fp32 accum */
+  KBO_VAR_AUTO = 2      /* FP64 while M·N² <= 2e11 (a few ms of FP64 pipe), tensor cores above that    */
 } kbo_var_mode;
 
 typedef enum kbo_dtype { KBO_F64 = 0, KBO_F32 = 1 } kbo_dtype;

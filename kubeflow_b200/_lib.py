@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libkbo.so")
 KBO_OK, KBO_ERR_INVALID, KBO_ERR_CUDA, KBO_ERR_NOT_PD, KBO_ERR_NOMEM, KBO_ERR_STATE = 0, -1, -2, -3, -4, -5
 KERNELS = {"rbf": 0, "matern52": 1}
 ACQS = {"ei": 0, "lcb": 1, "pi": 2}
-VAR_MODES = {"f64": 0, "tc": 1}
+VAR_MODES = {"f64": 0, "tc": 1, "auto": 2}
 KBO_F64, KBO_F32 = 0, 1
 
 

@@ -436,10 +436,12 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   if (p->n_length_scale != 1 && p->n_length_scale != D)
     KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: n_length_scale must be 1 or D=%d (got %d)", D, p->n_length_scale);
   if (!(p->noise >= 0.0) || !(p->amplitude > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: amplitude must be > 0 and noise >= 0");
+  if (p->var_mode < KBO_VAR_F64 || p->var_mode > KBO_VAR_AUTO) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: unknown var_mode %d", p->var_mode);
   if (p->kernel != KBO_KERNEL_RBF && p->kernel != KBO_KERNEL_MATERN52) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: unknown kernel %d", p->kernel);
   for (int d = 0; d < p->n_length_scale; d++)
     if (!(p->length_scale[d] > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: length_scale[%d] must be > 0", d);
   h->fitted = false;
+  h->have_planes = false;
   h->N = N;
   h->D = D;
   h->ld = round_up(N, 64);
@@ -474,7 +476,8 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   KBO_LAUNCH_CHECK(h);
   lml_kernel<<<1, 1024, 0, s>>>((const double*)h->K.p, N, ld, (const double*)h->yn.p, (const double*)h->alpha.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
-  if (p->var_mode == KBO_VAR_TC_F16X3) {
+  if (p->var_mode == KBO_VAR_TC_F16X3 || (p->var_mode == KBO_VAR_AUTO && N > 1024)) {
+    h->have_planes = true;
     const int Npad = h->Npad;
     KBO_TRY(kbo_reserve(h, h->Wh, sizeof(__half) * (size_t)Npad * Npad));
     KBO_TRY(kbo_reserve(h, h->Wl, sizeof(__half) * (size_t)Npad * Npad));

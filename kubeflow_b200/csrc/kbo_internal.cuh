@@ -24,6 +24,7 @@ struct kbo_handle {
 
   // ---- fit state -------------------------------------------------------------------------
   bool fitted = false;
+  bool have_planes = false;  // fp16 hi/lo planes of W built by the last fit
   int N = 0, D = 0, ld = 0;  // ld = leading dimension of L / W (multiple of 64)
   int Npad = 0;              // multiple of 256: extent of the fp16 W planes and of K* scratch rows
   kbo_params prm{};

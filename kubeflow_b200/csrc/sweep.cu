@@ -367,7 +367,8 @@ int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t 
   if (xc_dtype != KBO_F64 && xc_dtype != KBO_F32) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: xc_dtype must be KBO_F64 or KBO_F32");
   if (h->D > 256) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: D <= 256 supported (got %d)", h->D);
   const int N = h->N, D = h->D, ld = h->ld, Npad = h->Npad;
-  const bool tc = h->prm.var_mode == KBO_VAR_TC_F16X3;
+  const bool tc = h->prm.var_mode == KBO_VAR_TC_F16X3 ||
+                  (h->prm.var_mode == KBO_VAR_AUTO && h->have_planes && (double)M * h->N * h->N > 2e11);
   const size_t esz = xc_dtype == KBO_F64 ? 8 : 4;
   const double* scal = (const double*)h->scal.p;
   int64_t chunk;

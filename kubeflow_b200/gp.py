@@ -27,7 +27,7 @@ class Best:
 class GPEngine:
     def __init__(self, device: int = 0, *, kernel: str = "matern52", length_scale=1.0, amplitude: float = 1.0,
                  noise: float = 1e-10, acq: str = "ei", xi: float = 0.01, kappa: float = 1.96,
-                 normalize_y: bool = True, var_mode: str = "tc", tc_k_span: int = 0, scratch_limit: int | None = None):
+                 normalize_y: bool = True, var_mode: str = "auto", tc_k_span: int = 0, scratch_limit: int | None = None):
         if kernel not in L.KERNELS:
             raise ValueError(f"kernel must be one of {sorted(L.KERNELS)}, got {kernel!r}")
         if acq not in L.ACQS:
@@ -136,6 +136,8 @@ class GPEngine:
             M, D = Xc.shape
             ptr, on_host = Xc.ctypes.data, 1
             dt = L.KBO_F64 if Xc.dtype == np.float64 else L.KBO_F32
+        if self.N == 0:
+            raise L.KboError(L.KBO_ERR_STATE, "ask() before tell(): call tell(X, y) first")
         if D != self.D:
             raise ValueError(f"candidates have D={D}, fit had D={self.D}")
         mu = std = acq = None

@@ -1,0 +1,99 @@
+"""``Optimizer`` — the host-side mirror of ``skopt.Optimizer`` as Katib's skopt service drives it
+(upstream kubeflow/katib pkg/suggestion/v1beta1/skopt/base_service.py: ``tell(X, y)`` then ``ask()`` per
+requested assignment).  Differences, stated once:
+
+* θ is FIXED per request (length scales, amplitude, noise are settings), where skopt refits them by L-BFGS on the
+  log-marginal likelihood ($SK/_gpr.py:299-339) — bit-reproducing that optimiser is outside the 1e-5 contract
+  (SURVEY.md §7).  ``theta_grid`` > 1 picks the best of a small length-scale grid by the GPU-computed LML instead.
+* ``acq_optimizer`` is "sampling" over ``n_points`` candidates (skopt default 10 000; here 65 536 by default and
+  millions are cheap) — ``lbfgs`` polishing and ``gp_hedge`` are accepted by ValidateAlgorithmSettings and mapped to
+  sampling / EI.
+* ``ask(n_points=k)`` uses skopt's constant-liar "cl_min" strategy: k sequential asks with the lie y = min(y).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .space import Space
+
+
+class Optimizer:
+    def __init__(self, dimensions, base_estimator="GP", n_initial_points=10, acq_func="EI", acq_optimizer="sampling",
+                 random_state=None, *, n_points=65536, kernel="matern52", length_scale=None, amplitude=1.0, noise=1e-3, xi=0.01,
+                 kappa=1.96, var_mode="auto", theta_grid=1, device=0, engine=None):
+        if str(base_estimator).upper() != "GP":
+            raise ValueError("base_estimator must be GP (RF/ET/GBRT are not part of the GPU path)")
+        self.space = dimensions if isinstance(dimensions, Space) else Space(dimensions)
+        self.n_initial_points = int(n_initial_points)
+        acq = str(acq_func)
+        self.acq = {"EI": "ei", "LCB": "lcb", "PI": "pi", "gp_hedge": "ei", "EIps": "ei", "PIps": "pi"}.get(acq)
+        if self.acq is None:
+            raise ValueError(f"unknown acq_func {acq_func!r}")
+        if acq_optimizer not in ("auto", "sampling", "lbfgs"):
+            raise ValueError(f"unknown acq_optimizer {acq_optimizer!r}")
+        self.rng = np.random.default_rng(random_state)
+        self.n_points = int(n_points)
+        self.kernel, self.amplitude, self.noise, self.xi, self.kappa = kernel, amplitude, noise, xi, kappa
+        self.length_scale = length_scale
+        self.var_mode, self.theta_grid, self.device = var_mode, int(theta_grid), device
+        self.Xi, self.yi = [], []
+        self._engine = engine
+        self.last_best = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def tell(self, x, y):
+        if len(x) and not isinstance(x[0], (list, tuple)):
+            x, y = [x], [y]
+        if len(x) != len(y):
+            raise ValueError("x and y must have the same length")
+        self.Xi.extend([list(p) for p in x])
+        self.yi.extend([float(v) for v in y])
+
+    def _get_engine(self, ls):
+        from .gp import GPEngine
+        if self._engine is None:
+            self._engine = GPEngine(self.device, kernel=self.kernel, length_scale=ls, amplitude=self.amplitude, noise=self.noise,
+                                    acq=self.acq, xi=self.xi, kappa=self.kappa, var_mode=self.var_mode)
+        e = self._engine
+        e.kernel, e.acq, e.amplitude, e.noise, e.xi, e.kappa = self.kernel, self.acq, self.amplitude, self.noise, self.xi, self.kappa
+        e.length_scale = np.atleast_1d(np.asarray(ls, dtype=np.float64))
+        return e
+
+    def _default_ls(self):
+        return 0.3 * np.sqrt(self.space.transformed_n_dims) if self.length_scale is None else self.length_scale
+
+    def _ask_one(self, X, y):
+        if len(y) < max(self.n_initial_points, 1):
+            return self.space.inverse_transform(self.space.rvs_transformed(1, self.rng, np.float64))[0]
+        Xt = self.space.transform(X)
+        ya = np.asarray(y, dtype=np.float64)
+        base = np.atleast_1d(np.asarray(self._default_ls(), dtype=np.float64))
+        eng = self._get_engine(base)
+        if self.theta_grid > 1:   # choose ℓ-multiplier by GPU log-marginal likelihood
+            mults = np.geomspace(0.25, 4.0, self.theta_grid)
+            lmls = []
+            for m in mults:
+                eng.length_scale = base * m
+                eng.tell(Xt, ya)
+                try:
+                    lmls.append(eng.fit_info()["lml"])
+                except Exception:
+                    lmls.append(-np.inf)
+            eng.length_scale = base * mults[int(np.argmax(lmls))]
+        eng.tell(Xt, ya)
+        cand = self.space.rvs_transformed(self.n_points, self.rng, np.float32)
+        best = eng.ask(cand)
+        self.last_best = best
+        return self.space.inverse_transform(cand[best.index:best.index + 1].astype(np.float64))[0]
+
+    def ask(self, n_points=None):
+        if n_points is None:
+            return self._ask_one(self.Xi, self.yi)
+        X, y, out = list(self.Xi), list(self.yi), []
+        for _ in range(int(n_points)):
+            x = self._ask_one(X, y)
+            out.append(x)
+            if y:                      # constant liar, "cl_min"
+                X.append(x)
+                y.append(min(y))
+        return out

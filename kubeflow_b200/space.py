@@ -1,0 +1,104 @@
+"""Search-space transform: the ``skopt.space.Space(...).transform`` / ``inverse_transform`` pair with the
+"normalize" transformer skopt's GP optimizer uses: reals and integers map to [0,1],
+categoricals to one-hot columns (a two-category dimension takes ONE 0/1 column, as sklearn's LabelBinarizer does).
+Candidate sampling (``space.rvs``) happens directly in the transformed space."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class Real:
+    low: float
+    high: float
+    name: str = ""
+    width = 1
+
+    def to_unit(self, v):
+        return [(float(v) - self.low) / (self.high - self.low)]
+
+    def from_unit(self, u):
+        return float(min(max(self.low + float(u[0]) * (self.high - self.low), self.low), self.high))
+
+
+@dataclass
+class Integer:
+    low: int
+    high: int
+    name: str = ""
+    width = 1
+
+    def to_unit(self, v):
+        return [(int(v) - self.low) / (self.high - self.low)]
+
+    def from_unit(self, u):
+        return int(min(max(int(np.round(self.low + float(u[0]) * (self.high - self.low))), self.low), self.high))
+
+
+@dataclass
+class Categorical:
+    categories: list
+    name: str = ""
+
+    @property
+    def width(self):
+        return 1 if len(self.categories) == 2 else len(self.categories)
+
+    def to_unit(self, v):
+        i = self.categories.index(v)
+        if len(self.categories) == 2:
+            return [float(i)]
+        return [1.0 if j == i else 0.0 for j in range(len(self.categories))]
+
+    def from_unit(self, u):
+        if len(self.categories) == 2:
+            return self.categories[int(float(u[0]) >= 0.5)]
+        return self.categories[int(np.argmax(u))]
+
+
+class Space:
+    def __init__(self, dimensions):
+        self.dimensions = list(dimensions)
+        self.transformed_n_dims = sum(d.width for d in self.dimensions)
+
+    def transform(self, points) -> np.ndarray:
+        out = np.empty((len(points), self.transformed_n_dims), dtype=np.float64)
+        for r, p in enumerate(points):
+            row = []
+            for d, v in zip(self.dimensions, p):
+                row.extend(d.to_unit(v))
+            out[r] = row
+        return out
+
+    def inverse_transform(self, U) -> list:
+        U = np.atleast_2d(np.asarray(U, dtype=np.float64))
+        pts = []
+        for u in U:
+            c, p = 0, []
+            for d in self.dimensions:
+                p.append(d.from_unit(u[c:c + d.width]))
+                c += d.width
+            pts.append(p)
+        return pts
+
+    def rvs_transformed(self, n: int, rng: np.random.Generator, dtype=np.float32) -> np.ndarray:
+        """n random points of the space, already transformed (integers snapped to their grid, categoricals one-hot)."""
+        U = np.empty((n, self.transformed_n_dims), dtype=dtype)
+        c = 0
+        for d in self.dimensions:
+            if isinstance(d, Real):
+                U[:, c] = rng.random(n)
+            elif isinstance(d, Integer):
+                span = d.high - d.low
+                U[:, c] = rng.integers(0, span + 1, size=n) / span
+            else:
+                k = rng.integers(0, len(d.categories), size=n)
+                if d.width == 1:
+                    U[:, c] = k
+                else:
+                    U[:, c:c + d.width] = 0
+                    U[np.arange(n), c + k] = 1
+            c += d.width
+        return U

@@ -1,0 +1,143 @@
+"""CPU: the api.v1.beta1 Suggestion surface through a REAL in-process grpc.server (SURVEY.md §4 item iv):
+BASELINE.json config 1 (random search, 4-dim continuous space, 32 trials), ValidateAlgorithmSettings error mapping,
+request conversion, both service names, the health endpoint.  The GP algorithm itself needs a GPU: its gRPC test is
+in tests/test_gpu_service.py."""
+import grpc
+import numpy as np
+import pytest
+
+from kubeflow_b200.suggestion import api_pb as api
+from kubeflow_b200.suggestion.internal import AlgorithmSettingsError, HyperParameterSearchSpace, Trial
+from kubeflow_b200.suggestion.server import SERVICE_NAMES, SuggestionStub, serve
+from kubeflow_b200.suggestion.service import DispatchService, RandomService, SkoptService, validate_skopt_settings
+
+
+def make_experiment(algorithm="random", settings=None, objective=api.MINIMIZE, name="exp-1"):
+    e = api.Experiment()
+    e.name = name
+    e.spec.objective.type = objective
+    e.spec.objective.objective_metric_name = "loss"
+    e.spec.algorithm.algorithm_name = algorithm
+    for k, v in (settings or {}).items():
+        s = e.spec.algorithm.algorithm_settings.add()
+        s.name, s.value = k, str(v)
+    for i, (lo, hi) in enumerate([(0.01, 0.1), (-1.0, 1.0), (10.0, 20.0), (0.0, 5.0)]):
+        p = e.spec.parameter_specs.parameters.add()
+        p.name, p.parameter_type = f"x{i}", api.DOUBLE
+        p.feasible_space.min, p.feasible_space.max = str(lo), str(hi)
+    return e
+
+
+def add_trial(req, name, values, loss, condition=api.SUCCEEDED):
+    t = req.trials.add()
+    t.name = name
+    t.spec.objective.objective_metric_name = "loss"
+    for k, v in values.items():
+        a = t.spec.parameter_assignments.assignments.add()
+        a.name, a.value = k, str(v)
+    t.status.condition = condition
+    m = t.status.observation.metrics.add()
+    m.name, m.value = "loss", str(loss)
+    return t
+
+
+@pytest.fixture(scope="module")
+def stub():
+    server, port = serve(DispatchService([SkoptService(), RandomService()]), port=0, host="127.0.0.1")
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    yield SuggestionStub(ch)
+    ch.close()
+    server.stop(0)
+
+
+def test_config1_random_search_32_trials_over_grpc(stub):
+    exp = make_experiment("random", {"random_state": 7})
+    stub.ValidateAlgorithmSettings(api.ValidateAlgorithmSettingsRequest(experiment=exp))
+    req = api.GetSuggestionsRequest(experiment=exp, current_request_number=4)
+    seen = []
+    for round_ in range(8):                      # 8 × 4 = 32 trials, each call resends all completed trials
+        reply = stub.GetSuggestions(req)
+        assert len(reply.parameter_assignments) == 4
+        for pa in reply.parameter_assignments:
+            vals = {a.name: float(a.value) for a in pa.assignments}
+            assert list(vals) == ["x0", "x1", "x2", "x3"]
+            for (lo, hi), v in zip([(0.01, 0.1), (-1.0, 1.0), (10.0, 20.0), (0.0, 5.0)], vals.values()):
+                assert lo <= v <= hi
+            seen.append(tuple(vals.values()))
+            add_trial(req, f"t{len(seen)}", vals, loss=sum(vals.values()))
+    assert len(seen) == 32 and len(set(seen)) == 32
+
+
+def test_both_service_names_and_health():
+    server, port = serve(RandomService(), port=0, host="127.0.0.1")
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    for name in SERVICE_NAMES:
+        s = SuggestionStub(ch, name)
+        r = s.GetSuggestions(api.GetSuggestionsRequest(experiment=make_experiment("random"), current_request_number=1))
+        assert len(r.parameter_assignments) == 1
+    assert SuggestionStub(ch).HealthCheck(b"") == b"\x08\x01"
+    ch.close()
+    server.stop(0)
+
+
+@pytest.mark.parametrize("settings,frag", [({"base_estimator": "XGB"}, "base_estimator"), ({"n_initial_points": -1}, "n_initial_points"),
+                                            ({"acq_func": "UCBX"}, "acq_func"), ({"acq_optimizer": "adam"}, "acq_optimizer"),
+                                            ({"random_state": -3}, "random_state"), ({"n_points": "abc"}, "n_points"),
+                                            ({"bogus": 1}, "unknown setting"), ({"kernel": "linear"}, "kernel")])
+def test_validate_rejects_bad_settings_with_invalid_argument(stub, settings, frag):
+    with pytest.raises(grpc.RpcError) as ei:
+        stub.ValidateAlgorithmSettings(api.ValidateAlgorithmSettingsRequest(experiment=make_experiment("bayesianoptimization", settings)))
+    assert ei.value.code() == grpc.StatusCode.INVALID_ARGUMENT and frag in ei.value.details()
+
+
+def test_validate_accepts_upstream_and_engine_settings(stub):
+    ok = {"base_estimator": "GP", "n_initial_points": 10, "acq_func": "gp_hedge", "acq_optimizer": "auto", "random_state": 1,
+          "n_points": 4096, "kernel": "matern52", "noise": 1e-3, "var_mode": "tc"}
+    stub.ValidateAlgorithmSettings(api.ValidateAlgorithmSettingsRequest(experiment=make_experiment("bayesianoptimization", ok)))
+    assert validate_skopt_settings({k: str(v) for k, v in ok.items()})["n_points"] == 4096
+
+
+def test_unknown_algorithm_and_bad_space(stub):
+    with pytest.raises(grpc.RpcError) as ei:
+        stub.ValidateAlgorithmSettings(api.ValidateAlgorithmSettingsRequest(experiment=make_experiment("tpe")))
+    assert ei.value.code() == grpc.StatusCode.INVALID_ARGUMENT
+    e = make_experiment("random")
+    e.spec.parameter_specs.parameters[0].feasible_space.min = "9"      # min > max
+    with pytest.raises(grpc.RpcError) as ei:
+        stub.GetSuggestions(api.GetSuggestionsRequest(experiment=e, current_request_number=1))
+    assert ei.value.code() == grpc.StatusCode.INVALID_ARGUMENT
+
+
+def test_request_conversion_types_and_goal():
+    e = make_experiment("random", objective=api.MAXIMIZE)
+    p = e.spec.parameter_specs.parameters.add(); p.name, p.parameter_type = "layers", api.INT
+    p.feasible_space.min, p.feasible_space.max = "1", "8"
+    p = e.spec.parameter_specs.parameters.add(); p.name, p.parameter_type = "opt", api.CATEGORICAL
+    p.feasible_space.list.extend(["sgd", "adam", "ftrl"])
+    p = e.spec.parameter_specs.parameters.add(); p.name, p.parameter_type = "bs", api.DISCRETE
+    p.feasible_space.list.extend(["16", "32"])
+    ss = HyperParameterSearchSpace.convert(e)
+    assert ss.goal == "MAXIMIZE" and [q.type for q in ss.params] == ["double"] * 4 + ["int", "categorical", "discrete"]
+    req = api.GetSuggestionsRequest(experiment=e)
+    add_trial(req, "ok", {"x0": 0.05}, 0.5)
+    add_trial(req, "running", {"x0": 0.05}, 0.5, condition=1)
+    t = req.trials.add(); t.name = "no-metric"; t.status.condition = api.SUCCEEDED
+    conv = Trial.convert(req.trials)
+    assert [c.name for c in conv] == ["ok"] and conv[0].target_metric.value == "0.5"
+    e.spec.objective.type = api.UNKNOWN
+    with pytest.raises(AlgorithmSettingsError):
+        HyperParameterSearchSpace.convert(e)
+
+
+def test_space_transform_roundtrip():
+    from kubeflow_b200.space import Categorical, Integer, Real, Space
+    sp = Space([Real(0.01, 0.1), Integer(1, 8), Categorical(["sgd", "adam", "ftrl"]), Categorical(["16", "32"])])
+    assert sp.transformed_n_dims == 1 + 1 + 3 + 1
+    pts = [[0.05, 3, "adam", "32"], [0.01, 8, "ftrl", "16"]]
+    U = sp.transform(pts)
+    assert U.shape == (2, 6) and U.min() >= 0 and U.max() <= 1
+    back = sp.inverse_transform(U)
+    assert back[0][1:] == [3, "adam", "32"] and abs(back[0][0] - 0.05) < 1e-12 and back[1][1:] == [8, "ftrl", "16"]
+    R = sp.rvs_transformed(1000, np.random.default_rng(0))
+    assert R.shape == (1000, 6) and np.allclose(R[:, 2:5].sum(1), 1) and set(np.unique(R[:, 5])) == {0.0, 1.0}
+    assert np.allclose(R[:, 1] * 7, np.round(R[:, 1] * 7), atol=1e-5)
