@@ -6,24 +6,19 @@
 // B200 has a full FP64 pipe, and the fit is O(N³/3) once per suggestion next to the O(M·N²) sweep.
 #include "kbo_internal.cuh"
 #include "dgemm.cuh"
+#include "ktab.cuh"
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double kbo_kernel_eval(double d2, int kind) {
-  d2 = d2 < 0.0 ? 0.0 : d2;
-  if (kind == KBO_KERNEL_RBF) return exp(-0.5 * d2);
-  const double s = sqrt(5.0 * d2);
-  return (1.0 + s + s * s * (1.0 / 3.0)) * exp(-s);
-}
-
 // Xs = X / ℓ, nx = |Xs|² (one thread per trial row)
 __global__ void prep_x_kernel(const double* __restrict__ X, int N, int D, const double* __restrict__ inv_ls, int n_ls,
-                              double* __restrict__ Xs, double* __restrict__ nx) {
+                              double* __restrict__ Xs, double* __restrict__ XsT, int ldx, double* __restrict__ nx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double s = 0.0;
   for (int d = 0; d < D; d++) {
     const double v = X[(size_t)i * D + d] * inv_ls[n_ls == 1 ? 0 : d];
     Xs[(size_t)i * D + d] = v;
+    XsT[(size_t)d * ldx + i] = v;
     s = fma(v, v, s);
   }
   nx[i] = s;
@@ -126,7 +121,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs
     for (int j = 0; j < 4; j++) {
       const int gn = n0 + tx + 16 * j;
       if (gn >= N) continue;
-      double v = amp * kbo_kernel_eval(acc[i][j], kind);
+      double v = amp * kbo_kernel_exact(acc[i][j], kind);
       if (gm == gn) v += noise;
       K[(size_t)gm * ldk + gn] = v;
       if (m0 != n0) K[(size_t)gn * ldk + gm] = v;
@@ -146,34 +141,40 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
   const int t = threadIdx.x;
   if (*info != 0) return;  // an earlier panel already failed
   if (t == 0) bad = 0;
+  (void)bad;
   for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
     const int r = e >> 6, c = e & 63;
     S[r][c] = (r < jb && c <= r) ? A[(size_t)r * lda + c] : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();
-  for (int j = 0; j < jb; j++) {
-    const double djj = S[j][j];
-    if (!(djj > 0.0)) {
-      if (t == 0) {
-        bad = 1;
-        *info = k_global + j + 1;
+  // right-looking, thread (i, q) owns row i = t/4 and the 16 columns [16q, 16q+16) of that row
+  {
+    const int i = t >> 2, c0 = (t & 3) * 16;
+    for (int j = 0; j < jb; j++) {
+      const double djj = S[j][j];
+      if (!(djj > 0.0)) {
+        if (t == 0) {
+          bad = 1;
+          *info = k_global + j + 1;
+        }
+        __syncthreads();
+        return;   // uniform: every thread read the same S[j][j]
       }
+      const double rd = rsqrt(djj);
+      __syncthreads();  // everyone has read S[j][j] and (below) column j before it is rescaled
+      const double lij = (i > j && i < jb) ? S[i][j] * rd : 0.0;   // L[i][j]
+      // L[c][j] for this thread's columns: S[c][j]·rd  (c > j)
+      if (i > j && i < jb) {
+#pragma unroll 4
+        for (int c = max(c0, j + 1); c < c0 + 16 && c <= i; c++) S[i][c] = fma(-lij, S[c][j] * rd, S[i][c]);
+      }
+      __syncthreads();  // trailing update done reading column j
+      if ((t & 3) == 0) {
+        if (i == j) S[j][j] = sqrt(djj);
+        else if (i > j && i < jb) S[i][j] = lij;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (bad) return;
-    const double d = sqrt(djj);
-    const double rd = 1.0 / d;
-    __syncthreads();
-    if (t == 0) S[j][j] = d;
-    for (int i = j + 1 + t; i < jb; i += 256) S[i][j] *= rd;
-    __syncthreads();
-    // trailing update of the lower triangle: S[i][c] -= S[i][j]·S[c][j], j < c <= i < jb
-    const int rem = jb - j - 1;
-    for (int e = t; e < rem * rem; e += 256) {
-      const int i = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= i) S[i][c] = fma(-S[i][j], S[c][j], S[i][c]);
-    }
-    __syncthreads();
   }
   // inverse of the lower-triangular block by forward substitution, 4 threads per column
   {
@@ -347,11 +348,20 @@ __global__ void trmv_lower_kernel(const double* __restrict__ W, int N, int ldw, 
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) z[row] = s;
 }
-__global__ void trmv_lower_t_kernel(const double* __restrict__ W, int N, int ldw, const double* __restrict__ z, double* __restrict__ out) {
+// alpha = Wᵀ·z: block (x = 128 columns, y = row slab of 256) accumulates a partial; a second pass sums the slabs in order
+__global__ void trmv_lower_t_kernel(const double* __restrict__ W, int N, int ldw, const double* __restrict__ z, double* __restrict__ part) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.y * 256, i1 = min(N, i0 + 256);
+  if (k >= N) return;
+  double s = 0.0;
+  for (int i = max(i0, k); i < i1; i++) s = fma(W[(size_t)i * ldw + k], z[i], s);
+  part[(size_t)blockIdx.y * N + k] = s;
+}
+__global__ void trmv_t_reduce_kernel(const double* __restrict__ part, int N, int nslab, double* __restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= N) return;
   double s = 0.0;
-  for (int i = k; i < N; i++) s = fma(W[(size_t)i * ldw + k], z[i], s);
+  for (int b = 0; b < nslab; b++) s += part[(size_t)b * N + k];
   out[k] = s;
 }
 // LML = −½ ynᵀalpha − Σ log L_ii − N/2 log 2π  ($SK/_gpr.py:604-618)
@@ -453,6 +463,7 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   const int ld = h->ld;
   KBO_TRY(kbo_reserve(h, h->d_inv_ls, sizeof(double) * 512));
   KBO_TRY(kbo_reserve(h, h->Xs, sizeof(double) * (size_t)N * D));
+  KBO_TRY(kbo_reserve(h, h->XsT, sizeof(double) * (size_t)D * ld));
   KBO_TRY(kbo_reserve(h, h->nx, sizeof(double) * N));
   KBO_TRY(kbo_reserve(h, h->yn, sizeof(double) * N));
   KBO_TRY(kbo_reserve(h, h->K, sizeof(double) * (size_t)N * ld));
@@ -463,7 +474,7 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   KBO_TRY(kbo_reserve(h, h->info, sizeof(int) * 4));
   // inv_ls is tiny: stage through pageable memory is fine, but keep it async-safe by copying from the vector we own
   KBO_CUDA(h, cudaMemcpyAsync(h->d_inv_ls.p, h->inv_ls.data(), sizeof(double) * h->inv_ls.size(), cudaMemcpyHostToDevice, s));
-  prep_x_kernel<<<(N + 127) / 128, 128, 0, s>>>(X, N, D, (const double*)h->d_inv_ls.p, p->n_length_scale, (double*)h->Xs.p, (double*)h->nx.p);
+  prep_x_kernel<<<(N + 127) / 128, 128, 0, s>>>(X, N, D, (const double*)h->d_inv_ls.p, p->n_length_scale, (double*)h->Xs.p, (double*)h->XsT.p, ld, (double*)h->nx.p);
   KBO_LAUNCH_CHECK(h);
   prep_y_kernel<<<1, 1024, 0, s>>>(y, N, p->normalize_y, (double*)h->yn.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
@@ -472,8 +483,15 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
   trmv_lower_kernel<<<(N + 7) / 8, 256, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->yn.p, (double*)h->z.p);
   KBO_LAUNCH_CHECK(h);
-  trmv_lower_t_kernel<<<(N + 127) / 128, 128, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->z.p, (double*)h->alpha.p);
-  KBO_LAUNCH_CHECK(h);
+  {
+    const int nslab = (N + 255) / 256;
+    KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ld));  // reuse the trtri scratch for the slab partials
+    dim3 g((N + 127) / 128, nslab);
+    trmv_lower_t_kernel<<<g, 128, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->z.p, (double*)h->T.p);
+    KBO_LAUNCH_CHECK(h);
+    trmv_t_reduce_kernel<<<(N + 127) / 128, 128, 0, s>>>((const double*)h->T.p, N, nslab, (double*)h->alpha.p);
+    KBO_LAUNCH_CHECK(h);
+  }
   lml_kernel<<<1, 1024, 0, s>>>((const double*)h->K.p, N, ld, (const double*)h->yn.p, (const double*)h->alpha.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
   if (p->var_mode == KBO_VAR_TC_F16X3 || (p->var_mode == KBO_VAR_AUTO && N > 1024)) {

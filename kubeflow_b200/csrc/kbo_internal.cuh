@@ -30,6 +30,7 @@ struct kbo_handle {
   kbo_params prm{};
   std::vector<double> inv_ls;  // 1/ℓ_d, host copy
   DevBuf d_inv_ls;             // D doubles
+  DevBuf XsT;                  // Xs transposed: D × ld (coalesced trial-tile loads in the K* kernel)
   DevBuf Xs, nx, yraw, yn, K, W, Linv, T, alpha, z;
   DevBuf Wh, Wl;        // fp16 planes Npad×Npad (TC mode)
   DevBuf scal;          // device scalars, see ScalIdx

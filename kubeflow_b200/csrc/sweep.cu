@@ -5,121 +5,153 @@
 // fused Σv² epilogue, or the tcgen05 kernel in tc_var.cu)  →  once per sweep: acquisition + argmax.
 #include "kbo_internal.cuh"
 #include "dgemm.cuh"
-
-__device__ __forceinline__ double kbo_kernel_eval2(double d2, int kind) {
-  d2 = d2 < 0.0 ? 0.0 : d2;
-  if (kind == KBO_KERNEL_RBF) return exp(-0.5 * d2);
-  const double s = sqrt(5.0 * d2);
-  return (1.0 + s + s * s * (1.0 / 3.0)) * exp(-s);
-}
+#include "ktab.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// K* tile = 64 candidates × 64 trials per step, the CTA walks all trial tiles so μ needs no atomics.
-// MODE 0: K* written as fp64 (chunk × ldks).  MODE 1: K* written as fp16 hi/lo planes (chunk_pad × Npad),
-// hi = fp16(k), lo = fp16(k − hi): |k − hi − lo| ≤ 2⁻²⁴ for k ∈ [0, amp≈1].
+// K* kernel.  A CTA owns 128 candidates and walks all 64-trial tiles (so μ = K*·alpha needs no atomics).
+// The dot products are an FP64 GEMM with K = D: 8×4 outputs per thread (12 LDS per 32 DFMA keeps the FP64 pipe, not
+// shared memory, the limiter), the trial matrix is read from its TRANSPOSE (XsT, D × ldx) so global loads coalesce and
+// shared stores are conflict-free, and the next 32-dimension slab is prefetched into registers while the current one
+// is consumed (one __syncthreads per slab).  Epilogue per element: d² → branch-free FP64 kernel value (ktab.cuh) → μ FMA →
+// MODE 0: fp64 K* (chunk × ldks)   MODE 1: fp16 hi/lo planes (chunk_pad × Npad).
+#define CM_BM 128
+#define CM_BN 64
+#define CM_DC 32
 template <typename XT, typename MT, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* __restrict__ inv_ls, int n_ls,
-                  const double* __restrict__ Xs, const double* __restrict__ nx, int N, const double* __restrict__ alpha, int kind,
-                  double amp, double* __restrict__ Ks64, int ldks, __half* __restrict__ Ksh, __half* __restrict__ Ksl, int Npad,
-                  MT* __restrict__ mun) {
+                  const double* __restrict__ XsT, int ldx, const double* __restrict__ nx, int N, const double* __restrict__ alpha, int kind,
+                  double amp, double* __restrict__ Ks64, int ldks, __half* __restrict__ Ksh,
+                  __half* __restrict__ Ksl, int Npad, MT* __restrict__ mun) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int Dp = (D + 15) & ~15;
-  double* As = reinterpret_cast<double*>(smraw);  // [Dp][66]
-  double* Bs = As + (size_t)Dp * 66;              // [16][66]
-  double* nc = Bs + 16 * 66;                      // [64]
-  double* nxs = nc + 64;                          // [64]
-  double* als = nxs + 64;                         // [64]
-  __half* hs = reinterpret_cast<__half*>(als + 64);  // [64][72] (MODE 1)
-  __half* ls = hs + 64 * 72;
+  const int Dp = (D + CM_DC - 1) / CM_DC * CM_DC;
+  double* As = reinterpret_cast<double*>(smraw);        // [Dp][130]
+  double* Bs = As + (size_t)Dp * 130;                   // [2][32][66]
+  double* nc = Bs + 2 * CM_DC * 66;                     // [128]
+  double* nxs = nc + CM_BM;                             // [2][64]
+  double* als = nxs + 2 * CM_BN;                        // [2][64]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int64_t m0 = (int64_t)blockIdx.x * 64;
+  const int64_t m0 = (int64_t)blockIdx.x * CM_BM;
 
-  for (int e = tid; e < 64 * Dp; e += 256) {
+  for (int e = tid; e < CM_BM * Dp; e += 256) {
     const int r = e / Dp, d = e % Dp;
     double v = 0.0;
     if (m0 + r < rows && d < D) v = (double)Xc[(m0 + r) * D + d] * inv_ls[n_ls == 1 ? 0 : d];
-    As[d * 66 + r] = v;
+    As[d * 130 + r] = v;
   }
   __syncthreads();
-  if (tid < 64) {
+  if (tid < CM_BM) {
     double s = 0.0;
-    for (int d = 0; d < D; d++) s = fma(As[d * 66 + tid], As[d * 66 + tid], s);
+    for (int d = 0; d < D; d++) s = fma(As[d * 130 + tid], As[d * 130 + tid], s);
     nc[tid] = s;
   }
-  double musum[4] = {0.0, 0.0, 0.0, 0.0};
-  const int n_end = (MODE == 1) ? Npad : ((N + 63) & ~63);
-  for (int n0 = 0; n0 < n_end; n0 += 64) {
-    double acc[4][4];
+  const int nd = Dp / CM_DC;
+  const int ntiles = (N + CM_BN - 1) / CM_BN;
+  const int total = ntiles * nd;
+  double pf[8];
+  double pf_nx = 0.0, pf_al = 0.0;
+  // slab `it` = (tile it / nd, dims [ (it % nd)·32, +32 ) ): thread loads n = tid & 63, dd = (tid >> 6) + 4q
+  auto prefetch = [&](int it) {
+    const int n0 = (it / nd) * CM_BN, d0 = (it % nd) * CM_DC;
+    const int n = n0 + (tid & 63);
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int q = 0; q < 8; q++) {
+      const int d = d0 + (tid >> 6) + 4 * q;
+      pf[q] = (n < N && d < D) ? XsT[(size_t)d * ldx + n] : 0.0;
+    }
+    if ((it % nd) == 0 && tid < CM_BN) {
+      pf_nx = n < N ? nx[n] : 0.0;
+      pf_al = n < N ? alpha[n] : 0.0;
+    }
+  };
+  auto commit = [&](int it) {
+    double* B = Bs + (it & 1) * CM_DC * 66;
 #pragma unroll
-      for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-    if (n0 < N) {
-      if (tid < 64) {
-        const bool ok = n0 + tid < N;
-        nxs[tid] = ok ? nx[n0 + tid] : 0.0;
-        als[tid] = ok ? alpha[n0 + tid] : 0.0;
-      }
-      for (int d0 = 0; d0 < D; d0 += 16) {
-        const int d = tid & 15;
+    for (int q = 0; q < 8; q++) B[((tid >> 6) + 4 * q) * 66 + (tid & 63)] = pf[q];
+    if ((it % nd) == 0 && tid < CM_BN) {
+      const int tb = (it / nd) & 1;
+      nxs[tb * CM_BN + tid] = pf_nx;
+      als[tb * CM_BN + tid] = pf_al;
+    }
+  };
+  double musum[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int r = (tid >> 4) + 16 * i;
-          Bs[d * 66 + r] = (n0 + r < N && d0 + d < D) ? Xs[(size_t)(n0 + r) * D + d0 + d] : 0.0;
-        }
-        __syncthreads();
+  for (int i = 0; i < 8; i++) musum[i] = 0.0;
+  double acc[8][4];
+  if (total > 0) {
+    prefetch(0);
+    commit(0);
+  }
+  __syncthreads();
+  for (int it = 0; it < total; it++) {
+    const int tile = it / nd, dchunk = it % nd;
+    if (dchunk == 0) {
 #pragma unroll
-        for (int dd = 0; dd < 16; dd++) {
-          double a[4], b[4];
+      for (int i = 0; i < 8; i++)
 #pragma unroll
-          for (int i = 0; i < 4; i++) a[i] = As[(d0 + dd) * 66 + ty + 16 * i];
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    }
+    if (it + 1 < total) prefetch(it + 1);
+    {
+      const double* B = Bs + (it & 1) * CM_DC * 66;
+      const double* A = As + (size_t)dchunk * CM_DC * 130;
+#pragma unroll 8
+      for (int dd = 0; dd < CM_DC; dd++) {
+        double a[8], b[4];
 #pragma unroll
-          for (int j = 0; j < 4; j++) b[j] = Bs[dd * 66 + tx + 16 * j];
+        for (int i = 0; i < 8; i++) a[i] = A[dd * 130 + ty + 16 * i];
 #pragma unroll
-          for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) b[j] = B[dd * 66 + tx + 16 * j];
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-        }
-        __syncthreads();
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
       }
     }
+    if (dchunk == nd - 1) {
+      const int n0 = tile * CM_BN, tb = tile & 1;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int r = ty + 16 * i;
-      const bool rok = m0 + r < rows;
+      for (int i = 0; i < 8; i++) {
+        const int r = ty + 16 * i;
+        const bool rok = m0 + r < rows;
+        const double ncr = nc[r];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int c = tx + 16 * j;
-        double kv = 0.0;
-        if (rok && n0 + c < N) {
-          const double d2 = nc[r] + nxs[c] - 2.0 * acc[i][j];
-          kv = amp * kbo_kernel_eval2(d2, kind);
-          musum[i] = fma(kv, als[c], musum[i]);
-        }
-        if (MODE == 0) {
-          if (rok && n0 + c < N) Ks64[(size_t)(m0 + r) * ldks + n0 + c] = kv;
-        } else {
-          const __half hi = __double2half(kv);
-          hs[r * 72 + c] = hi;
-          ls[r * 72 + c] = __double2half(kv - (double)__half2float(hi));
+        for (int j = 0; j < 4; j++) {
+          const int c = tx + 16 * j;
+          double kv = 0.0;
+          if (rok && n0 + c < N) {
+            const double d2 = ncr + nxs[tb * CM_BN + c] - 2.0 * acc[i][j];
+            kv = amp * kbo_kernel_exact(d2, kind);
+            musum[i] = fma(kv, als[tb * CM_BN + c], musum[i]);
+          }
+          if (MODE == 0) {
+            if (rok && n0 + c < N) Ks64[(size_t)(m0 + r) * ldks + n0 + c] = kv;
+          } else {  // 16 lanes × 2 B = one full 32-byte sector per (row, 16-column group): no staging needed
+            const __half hi = __double2half(kv);
+            const size_t g = (size_t)(m0 + r) * Npad + n0 + c;
+            Ksh[g] = hi;
+            Ksl[g] = __double2half(kv - (double)__half2float(hi));
+          }
         }
       }
     }
-    if (MODE == 1) {
-      __syncthreads();
-      // 64 rows × 128 B per plane, 16 B per thread-store: fully coalesced rows
-      for (int e = tid; e < 64 * 8; e += 256) {
-        const int r = e >> 3, sgm = e & 7;
-        const size_t g = (size_t)(m0 + r) * Npad + n0 + sgm * 8;
-        *reinterpret_cast<uint4*>(Ksh + g) = *reinterpret_cast<const uint4*>(hs + r * 72 + sgm * 8);
-        *reinterpret_cast<uint4*>(Ksl + g) = *reinterpret_cast<const uint4*>(ls + r * 72 + sgm * 8);
-      }
-    }
+    if (it + 1 < total) commit(it + 1);
     __syncthreads();
   }
+  if (MODE == 1) {  // zero the padding columns [ntiles·64, Npad) of this CTA's rows (W is zero there, but 0·NaN must not happen)
+    const int c0 = ntiles * CM_BN, w = Npad - c0;
+    if (w > 0) {
+      const int segs = w / 8;
+      for (int e = tid; e < CM_BM * segs; e += 256) {
+        const int r = e / segs, sgm = e % segs;
+        const size_t g = (size_t)(m0 + r) * Npad + c0 + sgm * 8;
+        *reinterpret_cast<uint4*>(Ksh + g) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(Ksl + g) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 8; i++) {
     double s = musum[i];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -166,7 +198,7 @@ __global__ void __launch_bounds__(256)
 acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int64_t goff, int acq, double ymean, double ystd,
            double yopt, const double* __restrict__ scal_dev, double xi, double kappa, double* __restrict__ mu_out,
            double* __restrict__ std_out, double* __restrict__ acq_out, float* __restrict__ acq_out32,
-           BlockBest* __restrict__ partial) {
+           BlockBest* __restrict__ partial, unsigned int* __restrict__ ticket, kbo_best* __restrict__ best) {
   if (scal_dev) {  // composed path: y statistics stay on the device, no host round trip
     ymean = scal_dev[S_YMEAN];
     ystd = scal_dev[S_YSTD];
@@ -233,6 +265,7 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
   }
   __shared__ double sv[8];
   __shared__ long long si[8];
+  __shared__ unsigned int s_last;
   if ((threadIdx.x & 31) == 0) {
     sv[threadIdx.x >> 5] = bv;
     si[threadIdx.x >> 5] = bi;
@@ -246,40 +279,46 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
       }
     partial[blockIdx.x].v = bv;
     partial[blockIdx.x].i = bi;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
   }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(1024)
-argmax_final_kernel(const BlockBest* __restrict__ partial, int n, const T* __restrict__ mun, const T* __restrict__ varn, int64_t goff,
-                    int64_t M, double ymean, double ystd, const double* __restrict__ scal_dev, kbo_best* __restrict__ best) {
-  if (scal_dev) {
-    ymean = scal_dev[S_YMEAN];
-    ystd = scal_dev[S_YSTD];
-  }
-  __shared__ double sv[1024];
-  __shared__ long long si[1024];
-  double bv = -INFINITY;
-  long long bi = 0x7fffffffffffffffLL;
-  for (int e = threadIdx.x; e < n; e += 1024)
-    if (better(partial[e].v, partial[e].i, bv, bi)) {
-      bv = partial[e].v;
-      bi = partial[e].i;
-    }
-  sv[threadIdx.x] = bv;
-  si[threadIdx.x] = bi;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if (threadIdx.x < o && better(sv[threadIdx.x + o], si[threadIdx.x + o], sv[threadIdx.x], si[threadIdx.x])) {
-      sv[threadIdx.x] = sv[threadIdx.x + o];
-      si[threadIdx.x] = si[threadIdx.x + o];
+  if (!s_last) return;
+  // last block to finish: final reduce over the per-block partials (a max under a total order: order-independent)
+  __threadfence();
+  bv = -INFINITY;
+  bi = 0x7fffffffffffffffLL;
+  for (int e = threadIdx.x; e < (int)gridDim.x; e += 256) {
+    const double pv = ((volatile BlockBest*)partial)[e].v;
+    const long long pi = ((volatile BlockBest*)partial)[e].i;
+    if (better(pv, pi, bv, bi)) {
+      bv = pv;
+      bi = pi;
     }
-    __syncthreads();
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) {
+      bv = ov;
+      bi = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sv[threadIdx.x >> 5] = bv;
+    si[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    best->value = sv[0];
-    best->index = si[0];
-    const int64_t l = si[0] - goff;
+    for (int w = 1; w < 8; w++)
+      if (better(sv[w], si[w], bv, bi)) {
+        bv = sv[w];
+        bi = si[w];
+      }
+    best->value = bv;
+    best->index = bi;
+    const int64_t l = bi - goff;
     if (l >= 0 && l < M) {
       const double var = (double)varn[l] > 0.0 ? (double)varn[l] : 0.0;
       best->mu = ystd * (double)mun[l] + ymean;
@@ -288,6 +327,7 @@ argmax_final_kernel(const BlockBest* __restrict__ partial, int n, const T* __res
       best->mu = 0.0;
       best->std = 0.0;
     }
+    *ticket = 0;  // re-arm for the next launch on this stream
   }
 }
 
@@ -304,11 +344,13 @@ static int launch_acq(kbo_handle* h, const T* mun, const T* varn, int64_t M, int
                       const double* scal_dev, double xi, double kappa, double* mu_out, double* std_out, double* acq_out, float* acq_out32, kbo_best* best_dev,
                       cudaStream_t s) {
   const int g = acq_grid(h, M);
-  KBO_TRY(kbo_reserve(h, h->blockbest, sizeof(BlockBest) * (size_t)h->sm_count * 8));
+  if (h->blockbest.cap == 0) {
+    KBO_TRY(kbo_reserve(h, h->blockbest, sizeof(BlockBest) * (size_t)h->sm_count * 8 + 64));
+    KBO_CUDA(h, cudaMemsetAsync(h->blockbest.p, 0, h->blockbest.cap, s));
+  }
+  unsigned int* ticket = (unsigned int*)((BlockBest*)h->blockbest.p + (size_t)h->sm_count * 8);
   acq_kernel<T><<<g, 256, 0, s>>>(mun, varn, M, goff, acq, ymean, ystd, yopt, scal_dev, xi, kappa, mu_out, std_out, acq_out, acq_out32,
-                                  (BlockBest*)h->blockbest.p);
-  KBO_LAUNCH_CHECK(h);
-  argmax_final_kernel<T><<<1, 1024, 0, s>>>((const BlockBest*)h->blockbest.p, g, mun, varn, goff, M, ymean, ystd, scal_dev, best_dev);
+                                  (BlockBest*)h->blockbest.p, ticket, best_dev);
   KBO_LAUNCH_CHECK(h);
   return KBO_OK;
 }
@@ -324,9 +366,9 @@ int kbo_i_acq_argmax_f32(kbo_handle* h, const float* mu_n, const float* var_n, i
 
 // ------------------------------------------------------------------------------------------------
 static size_t cross_smem_bytes(int D, int mode) {
-  const int Dp = (D + 15) & ~15;
-  size_t b = sizeof(double) * ((size_t)Dp * 66 + 16 * 66 + 64 * 3);
-  if (mode == 1) b += sizeof(__half) * 2 * 64 * 72;
+  const int Dp = (D + CM_DC - 1) / CM_DC * CM_DC;
+  size_t b = sizeof(double) * ((size_t)Dp * 130 + 2 * CM_DC * 66 + CM_BM + 4 * CM_BN);
+  (void)mode;
   return b;
 }
 
@@ -335,8 +377,8 @@ static int launch_cross(kbo_handle* h, const XT* Xc, int64_t rows, int64_t rows_
                         cudaStream_t s) {
   const size_t smem = cross_smem_bytes(h->D, MODE);
   KBO_CUDA(h, cudaFuncSetAttribute(cross_mean_kernel<XT, MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cross_mean_kernel<XT, MT, MODE><<<(unsigned)((rows_grid + 63) / 64), 256, smem, s>>>(
-      Xc, rows, h->D, (const double*)h->d_inv_ls.p, (int)h->inv_ls.size(), (const double*)h->Xs.p, (const double*)h->nx.p, h->N,
+  cross_mean_kernel<XT, MT, MODE><<<(unsigned)((rows_grid + CM_BM - 1) / CM_BM), 256, smem, s>>>(
+      Xc, rows, h->D, (const double*)h->d_inv_ls.p, (int)h->inv_ls.size(), (const double*)h->XsT.p, h->ld, (const double*)h->nx.p, h->N,
       (const double*)h->alpha.p, h->prm.kernel, h->prm.amplitude, Ks64, ldks, Ksh, Ksl, h->Npad, mun);
   KBO_LAUNCH_CHECK(h);
   return KBO_OK;

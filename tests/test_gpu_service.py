@@ -1,0 +1,64 @@
+"""GPU: algorithm `bayesianoptimization` end to end through a real in-process grpc.server — the reference-facing call
+(katib-controller -> /api.v1.beta1.Suggestion/GetSuggestions) down to libkbo and back."""
+import grpc
+import numpy as np
+import pytest
+
+from kubeflow_b200.suggestion import api_pb as api
+from kubeflow_b200.suggestion.server import SuggestionStub, serve
+from kubeflow_b200.suggestion.service import DispatchService, RandomService, SkoptService
+from tests.test_grpc_service import add_trial, make_experiment
+
+pytestmark = pytest.mark.gpu
+
+
+def _f(vals):   # a smooth objective with its minimum inside the box
+    return (np.log10(vals["x0"]) + 1.5) ** 2 + (vals["x1"] - 0.3) ** 2 + ((vals["x2"] - 14.0) / 5) ** 2 + ((vals["x3"] - 2.0) / 2.5) ** 2
+
+
+@pytest.mark.parametrize("objective", [api.MINIMIZE, api.MAXIMIZE])
+def test_bayesianoptimization_over_grpc(objective):
+    server, port = serve(DispatchService([SkoptService(), RandomService()]), port=0, host="127.0.0.1")
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    stub = SuggestionStub(ch)
+    settings = {"base_estimator": "GP", "n_initial_points": 8, "acq_func": "EI", "acq_optimizer": "sampling", "random_state": 3,
+                "n_points": 20000}
+    exp = make_experiment("bayesianoptimization", settings, objective=objective, name=f"bo-{objective}")
+    stub.ValidateAlgorithmSettings(api.ValidateAlgorithmSettingsRequest(experiment=exp))
+    req = api.GetSuggestionsRequest(experiment=exp, current_request_number=2)
+    sign = 1.0 if objective == api.MINIMIZE else -1.0
+    losses = []
+    for _ in range(12):                                 # 24 trials: 8 random, then GP-EI with constant-liar pairs
+        reply = stub.GetSuggestions(req)
+        assert len(reply.parameter_assignments) == 2
+        for pa in reply.parameter_assignments:
+            vals = {a.name: float(a.value) for a in pa.assignments}
+            assert 0.01 <= vals["x0"] <= 0.1 and -1 <= vals["x1"] <= 1 and 10 <= vals["x2"] <= 20 and 0 <= vals["x3"] <= 5
+            loss = _f(vals)
+            losses.append(loss)
+            add_trial(req, f"t{len(losses)}", vals, sign * loss)
+    # the model-based phase must beat the random phase on this smooth bowl
+    assert min(losses[8:]) < min(losses[:8])
+    assert np.mean(sorted(losses[8:])[:4]) < np.mean(sorted(losses[:8])[:4])
+    ch.close()
+    server.stop(0)
+
+
+def test_optimizer_matches_oracle_argmax_on_transformed_space():
+    """kubeflow_b200.Optimizer.ask == oracle argmax over the same sampled candidates (same RNG stream)."""
+    from kubeflow_b200.optimizer import Optimizer
+    from kubeflow_b200.space import Integer, Real, Space
+    from oracle import gp_oracle as O
+    sp = Space([Real(0.0, 2.0), Real(-1.0, 1.0), Integer(1, 9)])
+    opt = Optimizer(sp, n_initial_points=5, acq_func="EI", random_state=11, n_points=5000, kernel="matern52", noise=1e-3)
+    r = np.random.default_rng(0)
+    pts = [[float(r.uniform(0, 2)), float(r.uniform(-1, 1)), int(r.integers(1, 10))] for _ in range(20)]
+    ys = [(p[0] - 1.2) ** 2 + p[1] ** 2 + 0.05 * (p[2] - 4) ** 2 for p in pts]
+    opt.tell(pts, ys)
+    rng_copy = np.random.default_rng(11)
+    x = opt.ask()
+    cand = sp.rvs_transformed(5000, rng_copy, np.float32).astype(np.float64)
+    ref = O.suggest(sp.transform(pts), np.asarray(ys), cand, kind="matern52", acq="ei", length_scale=0.3 * np.sqrt(3), amplitude=1.0,
+                    noise=1e-3)
+    assert opt.last_best.index == ref["index"] and abs(opt.last_best.value - ref["value"]) < 1e-7
+    assert x == sp.inverse_transform(cand[ref["index"]:ref["index"] + 1])[0]
