@@ -99,7 +99,8 @@ int kbo_version(void);
 int kbo_create(kbo_handle** out, int device);
 void kbo_destroy(kbo_handle* h);
 const char* kbo_last_error(const kbo_handle* h);
-/* cap (bytes) on the per-sweep K* scratch; default 2 GiB.  Determines the candidate chunk size. */
+/* cap (bytes) on the per-sweep K* scratch; default 4 GiB.  Determines the candidate chunk size (rounded down to a
+ * multiple of sm_count*128 rows so every launch is a whole number of waves). */
 int kbo_set_scratch_limit(kbo_handle* h, uint64_t bytes);
 
 /* ---- tell: GaussianProcessRegressor.fit at fixed θ ($SK/_gpr.py:275-280, 349-368) ---------------

@@ -20,7 +20,7 @@ struct kbo_handle {
   int device = 0;
   int sm_count = 148;
   std::string err;
-  uint64_t scratch_limit = 2ull << 30;
+  uint64_t scratch_limit = 4ull << 30;
 
   // ---- fit state -------------------------------------------------------------------------
   bool fitted = false;

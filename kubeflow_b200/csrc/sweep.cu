@@ -415,7 +415,11 @@ int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t 
   const double* scal = (const double*)h->scal.p;
   int64_t chunk;
   if (tc) {
-    chunk = (int64_t)(h->scratch_limit / ((size_t)Npad * 4)) / 128 * 128;
+    // wave-aligned chunks: the variance kernel runs one 128-row CTA per SM, the K* kernel two — a chunk that is a multiple
+    // of sm_count·128 rows leaves no partial wave (512 CTAs on 148 SMs idled 13 % of the tensor time; profiles/README.md)
+    const int64_t wave = (int64_t)h->sm_count * 128;
+    chunk = (int64_t)(h->scratch_limit / ((size_t)Npad * 4));
+    chunk = chunk >= wave ? chunk / wave * wave : chunk / 128 * 128;
     if (chunk < 128) chunk = 128;
     if (chunk > round_up64(M, 128)) chunk = round_up64(M, 128);
     KBO_TRY(kbo_reserve(h, h->Ksh, sizeof(__half) * (size_t)chunk * Npad));
