@@ -151,6 +151,25 @@ int kbo_acq_argmax(kbo_handle* h, const float* mu_n, const float* var_n, int64_t
                    int32_t acq, double y_mean, double y_std, double y_opt, double xi, double kappa,
                    float* acq_out, kbo_best* best_dev, void* stream);
 
+/* ---- CMA-ES (Katib algorithm `cmaes`, goptuna; N. Hansen's tutorial arXiv:1604.00772, active weights) ---------------
+ * State (mean, sigma, C, evolution paths, eigenbasis) lives on the device.  One generation = ask + tell:
+ *   kbo_cma_ask : X (lambda×D, device, fp64) = m + sigma·B·(d∘z); z from the built-in Philox stream (seed, generation) or,
+ *                 for parity tests, from z_in_dev (lambda×D device, may be NULL).
+ *   kbo_cma_tell: fitness (lambda, device, minimised, ties → lower sample index) for the X of the last ask → rank-μ/rank-1
+ *                 covariance update, step-size control and a warm-started Jacobi eigendecomposition.
+ * Limits: 1 <= D <= 128, 4 <= lambda <= 8192.  kbo_cma_state copies to HOST buffers (any may be NULL) and synchronises.
+ * kbo_cma_run_synthetic runs `generations` ask/fitness/tell rounds entirely on the device with a built-in fitness
+ * (0 = sphere, 1 = Rastrigin) — the BASELINE.json config-4 benchmark. */
+typedef struct kbo_cma kbo_cma;
+int kbo_cma_create(kbo_handle* h, kbo_cma** out, int32_t D, int32_t lambda, const double* mean0_host, double sigma0, uint64_t seed);
+void kbo_cma_destroy(kbo_cma* c);
+int kbo_cma_ask(kbo_handle* h, kbo_cma* c, double* X_dev, const double* z_in_dev, void* stream);
+int kbo_cma_tell(kbo_handle* h, kbo_cma* c, const double* fitness_dev, void* stream);
+int kbo_cma_state(kbo_handle* h, kbo_cma* c, double* mean, double* sigma, double* C, double* p_sigma, double* p_c, double* B,
+                  double* d, double* Y_last, int64_t* generation, void* stream);
+int kbo_cma_run_synthetic(kbo_handle* h, kbo_cma* c, int32_t fitness_kind, int32_t generations, double* best_f_host,
+                          float* elapsed_ms, double* jacobi_sweeps_last);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,7 +51,8 @@ class KboNotPositiveDefinite(KboError):
 # every symbol include/kbo.h declares (tests/test_abi.py checks the .so exports exactly these)
 EXPORTS = ["kbo_version", "kbo_create", "kbo_destroy", "kbo_last_error", "kbo_set_scratch_limit", "kbo_fit",
            "kbo_fit_info", "kbo_fit_state", "kbo_sweep", "kbo_best_to_host", "kbo_suggest_host", "kbo_last_timings",
-           "kbo_gram", "kbo_potrf", "kbo_trtri", "kbo_acq_argmax"]
+           "kbo_gram", "kbo_potrf", "kbo_trtri", "kbo_acq_argmax",
+           "kbo_cma_create", "kbo_cma_destroy", "kbo_cma_ask", "kbo_cma_tell", "kbo_cma_state", "kbo_cma_run_synthetic"]
 
 _lib = None
 
@@ -86,6 +87,13 @@ def load() -> C.CDLL:
     lib.kbo_potrf.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.kbo_trtri.argtypes = [vp, vp, i32, i32, vp, i32, vp]
     lib.kbo_acq_argmax.argtypes = [vp, vp, vp, i64, i64, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, vp]
+    lib.kbo_cma_create.argtypes = [vp, C.POINTER(vp), i32, i32, pd, dbl, C.c_uint64]
+    lib.kbo_cma_destroy.argtypes = [vp]
+    lib.kbo_cma_destroy.restype = None
+    lib.kbo_cma_ask.argtypes = [vp, vp, vp, vp, vp]
+    lib.kbo_cma_tell.argtypes = [vp, vp, vp, vp]
+    lib.kbo_cma_state.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
+    lib.kbo_cma_run_synthetic.argtypes = [vp, vp, i32, i32, pd, C.POINTER(C.c_float), pd]
     lib.kbo_tc_variance_raw.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp, dbl, vp, vp, i32, vp]
     for name in EXPORTS + ["kbo_tc_variance_raw"]:
         fn = getattr(lib, name)

@@ -1,0 +1,104 @@
+"""CPU oracle for the CMA-ES sampler behind Katib's ``cmaes`` algorithm.
+
+TEST INFRASTRUCTURE ONLY (same rule as gp_oracle.py).  PARITY UNPINNED: Katib's goptuna service (Go) and its
+dependencies are neither in /root/reference nor installable here (no Go toolchain, no ``cma``/``cmaes`` wheels), so
+this is a NumPy restatement of the published algorithm — N. Hansen, "The CMA Evolution Strategy: A Tutorial"
+(arXiv:1604.00772), in the variant with active (negative) recombination weights that CyberAgent's ``cmaes`` library
+implements and goptuna ports [RECALL]: parameter defaults eqs. (49)–(58), update eqs. (41)–(47) of the tutorial.
+The known-answer checks in tests/test_cma_oracle.py (weights sum, μ_eff, invariances, convergence on the sphere)
+pin it as far as is possible offline.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EPS = 1e-8
+
+
+class CmaParams:
+    """Strategy parameters for dimension n and population λ (tutorial Table 1 / ``cmaes`` defaults)."""
+
+    def __init__(self, n: int, popsize: int):
+        assert n >= 1 and popsize >= 2
+        self.n, self.popsize = n, popsize
+        mu = popsize // 2
+        wp = np.log((popsize + 1) / 2.0) - np.log(np.arange(1, popsize + 1))
+        mu_eff = wp[:mu].sum() ** 2 / (wp[:mu] ** 2).sum()
+        mu_eff_minus = wp[mu:].sum() ** 2 / (wp[mu:] ** 2).sum()
+        alpha_cov = 2.0
+        c1 = alpha_cov / ((n + 1.3) ** 2 + mu_eff)
+        cmu = min(1 - c1 - 1e-8, alpha_cov * (mu_eff - 2 + 1 / mu_eff) / ((n + 2) ** 2 + alpha_cov * mu_eff / 2))
+        min_alpha = min(1 + c1 / cmu, 1 + (2 * mu_eff_minus) / (mu_eff + 2), (1 - c1 - cmu) / (n * cmu))
+        pos_sum = wp[wp > 0].sum()
+        neg_sum = np.abs(wp[wp < 0]).sum()
+        self.weights = np.where(wp >= 0, wp / pos_sum, min_alpha / neg_sum * wp)
+        self.mu, self.mu_eff, self.c1, self.cmu, self.cm = mu, mu_eff, c1, cmu, 1.0
+        self.c_sigma = (mu_eff + 2) / (n + mu_eff + 5)
+        self.d_sigma = 1 + 2 * max(0.0, np.sqrt((mu_eff - 1) / (n + 1)) - 1) + self.c_sigma
+        self.cc = (4 + mu_eff / n) / (n + 4 + 2 * mu_eff / n)
+        self.chi_n = np.sqrt(n) * (1.0 - 1.0 / (4.0 * n) + 1.0 / (21.0 * n * n))
+
+
+class CmaState:
+    def __init__(self, mean, sigma, popsize):
+        self.mean = np.asarray(mean, dtype=np.float64).copy()
+        n = len(self.mean)
+        self.p = CmaParams(n, popsize)
+        self.sigma = float(sigma)
+        self.C = np.eye(n)
+        self.p_sigma = np.zeros(n)
+        self.pc = np.zeros(n)
+        self.g = 0
+
+
+def eigen(C):
+    """C = B diag(D²) Bᵀ, symmetrised, eigenvalues floored at EPS (as ``cmaes`` does before the square root)."""
+    C = (C + C.T) / 2
+    D2, B = np.linalg.eigh(C)
+    D = np.sqrt(np.where(D2 < 0, EPS, D2))
+    return B, D
+
+
+def ask(state: CmaState, z):
+    """x_k = m + σ·B·(D∘z_k) for the supplied standard normals z (λ×n).  Returns (X, Y)."""
+    B, D = eigen(state.C)
+    Y = (z * D) @ B.T
+    return state.mean + state.sigma * Y, Y
+
+
+def tell(state: CmaState, Y, fitness, znorm2=None):
+    """One generation update from the steps Y = (X − m)/σ (λ×n, in the order they were sampled) and their fitness
+    (minimised; ties broken by sample index).  ``znorm2`` = ‖C^{-1/2} y_k‖² per sample (defaults to computing it)."""
+    p, n = state.p, len(state.mean)
+    order = np.lexsort((np.arange(len(fitness)), np.asarray(fitness)))
+    Ys = np.asarray(Y, dtype=np.float64)[order]
+    B, D = eigen(state.C)
+    C_2 = B @ np.diag(1.0 / D) @ B.T
+    y_w = (Ys[:p.mu] * p.weights[:p.mu, None]).sum(0)
+    state.mean = state.mean + p.cm * state.sigma * y_w
+    state.p_sigma = (1 - p.c_sigma) * state.p_sigma + np.sqrt(p.c_sigma * (2 - p.c_sigma) * p.mu_eff) * (C_2 @ y_w)
+    norm_ps = np.linalg.norm(state.p_sigma)
+    sigma_new = state.sigma * np.exp((p.c_sigma / p.d_sigma) * (norm_ps / p.chi_n - 1))
+    h_left = norm_ps / np.sqrt(1 - (1 - p.c_sigma) ** (2 * (state.g + 1)))
+    h_sigma = 1.0 if h_left < (1.4 + 2 / (n + 1)) * p.chi_n else 0.0
+    state.pc = (1 - p.cc) * state.pc + h_sigma * np.sqrt(p.cc * (2 - p.cc) * p.mu_eff) * y_w
+    if znorm2 is None:
+        zn2 = ((Ys @ C_2.T) ** 2).sum(1)
+    else:
+        zn2 = np.asarray(znorm2)[order]
+    w_io = p.weights * np.where(p.weights >= 0, 1.0, n / (zn2 + EPS))
+    delta_h = (1 - h_sigma) * p.cc * (2 - p.cc)
+    rank_one = np.outer(state.pc, state.pc)
+    rank_mu = (Ys * w_io[:, None]).T @ Ys
+    state.C = (1 + p.c1 * delta_h - p.c1 - p.cmu * p.weights.sum()) * state.C + p.c1 * rank_one + p.cmu * rank_mu
+    state.sigma = float(sigma_new)
+    state.g += 1
+    return state
+
+
+def sphere(X):
+    return (X * X).sum(1)
+
+
+def rastrigin(X):
+    return 10.0 * X.shape[1] + (X * X - 10.0 * np.cos(2 * np.pi * X)).sum(1)

@@ -62,3 +62,33 @@ def test_optimizer_matches_oracle_argmax_on_transformed_space():
                     noise=1e-3)
     assert opt.last_best.index == ref["index"] and abs(opt.last_best.value - ref["value"]) < 1e-7
     assert x == sp.inverse_transform(cand[ref["index"]:ref["index"] + 1])[0]
+
+
+def test_cmaes_over_grpc():
+    """Katib algorithm `cmaes` on the GPU sampler: three full generations through the gRPC surface improve a bowl."""
+    from kubeflow_b200.suggestion.cmaes_service import CmaesService
+    server, port = serve(DispatchService([CmaesService()]), port=0, host="127.0.0.1")
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    stub = SuggestionStub(ch)
+    exp = make_experiment("cmaes", {"random_state": 2, "popsize": 12, "sigma": 0.25}, name="cma-1")
+    stub.ValidateAlgorithmSettings(api.ValidateAlgorithmSettingsRequest(experiment=exp))
+    req = api.GetSuggestionsRequest(experiment=exp, current_request_number=6)
+    gen_means = []
+    losses = []
+    for call in range(12):                     # 6 generations of 12, two calls each
+        reply = stub.GetSuggestions(req)
+        assert len(reply.parameter_assignments) == 6
+        for pa in reply.parameter_assignments:
+            vals = {a.name: float(a.value) for a in pa.assignments}
+            assert 0.01 <= vals["x0"] <= 0.1 and -1 <= vals["x1"] <= 1 and 10 <= vals["x2"] <= 20 and 0 <= vals["x3"] <= 5
+            losses.append(_f(vals))
+            add_trial(req, f"t{len(losses)}", vals, losses[-1])
+        if call % 2:
+            gen_means.append(np.mean(losses[-12:]))
+    assert gen_means[-1] < gen_means[0]
+    with pytest.raises(grpc.RpcError) as ei:
+        bad = make_experiment("cmaes", {"popsize": 2})
+        stub.ValidateAlgorithmSettings(api.ValidateAlgorithmSettingsRequest(experiment=bad))
+    assert ei.value.code() == grpc.StatusCode.INVALID_ARGUMENT
+    ch.close()
+    server.stop(0)
