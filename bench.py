@@ -43,6 +43,16 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
 
 
+def tc_traffic(rows_per_launch):
+    """dram bytes per launch of tc_variance_kernel from the committed `ncu --set full` capture (profiles/), scaled by rows."""
+    p = os.path.join(ROOT, "profiles", "tcvar_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"bytes_per_launch": (d["dram_read_bytes"] + d["dram_write_bytes"]) * rows_per_launch / d["rows"], "source": d["source"],
+            "captured_rows_per_launch": d["rows"]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -226,24 +236,64 @@ def main():
     ms_step_e2e = float(ms2.item()) / args.steps
     assert best_h.index == best.index, "host and device paths disagree on the argmax"
 
-    # ---- standalone acquisition pass: the HBM-bound kernel (8 B/candidate in + 4 B out) ---------------------------------
-    Ma = M
-    mu_n = torch.randn(Ma, device=dev, dtype=torch.float32)
-    var_n = torch.rand(Ma, device=dev, dtype=torch.float32)
-    acq_o = torch.empty(Ma, device=dev, dtype=torch.float32)
+    # ---- standalone acquisition pass: the HBM-bound kernel (8 B/candidate in + 4 B out), at this rank's M and at cfg5's 16M ----
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    ts = []
-    for i in range(8):
-        flush.zero_()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        eng.lib.kbo_acq_argmax(eng._h, mu_n.data_ptr(), var_n.data_ptr(), Ma, 0, 0, 0.0, 1.0, -1.0, 0.01, 1.96, acq_o.data_ptr(),
-                               eng._best_dev.data_ptr(), eng._stream())
-        a1.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            ts.append(a0.elapsed_time(a1))
-    acq_gbs = 12.0 * Ma / (np.mean(ts) * 1e-3) / 1e9
+
+    def acq_bw(Ma):
+        mu_n = torch.randn(Ma, device=dev, dtype=torch.float32)
+        var_n = torch.rand(Ma, device=dev, dtype=torch.float32)
+        acq_o = torch.empty(Ma, device=dev, dtype=torch.float32)
+        ts = []
+        for i in range(10):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            eng.lib.kbo_acq_argmax(eng._h, mu_n.data_ptr(), var_n.data_ptr(), Ma, 0, 0, 0.0, 1.0, -1.0, 0.01, 1.96, acq_o.data_ptr(),
+                                   eng._best_dev.data_ptr(), eng._stream())
+            a1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a0.elapsed_time(a1))
+        t = float(np.median(ts))
+        return 12.0 * Ma / (t * 1e-3) / 1e9, t
+
+    acq_gbs, acq_ms = acq_bw(M)
+    acq_gbs16, acq_ms16 = acq_bw(16_777_216)
+
+    # ---- the other BASELINE.json configurations, briefly (rank 0, single GPU): cfg2 (GP RBF) and cfg4 (CMA-ES) ---------------------
+    other = {}
+    if rank == 0 and world == 1:
+        try:
+            X2, y2, Xc2 = O.synthetic(1024, 65536, 8)
+            e2 = GPEngine(local, kernel="rbf", acq="ei", var_mode="auto", **O.theta_of_record(8))
+            X2d, y2d, Xc2d = torch.tensor(X2, device=dev), torch.tensor(y2, device=dev), torch.tensor(Xc2.astype(np.float32), device=dev)
+            for _ in range(3):
+                e2.tell(X2d, y2d); e2.ask(Xc2d)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                e2.tell(X2d, y2d); b2 = e2.ask(Xc2d)
+            torch.cuda.synchronize()
+            other["cfg2_gp_rbf_n1024_m65536_d8"] = {"suggestions_per_s": 10 / (time.perf_counter() - t0), "var_mode": "auto (FP64 contraction)",
+                                                     "argmax_index": b2.index}
+            e2.close()
+            from kubeflow_b200.cmaes import CmaEs
+            es = CmaEs(np.full(128, 3.0), 2.0, popsize=4096, seed=7, device=local)
+            es.run_synthetic("rastrigin", 20)
+            r4 = es.run_synthetic("rastrigin", 200)
+            other["cfg4_cmaes_d128_pop4096_200gen"] = {"generations_per_s": r4["generations_per_s"], "elapsed_ms": r4["elapsed_ms"],
+                                                        "jacobi_sweeps_last": r4["jacobi_sweeps"]}
+            es.close()
+            from oracle import cma_oracle as CO
+            st = CO.CmaState(np.full(128, 3.0), 2.0, 4096)
+            rr = np.random.default_rng(7)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                Xo, Yo = CO.ask(st, rr.standard_normal((4096, 128)))
+                CO.tell(st, Yo, CO.rastrigin(Xo))
+            other["cfg4_cmaes_d128_pop4096_200gen"]["cpu_oracle_generations_per_s"] = 5 / (time.perf_counter() - t0)
+        except Exception as e:  # noqa: BLE001 — the extras must never take the headline line down
+            other["error"] = f"{type(e).__name__}: {e}"
 
     if rank == 0:
         pk = peaks()
@@ -267,11 +317,13 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tc_variance_kernel", "achieved": achieved_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s",
                          "frac": achieved_tf / pk["tf_sus"], "peak_source": f"bf16_tflops_sustained, {pk['src']}",
-                         "issued_mma_tflops": 3.0 * achieved_tf * (1.0 + 256.0 / N), "traffic": None,
+                         "issued_mma_tflops": 3.0 * achieved_tf * (1.0 + 256.0 / N), "traffic": tc_traffic(rows_per_launch),
                          "launch_ms": var_launch_ms, "launches_per_step": chunks, "flops_per_launch": flops_launch},
-            "acquisition_hbm": {"kernel": "acq_kernel<float>", "bytes_per_candidate": 12, "candidates": Ma, "achieved": acq_gbs, "peak": pk["hbm"],
-                                "unit": "GB/s", "frac": acq_gbs / pk["hbm"], "peak_source": f"hbm_gbs, {pk['src']}", "launch_ms": float(np.mean(ts)),
+            "acquisition_hbm": {"kernel": "acq_kernel<float>", "bytes_per_candidate": 12, "candidates": M, "achieved": acq_gbs, "peak": pk["hbm"],
+                                "unit": "GB/s", "frac": acq_gbs / pk["hbm"], "peak_source": f"hbm_gbs, {pk['src']}", "launch_ms": acq_ms,
+                                "at_16M_candidates": {"achieved": acq_gbs16, "frac": acq_gbs16 / pk["hbm"], "launch_ms": acq_ms16},
                                 "l2": "flushed (256 MiB write) before each timed launch"},
+            "other_configs": other,
             "phases_ms": {"fit": float(np.mean(fit_ms)), "cross_kernel": float(np.mean(cross_ms)), "variance_kernel": float(np.mean(var_ms)),
                           "acquisition": float(np.mean(acq_ms))},
         }

@@ -137,7 +137,7 @@ int kbo_last_timings(kbo_handle* h, kbo_timings* out);
 
 /* ---- building blocks, caller-owned device memory (used by the parity tests one kernel at a time) --
  * kbo_gram:  K (N×ldk, fp64) = amplitude·k(Xs,Xs) + noise·I, Xs already divided by ℓ. ($SK/kernels.py:1561,1716)
- * kbo_potrf: in-place lower Cholesky of A (N×lda); upper triangle untouched; info_dev = 0 or failed pivot. ($SK/_gpr.py:352)
+ * kbo_potrf: in-place lower Cholesky of A (N×lda); the strict upper triangle is scratch afterwards; info_dev = 0 or failed pivot. ($SK/_gpr.py:352)
  * kbo_trtri: W (N×ldw, zero upper) = L^-1 for lower-triangular L.  Needs the potrf of the same handle just before
  *            (reuses its inverted diagonal blocks).
  * kbo_acq_argmax: standalone acquisition + argmax pass over (mu, var) in the NORMALISED y scale:

@@ -33,7 +33,7 @@ int kbo_create(kbo_handle** out, int device) {
 void kbo_destroy(kbo_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  DevBuf* bufs[] = {&h->d_inv_ls, &h->Xs, &h->nx, &h->yraw, &h->yn, &h->K, &h->W, &h->Linv, &h->T, &h->alpha, &h->z, &h->Wh, &h->Wl,
+  DevBuf* bufs[] = {&h->d_inv_ls, &h->Xs, &h->nx, &h->yn, &h->K, &h->W, &h->Linv, &h->T, &h->alpha, &h->z, &h->Wh, &h->Wl,
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
                     &h->blockbest, &h->best, &h->XsT};
   for (DevBuf* b : bufs)

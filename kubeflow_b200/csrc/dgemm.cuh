@@ -1,8 +1,7 @@
 // FP64 SIMT GEMM building block (B200 keeps a full-rate FP64 pipe: 64 DFMA/clk/SM).
 // C[M×N] = alpha · A[M×K] · op(B) + beta · C, with per-tile K-range clipping for triangular operands.
 // Used by the blocked Cholesky (syrk trailing update), the triangular inverse and the FP64
-// (checker-precision) variance contraction.  64×64 tile, BK = 16, 256 threads, 4×4 per thread with
-// a strided micro-tile so shared-memory reads are conflict-free and global writes coalesce.
+// (checker-precision) variance contraction.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -10,13 +9,16 @@ enum { KM_FULL = 0, KM_UPTO_N = 1, KM_FROM_N = 2, KM_UPTO_M = 3 };
 enum { EPI_STORE = 0, EPI_ROWSUMSQ = 1 };
 enum { TS_NONE = 0, TS_LOWER = 1 };
 
-#define DG_BM 64
+#define DG_BM 128
 #define DG_BN 64
 #define DG_BK 16
 
 // TRANSB = true : B is N×K row-major (C = A·Bᵀ, "NT");  false: B is K×N row-major ("NN").
+// 128×64 tile, 8×4 outputs per thread: 12 LDS per 32 DFMA, so the FP64 pipe — not shared memory — is the limiter
+// (the first version's 4×4 tile ran at 16 TFLOP/s, shared-memory bound).  The next K-slab is prefetched into registers
+// while the current one is consumed.
 template <bool TRANSB, int EPI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                double* __restrict__ C, int ldc, double alpha, double beta, int kmode, int kbegin, int tileskip,
                long long strideA, long long strideB, long long strideC) {
@@ -34,58 +36,79 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   if (kmode == KM_UPTO_M) ke = min(K, m0 + DG_BM);
   kb = kb & ~(DG_BK - 1);
 
-  double acc[4][4];
+  double acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 8; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
 
-  for (int k0 = kb; k0 < ke; k0 += DG_BK) {
-    {  // A tile: rows m0.., k contiguous
-      const int k = tid & 15;
+  double pa[8], pb[4];
+  auto prefetch = [&](int k0) {
+    {
+      const int k = tid & 15, gk = k0 + k;
+      const bool kok = gk < ke && gk >= kbegin;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int r = (tid >> 4) + 16 * i;
-        const int gm = m0 + r, gk = k0 + k;
-        As[k][r] = (gm < M && gk < ke && gk >= kbegin) ? A[(size_t)gm * lda + gk] : 0.0;
+      for (int i = 0; i < 8; i++) {
+        const int gm = m0 + (tid >> 4) + 16 * i;
+        pa[i] = (kok && gm < M) ? A[(size_t)gm * lda + gk] : 0.0;
       }
     }
     if (TRANSB) {
-      const int k = tid & 15;
+      const int k = tid & 15, gk = k0 + k;
+      const bool kok = gk < ke && gk >= kbegin;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int r = (tid >> 4) + 16 * i;
-        const int gn = n0 + r, gk = k0 + k;
-        Bs[k][r] = (gn < N && gk < ke && gk >= kbegin) ? B[(size_t)gn * ldb + gk] : 0.0;
+        const int gn = n0 + (tid >> 4) + 16 * i;
+        pb[i] = (kok && gn < N) ? B[(size_t)gn * ldb + gk] : 0.0;
       }
     } else {
-      const int n = tid & 63;
+      const int gn = n0 + (tid & 63);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int k = (tid >> 6) + 4 * i;
-        const int gn = n0 + n, gk = k0 + k;
-        Bs[k][n] = (gn < N && gk < ke && gk >= kbegin) ? B[(size_t)gk * ldb + gn] : 0.0;
+        const int gk = k0 + (tid >> 6) + 4 * i;
+        pb[i] = (gn < N && gk < ke && gk >= kbegin) ? B[(size_t)gk * ldb + gn] : 0.0;
       }
     }
-    __syncthreads();
+  };
+  auto commit = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; i++) As[tid & 15][(tid >> 4) + 16 * i] = pa[i];
+    if (TRANSB) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) Bs[tid & 15][(tid >> 4) + 16 * i] = pb[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) Bs[(tid >> 6) + 4 * i][tid & 63] = pb[i];
+    }
+  };
+  if (kb < ke) {
+    prefetch(kb);
+    commit();
+  }
+  __syncthreads();
+  for (int k0 = kb; k0 < ke; k0 += DG_BK) {
+    const bool more = k0 + DG_BK < ke;
+    if (more) prefetch(k0 + DG_BK);
 #pragma unroll
     for (int k = 0; k < DG_BK; k++) {
-      double a[4], b[4];
+      double a[8], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = As[k][ty + 16 * i];
+      for (int i = 0; i < 8; i++) a[i] = As[k][ty + 16 * i];
 #pragma unroll
       for (int j = 0; j < 4; j++) b[j] = Bs[k][tx + 16 * j];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
+    __syncthreads();
+    if (more) commit();
     __syncthreads();
   }
 
   if (EPI == EPI_STORE) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 8; i++) {
       const int gm = m0 + ty + 16 * i;
       if (gm >= M) continue;
 #pragma unroll
@@ -98,7 +121,7 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
     }
   } else {  // EPI_ROWSUMSQ: C is part[M × ldc], column = this block's n-tile; fixed reduction order
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 8; i++) {
       double s = 0.0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {

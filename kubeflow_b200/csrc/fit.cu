@@ -4,6 +4,8 @@
 // Why FP64 here (not fp32/tensor cores): the posterior mean is K*·alpha with |alpha|₂ up to ~3e3 for the
 // workloads of record; fp32 L/alpha moves EI by 1e-4 (measured) against a 1e-5 contract.
 // B200 has a full FP64 pipe, and the fit is O(N³/3) once per suggestion next to the O(M·N²) sweep.
+#include <stdlib.h>
+
 #include "kbo_internal.cuh"
 #include "dgemm.cuh"
 #include "ktab.cuh"
@@ -131,66 +133,66 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs
 
 // ------------------------------------------------------------------------------------------------
 // Blocked right-looking Cholesky (lower), NB = 64.
-// potf2_inv: factor one diagonal block in shared memory and invert it (for the panel solve).
-__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, int lda, int jb, int k_global,
-                                                        double* __restrict__ Linv, int* __restrict__ info) {
+// potf2_inv: factor one diagonal block in shared memory and invert it (for the panel solve).  1024 threads:
+// thread (i, q) owns row i = t/16 and columns [4q, 4q+4).  Right-looking with ONE barrier per column: the trailing
+// update of column j reads the still-unscaled column j and writes only columns > j; column j itself is rescaled after
+// the barrier, when nobody reads it any more.
+__device__ __forceinline__ void tri_inverse_64(double (*S)[KBO_NB + 1], double (*T)[KBO_NB + 1], double* invd, int t) {
+  // T = S⁻¹ (lower), forward substitution per column, 16 threads per column; invd[i] = 1/S[i][i]
+  if (t < KBO_NB) invd[t] = 1.0 / S[t][t];
+  __syncthreads();
+  const int c = t >> 4, q = t & 15;
+  for (int i = 0; i < KBO_NB; i++) {
+    double s = 0.0;
+    for (int k = c + q; k < i; k += 16) s = fma(S[i][k], T[k][c], s);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (q == 0) T[i][c] = (i < c) ? 0.0 : (i == c ? invd[i] : -s * invd[i]);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(1024) potf2_inv_kernel(double* __restrict__ A, int lda, int jb, int k_global,
+                                                         double* __restrict__ Linv, int* __restrict__ info) {
   extern __shared__ double sm[];
   double(*S)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm);
   double(*T)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm + KBO_NB * (KBO_NB + 1));
-  __shared__ int bad;
+  __shared__ double invd[KBO_NB];
   const int t = threadIdx.x;
   if (*info != 0) return;  // an earlier panel already failed
-  if (t == 0) bad = 0;
-  (void)bad;
-  for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+  for (int e = t; e < KBO_NB * KBO_NB; e += 1024) {
     const int r = e >> 6, c = e & 63;
     S[r][c] = (r < jb && c <= r) ? A[(size_t)r * lda + c] : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();
-  // right-looking, thread (i, q) owns row i = t/4 and the 16 columns [16q, 16q+16) of that row
   {
-    const int i = t >> 2, c0 = (t & 3) * 16;
+    const int i = t >> 4, c0 = (t & 15) * 4;
     for (int j = 0; j < jb; j++) {
       const double djj = S[j][j];
-      if (!(djj > 0.0)) {
-        if (t == 0) {
-          bad = 1;
-          *info = k_global + j + 1;
-        }
-        __syncthreads();
-        return;   // uniform: every thread read the same S[j][j]
+      if (!(djj > 0.0)) {  // uniform: every thread reads the same value
+        if (t == 0) *info = k_global + j + 1;
+        return;
       }
       const double rd = rsqrt(djj);
-      __syncthreads();  // everyone has read S[j][j] and (below) column j before it is rescaled
-      const double lij = (i > j && i < jb) ? S[i][j] * rd : 0.0;   // L[i][j]
-      // L[c][j] for this thread's columns: S[c][j]·rd  (c > j)
+      const double lij = (i > j && i < jb) ? S[i][j] * rd : 0.0;
       if (i > j && i < jb) {
-#pragma unroll 4
-        for (int c = max(c0, j + 1); c < c0 + 16 && c <= i; c++) S[i][c] = fma(-lij, S[c][j] * rd, S[i][c]);
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          const int c = c0 + cc;
+          if (c > j && c <= i) S[i][c] = fma(-lij, S[c][j] * rd, S[i][c]);
+        }
       }
-      __syncthreads();  // trailing update done reading column j
-      if ((t & 3) == 0) {
+      __syncthreads();
+      if ((t & 15) == 0) {
         if (i == j) S[j][j] = sqrt(djj);
         else if (i > j && i < jb) S[i][j] = lij;
       }
-      __syncthreads();
-    }
-  }
-  // inverse of the lower-triangular block by forward substitution, 4 threads per column
-  {
-    const int c = t >> 2, q = t & 3;
-    for (int i = 0; i < KBO_NB; i++) {
-      double s = 0.0;
-      if (i > c)
-        for (int k = c + q; k < i; k += 4) s = fma(S[i][k], T[k][c], s);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (q == 0) T[i][c] = (i < c) ? 0.0 : (i == c ? 1.0 / S[i][i] : -s / S[i][i]);
-      __syncwarp();
     }
   }
   __syncthreads();
-  for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+  tri_inverse_64(S, T, invd, t);
+  __syncthreads();
+  for (int e = t; e < KBO_NB * KBO_NB; e += 1024) {
     const int r = e >> 6, c = e & 63;
     if (r < jb && c <= r) A[(size_t)r * lda + c] = S[r][c];
     Linv[e] = T[r][c];
@@ -198,28 +200,20 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
 }
 
 // batched inverse of the 64×64 diagonal blocks of a lower-triangular L (for kbo_trtri); one CTA per block
-__global__ void __launch_bounds__(256) diag_inv_kernel(const double* __restrict__ L, int N, int ldl, double* __restrict__ W, int ldw) {
+__global__ void __launch_bounds__(1024) diag_inv_kernel(const double* __restrict__ L, int N, int ldl, double* __restrict__ W, int ldw) {
   extern __shared__ double sm[];
   double(*S)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm);
   double(*T)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm + KBO_NB * (KBO_NB + 1));
+  __shared__ double invd[KBO_NB];
   const int t = threadIdx.x, k0 = blockIdx.x * KBO_NB, jb = min(KBO_NB, N - k0);
-  for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+  for (int e = t; e < KBO_NB * KBO_NB; e += 1024) {
     const int r = e >> 6, c = e & 63;
     S[r][c] = (r < jb && c <= r) ? L[(size_t)(k0 + r) * ldl + k0 + c] : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();
-  const int c = t >> 2, q = t & 3;
-  for (int i = 0; i < KBO_NB; i++) {
-    double s = 0.0;
-    if (i > c)
-      for (int k = c + q; k < i; k += 4) s = fma(S[i][k], T[k][c], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (q == 0) T[i][c] = (i < c) ? 0.0 : (i == c ? 1.0 / S[i][i] : -s / S[i][i]);
-    __syncwarp();
-  }
+  tri_inverse_64(S, T, invd, t);
   __syncthreads();
-  for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+  for (int e = t; e < KBO_NB * KBO_NB; e += 1024) {
     const int r = e >> 6, c = e & 63;
     if (r < jb && c < jb) W[(size_t)(k0 + r) * ldw + k0 + c] = T[r][c];
   }
@@ -276,18 +270,36 @@ int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStr
   }
   KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   double* Linv = (double*)h->Linv.p;
-  for (int k = 0; k < N; k += KBO_NB) {
-    const int jb = min(KBO_NB, N - k);
-    double* Akk = A + (size_t)k * lda + k;
-    potf2_inv_kernel<<<1, 256, smem, s>>>(Akk, lda, jb, k, Linv, info_dev);
-    KBO_LAUNCH_CHECK(h);
-    const int rows = N - k - jb;
-    if (rows > 0) {
-      double* P = A + (size_t)(k + jb) * lda + k;
-      trsm_panel_kernel<<<(rows + 63) / 64, 256, smem, s>>>(P, lda, rows, jb, Linv, info_dev);
+  // Two-level blocking: 64-wide diagonal blocks (one CTA each) inside 256-wide outer panels.  Inside a panel only the
+  // panel's own remaining columns are updated after each 64-block (K = 64, ≤ 192 columns); the rest of the trailing
+  // matrix sees ONE update per outer panel with K = 256 — 4× less read-modify-write traffic on the trailing matrix than
+  // updating it after every 64-block (that version was memory bound: 46 GB of traffic at N = 8192).
+  const int OW = 256;
+  for (int K0 = 0; K0 < N; K0 += OW) {
+    const int W = min(OW, N - K0);
+    for (int k = K0; k < K0 + W; k += KBO_NB) {
+      const int jb = min(KBO_NB, N - k);
+      double* Akk = A + (size_t)k * lda + k;
+      potf2_inv_kernel<<<1, 1024, smem, s>>>(Akk, lda, jb, k, Linv, info_dev);
       KBO_LAUNCH_CHECK(h);
-      double* C = A + (size_t)(k + jb) * lda + (k + jb);
-      dgemm64_launch<true, EPI_STORE>(s, rows, rows, jb, P, lda, P, lda, C, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+      const int rows = N - k - jb;
+      if (rows > 0) {
+        double* P = A + (size_t)(k + jb) * lda + k;
+        trsm_panel_kernel<<<(rows + 63) / 64, 256, smem, s>>>(P, lda, rows, jb, Linv, info_dev);
+        KBO_LAUNCH_CHECK(h);
+        const int cin = K0 + W - (k + jb);  // columns of the outer panel still to be factorised
+        if (cin > 0) {
+          double* C = A + (size_t)(k + jb) * lda + (k + jb);
+          dgemm64_launch<true, EPI_STORE>(s, rows, cin, jb, P, lda, P, lda, C, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+          KBO_LAUNCH_CHECK(h);
+        }
+      }
+    }
+    const int rows_t = N - (K0 + W);
+    if (rows_t > 0) {
+      const double* Pp = A + (size_t)(K0 + W) * lda + K0;  // rows below the panel × the panel's W columns
+      double* C = A + (size_t)(K0 + W) * lda + (K0 + W);
+      dgemm64_launch<true, EPI_STORE>(s, rows_t, rows_t, W, Pp, lda, Pp, lda, C, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
       KBO_LAUNCH_CHECK(h);
     }
   }
@@ -305,7 +317,7 @@ int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int l
   KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
   double* T = (double*)h->T.p;
   KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));
-  diag_inv_kernel<<<(N + KBO_NB - 1) / KBO_NB, 256, smem, s>>>(L, N, ldl, W, ldw);
+  diag_inv_kernel<<<(N + KBO_NB - 1) / KBO_NB, 1024, smem, s>>>(L, N, ldl, W, ldw);
   KBO_LAUNCH_CHECK(h);
   for (long long b = KBO_NB; b < N; b *= 2) {
     const int full = (int)(N / (2 * b));
@@ -478,9 +490,18 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   KBO_LAUNCH_CHECK(h);
   prep_y_kernel<<<1, 1024, 0, s>>>(y, N, p->normalize_y, (double*)h->yn.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
+  // KBO_FIT_TRACE=1: per-phase CUDA-event timings on stderr (debug aid; adds stream syncs)
+  static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
+  cudaEvent_t te[6];
+  if (trace)
+    for (auto& e : te) cudaEventCreate(&e);
+  if (trace) cudaEventRecord(te[0], s);
   KBO_TRY(kbo_i_gram(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, s));
+  if (trace) cudaEventRecord(te[1], s);
   KBO_TRY(kbo_i_potrf(h, (double*)h->K.p, N, ld, (int*)h->info.p, s));
+  if (trace) cudaEventRecord(te[2], s);
   KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
+  if (trace) cudaEventRecord(te[3], s);
   trmv_lower_kernel<<<(N + 7) / 8, 256, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->yn.p, (double*)h->z.p);
   KBO_LAUNCH_CHECK(h);
   {
@@ -506,6 +527,17 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
     dim3 g((Npad + 255) / 256, Npad);
     split_w_kernel<<<g, 256, 0, s>>>((const double*)h->W.p, N, ld, Npad, amax, (__half*)h->Wh.p, (__half*)h->Wl.p, (double*)h->scal.p + 6);
     KBO_LAUNCH_CHECK(h);
+  }
+  if (trace) {
+    cudaEventRecord(te[4], s);
+    cudaEventSynchronize(te[4]);
+    float g, c, t, r;
+    cudaEventElapsedTime(&g, te[0], te[1]);
+    cudaEventElapsedTime(&c, te[1], te[2]);
+    cudaEventElapsedTime(&t, te[2], te[3]);
+    cudaEventElapsedTime(&r, te[3], te[4]);
+    fprintf(stderr, "[kbo fit N=%d] gram %.3f ms | potrf %.3f ms | trtri %.3f ms | alpha+lml+split %.3f ms\n", N, g, c, t, r);
+    for (auto& e : te) cudaEventDestroy(e);
   }
   h->fitted = true;
   return KBO_OK;

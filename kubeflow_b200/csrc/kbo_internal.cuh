@@ -31,7 +31,7 @@ struct kbo_handle {
   std::vector<double> inv_ls;  // 1/ℓ_d, host copy
   DevBuf d_inv_ls;             // D doubles
   DevBuf XsT;                  // Xs transposed: D × ld (coalesced trial-tile loads in the K* kernel)
-  DevBuf Xs, nx, yraw, yn, K, W, Linv, T, alpha, z;
+  DevBuf Xs, nx, yn, K, W, Linv, T, alpha, z;
   DevBuf Wh, Wl;        // fp16 planes Npad×Npad (TC mode)
   DevBuf scal;          // device scalars, see ScalIdx
   DevBuf info;          // int32: potrf info
@@ -113,4 +113,3 @@ int kbo_i_acq_argmax_f32(kbo_handle* h, const float* mu_n, const float* var_n, i
 // var_n[m] = amp − Σ_j (Σ_k K*[m,k] W[j,k])²  for the rows of one chunk, on tcgen05 tensor cores.
 int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl,
                       int Npad, double w_scale_inv, double amp, float* var_n_out, int k_span, cudaStream_t s);
-int kbo_i_tc_selftest(kbo_handle* h);

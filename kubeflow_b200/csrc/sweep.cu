@@ -193,6 +193,28 @@ __device__ __forceinline__ T acq_value(T mun, T varn, int acq, T ymean, T ystd, 
   return imp * cdf + sd * pdf;
 }
 
+// One pass: 8 B/candidate in (μ_n, σ²_n as fp32), optional 4 B out.  Persistent-style grid (≤ 2 CTAs per SM, 256 threads),
+// each thread streams groups of 4 candidates with TWO groups (4×16 B loads) in flight before any math, so a 12 MB pass is
+// not latency-bound on a single load→erfc→store chain per thread.
+// fp32 path of the HBM-bound pass, specialised per acquisition kind (no runtime switch inside the candidate loop):
+//   σ = σ²·rsqrt(σ²)·y_std (MUFU.RSQ), z = imp·rcp(σ), φ(z) = exp2(−z²·log2e/2)/√(2π) (MUFU.EX2), Φ(z) = erfcf(−z/√2)/2.
+// erfcf keeps RELATIVE accuracy in the lower tail, which is what ranks candidates when every EI is tiny (a cheaper
+// Abramowitz–Stegun Φ was tried: 7.5e-8 absolute error but it mis-ranks the z < −5 tail — tests/test_gpu_parity.py edge cases).
+template <int ACQ>
+__device__ __forceinline__ float acq_value_f32(float mun, float varn, float ymean, float ystd, float yopt, float xi, float kappa) {
+  const float var = fmaxf(varn, 0.f);
+  const float mu = fmaf(ystd, mun, ymean);
+  const float sd = var > 0.f ? var * rsqrtf(var) * ystd : 0.f;
+  if (ACQ == KBO_ACQ_LCB) return kappa * sd - mu;
+  if (!(sd > 0.f)) return 0.f;
+  const float imp = yopt - xi - mu;
+  const float z = __fdividef(imp, sd);   // MUFU.RCP + FMUL (2 ulp), no IEEE-division subroutine
+  const float cdf = 0.5f * erfcf(-0.70710678118654752440f * z);
+  if (ACQ == KBO_ACQ_PI) return cdf;
+  const float pdf = 0.3989422804014327f * exp2f(-0.72134752044448170368f * z * z);
+  return fmaf(imp, cdf, sd * pdf);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int64_t goff, int acq, double ymean, double ystd,
@@ -208,19 +230,19 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
   long long bi = 0x7fffffffffffffffLL;
   const T ym = (T)ymean, ys = (T)ystd, yo = (T)yopt, x = (T)xi, kp = (T)kappa;
   const int64_t stride = (int64_t)gridDim.x * 256 * 4;
-  for (int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; base < M; base += stride) {
-    T m4[4], v4[4];
-    const bool full = base + 3 < M;
-    if (full && sizeof(T) == 4) {
-      const float4 a = *reinterpret_cast<const float4*>(mun + base);
-      const float4 b = *reinterpret_cast<const float4*>(varn + base);
-      m4[0] = a.x; m4[1] = a.y; m4[2] = a.z; m4[3] = a.w;
-      v4[0] = b.x; v4[1] = b.y; v4[2] = b.z; v4[3] = b.w;
-    } else if (full) {
-      const double2 a0 = *reinterpret_cast<const double2*>(mun + base), a1 = *reinterpret_cast<const double2*>(mun + base + 2);
-      const double2 b0 = *reinterpret_cast<const double2*>(varn + base), b1 = *reinterpret_cast<const double2*>(varn + base + 2);
-      m4[0] = a0.x; m4[1] = a0.y; m4[2] = a1.x; m4[3] = a1.y;
-      v4[0] = b0.x; v4[1] = b0.y; v4[2] = b1.x; v4[3] = b1.y;
+  auto load4 = [&](int64_t base, T (&m4)[4], T (&v4)[4]) {
+    if (base + 3 < M) {
+      if (sizeof(T) == 4) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(mun + base));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(varn + base));
+        m4[0] = a.x; m4[1] = a.y; m4[2] = a.z; m4[3] = a.w;
+        v4[0] = b.x; v4[1] = b.y; v4[2] = b.z; v4[3] = b.w;
+      } else {
+        const double2 a0 = *reinterpret_cast<const double2*>(mun + base), a1 = *reinterpret_cast<const double2*>(mun + base + 2);
+        const double2 b0 = *reinterpret_cast<const double2*>(varn + base), b1 = *reinterpret_cast<const double2*>(varn + base + 2);
+        m4[0] = a0.x; m4[1] = a0.y; m4[2] = a1.x; m4[3] = a1.y;
+        v4[0] = b0.x; v4[1] = b0.y; v4[2] = b1.x; v4[3] = b1.y;
+      }
     } else {
 #pragma unroll
       for (int q = 0; q < 4; q++) {
@@ -228,30 +250,60 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
         v4[q] = base + q < M ? varn[base + q] : (T)0;
       }
     }
+  };
+  // Per-thread running best is kept in the value type T with a strict '>' (indices only grow inside a thread, so the
+  // first maximum wins without an index compare); it is widened to (double, int64) once, before the cross-thread reduce.
+  T tbest = -(T)INFINITY;
+  int64_t tidx = 0x7fffffffffffffffLL;
+  const bool fast32 = sizeof(T) == 4 && !mu_out && !std_out;
+  auto process4 = [&](int64_t base, const T (&m4)[4], const T (&v4)[4]) {
+    if (base >= M) return;
+    const bool full = base + 3 < M;
     float o4[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      T mu, sd;
-      const T a = acq_value<T>(m4[q], v4[q], acq, ym, ys, yo, x, kp, &mu, &sd);
+      T mu = (T)0, sd = (T)0;
+      T a;
+      if (fast32) {
+        const float fm = (float)m4[q], fv = (float)v4[q];
+        a = (T)(acq == KBO_ACQ_EI    ? acq_value_f32<KBO_ACQ_EI>(fm, fv, (float)ym, (float)ys, (float)yo, (float)x, (float)kp)
+                : acq == KBO_ACQ_LCB ? acq_value_f32<KBO_ACQ_LCB>(fm, fv, (float)ym, (float)ys, (float)yo, (float)x, (float)kp)
+                                     : acq_value_f32<KBO_ACQ_PI>(fm, fv, (float)ym, (float)ys, (float)yo, (float)x, (float)kp));
+      } else {
+        a = acq_value<T>(m4[q], v4[q], acq, ym, ys, yo, x, kp, &mu, &sd);
+      }
       o4[q] = (float)a;
-      if (base + q < M) {
-        if (mu_out) mu_out[base + q] = (double)mu;
-        if (std_out) std_out[base + q] = (double)sd;
+      if (full || base + q < M) {
+        if (!fast32) {
+          if (mu_out) mu_out[base + q] = (double)mu;
+          if (std_out) std_out[base + q] = (double)sd;
+        }
         if (acq_out) acq_out[base + q] = (double)a;
-        const double av = (a == a) ? (double)a : -INFINITY;  // NaN never wins
-        if (better(av, goff + base + q, bv, bi)) {
-          bv = av;
-          bi = goff + base + q;
+        if (a > tbest || (tidx == 0x7fffffffffffffffLL && a == a)) {  // NaN never wins; −inf can (all-hopeless grids)
+          tbest = a;
+          tidx = base + q;
         }
       }
     }
     if (acq_out32) {
       if (full) {
-        *reinterpret_cast<float4*>(acq_out32 + base) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        __stcs(reinterpret_cast<float4*>(acq_out32 + base), make_float4(o4[0], o4[1], o4[2], o4[3]));
       } else {
         for (int q = 0; q < 4 && base + q < M; q++) acq_out32[base + q] = o4[q];
       }
     }
+  };
+  for (int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; base < M; base += 2 * stride) {
+    T ma[4], va[4], mb[4], vb[4];
+    load4(base, ma, va);
+    const int64_t base2 = base + stride;
+    if (base2 < M) load4(base2, mb, vb);
+    process4(base, ma, va);
+    if (base2 < M) process4(base2, mb, vb);
+  }
+  if (tidx != 0x7fffffffffffffffLL) {
+    bv = (double)tbest;
+    bi = goff + tidx;
   }
   // warp-shuffle argmax (lowest index wins ties), then across the 8 warps through shared memory
 #pragma unroll
@@ -332,8 +384,8 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
 }
 
 static int acq_grid(kbo_handle* h, int64_t M) {
-  int64_t g = (M + 1023) / 1024;
-  const int64_t cap = (int64_t)h->sm_count * 8;
+  int64_t g = (M + 2047) / 2048;   // two groups of 4 candidates per thread per trip
+  const int64_t cap = (int64_t)h->sm_count * 4;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;

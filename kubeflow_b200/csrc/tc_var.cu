@@ -11,9 +11,12 @@
 // k < 256(t+1) is issued (W is lower triangular).  K is consumed in 32-wide chunks, 4-stage TMA→smem ring:
 //   warp 0     TMA producer (A hi/lo 128×32, B hi/lo 256×32 per stage, SWIZZLE_64B, mbarrier expect_tx)
 //   warp 1     MMA issuer  (single thread, tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16)
-//   warps 2-9  epilogue: TMEM → registers every `k_span` trials (two 256-column TMEM buffers ping-pong) and
+//   warps 2-17 epilogue: TMEM → registers every `k_span` trials (two 256-column TMEM buffers ping-pong) and
 //              accumulate in fp32 registers with round-to-nearest — bounds the length of the in-TMEM
-//              accumulation chain — then Σv² per row at the end of each j-tile.
+//              accumulation chain — then Σv² per row at the end of each j-tile.  16 warps (one row × 64 columns
+//              per thread, 4 tcgen05.ld.x16 per drain).  Measured: the per-span cost (~350 cycles) is TMEM read-port
+//              contention between the drains and the MMAs' own accumulator traffic, not epilogue latency (8 vs 16
+//              epilogue warps time the same), so k_span trades accuracy against tensor time directly.
 #include <cuda.h>
 
 #include "kbo_internal.cuh"
@@ -25,7 +28,8 @@
 #define TC_A_BYTES (TC_BM * TC_BK * 2)        // 8 KB per plane
 #define TC_B_BYTES (TC_BN * TC_BK * 2)        // 16 KB per plane
 #define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)  // 48 KB
-#define TC_THREADS 320
+#define TC_EPI_WARPS 16                       // 4 lane quarters × 4 column groups of 64
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS)
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 
 namespace {
@@ -96,15 +100,12 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -143,7 +144,7 @@ tc_variance_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(smem_u32(&S->tmem_full[i]), 1);
-      mbar_init(smem_u32(&S->tmem_empty[i]), 8);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&S->tmem_empty[i]), TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,13 +216,13 @@ tc_variance_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     __syncwarp();
   } else {
     // ===================================== epilogue warps =========================================
-    const int ew = warp - 2;             // 0..7
+    const int ew = warp - 2;             // 0..15
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = ew >> 2;            // which 128 of the 256 accumulator columns
+    const int cg = ew >> 2;              // which 64 of the 256 accumulator columns
     const int row = quarter * 32 + lane; // candidate row within the CTA tile (= TMEM lane)
-    float acc[128];
+    float acc[64];
 #pragma unroll
-    for (int i = 0; i < 128; i++) acc[i] = 0.f;
+    for (int i = 0; i < 64; i++) acc[i] = 0.f;
     double rowacc = 0.0;
     uint32_t span = 0;
     for (int jt = 0; jt < n_jtiles; jt++) {
@@ -230,23 +231,23 @@ tc_variance_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const uint32_t buf = span & 1, use = span >> 1;
         mbar_wait(smem_u32(&S->tmem_full[buf]), use & 1, 4);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC_BN + half * 128;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC_BN + cg * 64;
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-          uint32_t r[32];
-          tmem_ld32(taddr + p * 32, r);
+          uint32_t r[16];
+          tmem_ld16(taddr + p * 16, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i++) acc[p * 32 + i] += __uint_as_float(r[i]);
+          for (int i = 0; i < 16; i++) acc[p * 16 + i] += __uint_as_float(r[i]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&S->tmem_empty[buf]));
       }
-      // j-tile complete: Σ v² over this thread's 128 columns (4 partial sums, then fp64 across tiles)
+      // j-tile complete: Σ v² over this thread's 64 columns (4 partial sums, then fp64 across tiles)
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < 64; i += 4) {
         s0 = fmaf(acc[i], acc[i], s0);
         s1 = fmaf(acc[i + 1], acc[i + 1], s1);
         s2 = fmaf(acc[i + 2], acc[i + 2], s2);
@@ -256,13 +257,12 @@ tc_variance_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       rowacc += (double)((s0 + s1) + (s2 + s3));
     }
     const double sc = w_scale[1];
-    const double total_half = rowacc * sc * sc;
-    // combine the two column halves through shared memory (fixed order: half 0 + half 1)
-    __shared__ double halfsum[TC_BM];
-    if (half == 1) halfsum[row] = total_half;
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-    if (half == 0) {
-      const double tot = total_half + halfsum[row];
+    // combine the four column groups through shared memory in a fixed order
+    __shared__ double partsum[4][TC_BM];
+    partsum[cg][row] = rowacc * sc * sc;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");  // the epilogue warps only
+    if (cg == 0) {
+      const double tot = ((partsum[0][row] + partsum[1][row]) + partsum[2][row]) + partsum[3][row];
       var_out[m0 + row] = (float)(amp - tot);
       if (sumsq_out) sumsq_out[m0 + row] = tot;
     }

@@ -52,6 +52,9 @@ def test_golden(golden, var_mode, tol):
     np.testing.assert_allclose(acq, golden["acq"], rtol=0, atol=tol)
     _check_argmax(best, golden["acq"], tol)
     assert abs(best.mu - golden["mu"][best.index]) < 1e-5 and abs(best.std - golden["std"][best.index]) < 1e-4
+    # the array-free call is the product path (fp32 fast acquisition in tc mode): same winner, same value within tol
+    b2 = eng.ask(golden["Xc"])
+    _check_argmax(b2, golden["acq"], max(tol, 1e-6) if var_mode == "tc" else tol)
     eng.close()
 
 
