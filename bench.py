@@ -121,7 +121,7 @@ def run_reference(args, rank):
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(sample_rows=1024)
+        last = cpu_baseline(sample_rows=2048)
         if i >= args.warmup:
             vals.append(1.0 / last["value"])
     t = float(np.mean(vals))

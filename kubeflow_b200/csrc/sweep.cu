@@ -109,28 +109,41 @@ cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* 
       }
     }
     if (dchunk == nd - 1) {
+      // branch-free epilogue: all 32 kernel values are computed unconditionally (inputs are always finite) and masked at
+      // the end, so the whole block is one scheduling region with 32 independent FP64 dependency chains to interleave
       const int n0 = tile * CM_BN, tb = tile & 1;
+      double nxv[4], alv[4];
+      bool cok[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = tx + 16 * j;
+        nxv[j] = nxs[tb * CM_BN + c];
+        alv[j] = als[tb * CM_BN + c];
+        cok[j] = n0 + c < N;
+      }
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int r = ty + 16 * i;
         const bool rok = m0 + r < rows;
         const double ncr = nc[r];
+        double kv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) kv[j] = amp * kbo_kernel_exact(fma(-2.0, acc[i][j], ncr + nxv[j]), kind);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          kv[j] = (rok && cok[j]) ? kv[j] : 0.0;
+          musum[i] = fma(kv[j], alv[j], musum[i]);   // alpha is zero-padded past N, kv is masked: padding adds exactly 0
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int c = tx + 16 * j;
-          double kv = 0.0;
-          if (rok && n0 + c < N) {
-            const double d2 = ncr + nxs[tb * CM_BN + c] - 2.0 * acc[i][j];
-            kv = amp * kbo_kernel_exact(d2, kind);
-            musum[i] = fma(kv, als[tb * CM_BN + c], musum[i]);
-          }
           if (MODE == 0) {
-            if (rok && n0 + c < N) Ks64[(size_t)(m0 + r) * ldks + n0 + c] = kv;
+            if (rok && cok[j]) Ks64[(size_t)(m0 + r) * ldks + n0 + c] = kv[j];
           } else {  // 16 lanes × 2 B = one full 32-byte sector per (row, 16-column group): no staging needed
-            const __half hi = __double2half(kv);
+            const __half hi = __double2half(kv[j]);
             const size_t g = (size_t)(m0 + r) * Npad + n0 + c;
             Ksh[g] = hi;
-            Ksl[g] = __double2half(kv - (double)__half2float(hi));
+            Ksl[g] = __double2half(kv[j] - (double)__half2float(hi));
           }
         }
       }

@@ -301,7 +301,9 @@ int encode_map(kbo_handle* h, CUtensorMap* out, const void* base, uint64_t inner
 int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl, int Npad,
               const double* w_scale_dev, double amp, float* var_out, double* sumsq_out, int k_span, cudaStream_t s) {
   if (rows % TC_BM != 0 || Npad % TC_BN != 0) KBO_FAIL(h, KBO_ERR_INVALID, "tc_variance: rows %% 128 and Npad %% 256 must be 0");
-  if (k_span <= 0) k_span = 64;  // TMEM accumulation rounds toward zero: keep the in-TMEM chain short (profiles/r1_tmem_truncation.md)
+  // TMEM accumulation rounds toward zero (one-sided error ≈ 5e-9·k_span relative on Σv², profiles/README.md): 128 puts the
+  // truncation at the level of the fp16×3 split error (≈ 5e-7) and costs 8 % of tensor time against never draining.
+  if (k_span <= 0) k_span = 128;
   int span_chunks = k_span / TC_BK;
   if (span_chunks < 1) span_chunks = 1;
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
