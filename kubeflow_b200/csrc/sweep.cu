@@ -228,7 +228,9 @@ __device__ __forceinline__ float acq_value_f32(float mun, float varn, float ymea
   return fmaf(imp, cdf, sd * pdf);
 }
 
-template <typename T>
+// FAST_ACQ = −1: generic path (runtime acquisition kind, erfc/exp/sqrt in T, optional fp64 μ/σ outputs);
+// FAST_ACQ = 0/1/2: the fp32 specialisation for EI / LCB / PI chosen on the host — no per-candidate switch.
+template <typename T, int FAST_ACQ>
 __global__ void __launch_bounds__(256)
 acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int64_t goff, int acq, double ymean, double ystd,
            double yopt, const double* __restrict__ scal_dev, double xi, double kappa, double* __restrict__ mu_out,
@@ -268,7 +270,7 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
   // first maximum wins without an index compare); it is widened to (double, int64) once, before the cross-thread reduce.
   T tbest = -(T)INFINITY;
   int64_t tidx = 0x7fffffffffffffffLL;
-  const bool fast32 = sizeof(T) == 4 && !mu_out && !std_out;
+  constexpr bool fast32 = FAST_ACQ >= 0;
   auto process4 = [&](int64_t base, const T (&m4)[4], const T (&v4)[4]) {
     if (base >= M) return;
     const bool full = base + 3 < M;
@@ -279,9 +281,7 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
       T a;
       if (fast32) {
         const float fm = (float)m4[q], fv = (float)v4[q];
-        a = (T)(acq == KBO_ACQ_EI    ? acq_value_f32<KBO_ACQ_EI>(fm, fv, (float)ym, (float)ys, (float)yo, (float)x, (float)kp)
-                : acq == KBO_ACQ_LCB ? acq_value_f32<KBO_ACQ_LCB>(fm, fv, (float)ym, (float)ys, (float)yo, (float)x, (float)kp)
-                                     : acq_value_f32<KBO_ACQ_PI>(fm, fv, (float)ym, (float)ys, (float)yo, (float)x, (float)kp));
+        a = (T)acq_value_f32<(FAST_ACQ >= 0 ? FAST_ACQ : 0)>(fm, fv, (float)ym, (float)ys, (float)yo, (float)x, (float)kp);
       } else {
         a = acq_value<T>(m4[q], v4[q], acq, ym, ys, yo, x, kp, &mu, &sd);
       }
@@ -414,8 +414,17 @@ static int launch_acq(kbo_handle* h, const T* mun, const T* varn, int64_t M, int
     KBO_CUDA(h, cudaMemsetAsync(h->blockbest.p, 0, h->blockbest.cap, s));
   }
   unsigned int* ticket = (unsigned int*)((BlockBest*)h->blockbest.p + (size_t)h->sm_count * 8);
-  acq_kernel<T><<<g, 256, 0, s>>>(mun, varn, M, goff, acq, ymean, ystd, yopt, scal_dev, xi, kappa, mu_out, std_out, acq_out, acq_out32,
-                                  (BlockBest*)h->blockbest.p, ticket, best_dev);
+#define KBO_ACQ_LAUNCH(FA)                                                                                                     \
+  acq_kernel<T, FA><<<g, 256, 0, s>>>(mun, varn, M, goff, acq, ymean, ystd, yopt, scal_dev, xi, kappa, mu_out, std_out, acq_out, \
+                                      acq_out32, (BlockBest*)h->blockbest.p, ticket, best_dev)
+  if (sizeof(T) == 4 && !mu_out && !std_out) {
+    if (acq == KBO_ACQ_EI) KBO_ACQ_LAUNCH(KBO_ACQ_EI);
+    else if (acq == KBO_ACQ_LCB) KBO_ACQ_LAUNCH(KBO_ACQ_LCB);
+    else KBO_ACQ_LAUNCH(KBO_ACQ_PI);
+  } else {
+    KBO_ACQ_LAUNCH(-1);
+  }
+#undef KBO_ACQ_LAUNCH
   KBO_LAUNCH_CHECK(h);
   return KBO_OK;
 }
