@@ -166,6 +166,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version banner off stdout: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, M, D = args.trials, args.candidates, args.dim
     th = O.theta_of_record(D)
