@@ -418,12 +418,8 @@ int kbo_cma_create(kbo_handle* h, kbo_cma** out, int32_t D, int32_t lambda, cons
   cudaMemcpy(c->weights.p, w.data(), 8 * lambda, cudaMemcpyHostToDevice);
   cudaMemcpy(c->scal.p, sc, sizeof sc, cudaMemcpyHostToDevice);
   cma_init_kernel<<<D, 128>>>((double*)c->C.p, (double*)c->B.p, (double*)c->Dv.p, (double*)c->ps.p, (double*)c->pc.p, D);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(cma_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CMA_MAXD * (CMA_MAXD + 1)));
-    cudaFuncSetAttribute(cma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
-    attr = true;
-  }
+  cudaFuncSetAttribute(cma_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CMA_MAXD * (CMA_MAXD + 1)));
+  cudaFuncSetAttribute(cma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
   KBO_CUDA(h, cudaDeviceSynchronize());
   *out = c;
   return KBO_OK;

@@ -260,13 +260,12 @@ __global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ P,
 
 int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s) {
   KBO_TRY(kbo_reserve(h, h->Linv, sizeof(double) * KBO_NB * KBO_NB));
-  static bool attr_set = false;
   const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
-  if (!attr_set) {
+  if (!h->attr_fit) {
     KBO_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     KBO_CUDA(h, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    h->attr_fit = true;
   }
   KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   double* Linv = (double*)h->Linv.p;
@@ -308,12 +307,8 @@ int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStr
 
 // W = L^-1 by recursive doubling: [[W11,0],[−W22·L21·W11, W22]] — log2(N/64) levels of two batched GEMMs.
 int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int ldw, cudaStream_t s) {
-  static bool attr_set = false;
   const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
-  if (!attr_set) {
-    KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
   double* T = (double*)h->T.p;
   KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));

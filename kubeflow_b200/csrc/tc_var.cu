@@ -311,10 +311,9 @@ int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows,
   KBO_TRY(encode_map(h, &tmAl, Ksl, (uint64_t)Npad, (uint64_t)rows, TC_BM));
   KBO_TRY(encode_map(h, &tmBh, Wh, (uint64_t)Npad, (uint64_t)Npad, TC_BN));
   KBO_TRY(encode_map(h, &tmBl, Wl, (uint64_t)Npad, (uint64_t)Npad, TC_BN));
-  static bool attr = false;
-  if (!attr) {
+  if (!h->attr_tc) {
     KBO_CUDA(h, cudaFuncSetAttribute(tc_variance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr = true;
+    h->attr_tc = true;
   }
   tc_variance_kernel<<<(unsigned)(rows / TC_BM), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh, tmAl, tmBh, tmBl, Npad / TC_BN, span_chunks, w_scale_dev,
                                                                                 amp, var_out, sumsq_out);

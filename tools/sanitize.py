@@ -1,0 +1,21 @@
+"""Small end-to-end invocations of every kernel for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from kubeflow_b200.gp import GPEngine
+from kubeflow_b200.cmaes import CmaEs
+from oracle import gp_oracle as O
+
+for N, M, D, mode in ((70, 300, 3, "f64"), (130, 515, 5, "tc"), (300, 700, 33, "tc")):
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    e = GPEngine(0, kernel="matern52", acq="ei", var_mode=mode, **th)
+    e.tell(X, y)
+    b = e.ask(Xc.astype(np.float32))
+    b2, t = e.suggest_host(X, y, Xc)
+    print(N, M, D, mode, b.index, b2.index)
+    e.close()
+es = CmaEs(np.zeros(9), 1.0, popsize=20, seed=1)
+print(es.run_synthetic("sphere", 3))
+es.close()
