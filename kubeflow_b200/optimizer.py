@@ -20,7 +20,7 @@ from .space import Space
 class Optimizer:
     def __init__(self, dimensions, base_estimator="GP", n_initial_points=10, acq_func="EI", acq_optimizer="sampling",
                  random_state=None, *, n_points=65536, kernel="matern52", length_scale=None, amplitude=1.0, noise=1e-3, xi=0.01,
-                 kappa=1.96, var_mode="auto", theta_grid=1, device=0, engine=None):
+                 kappa=1.96, var_mode="auto", theta_grid=1, device=0, engine=None, candidate_backend="torch"):
         if str(base_estimator).upper() != "GP":
             raise ValueError("base_estimator must be GP (RF/ET/GBRT are not part of the GPU path)")
         self.space = dimensions if isinstance(dimensions, Space) else Space(dimensions)
@@ -36,7 +36,13 @@ class Optimizer:
         self.kernel, self.amplitude, self.noise, self.xi, self.kappa = kernel, amplitude, noise, xi, kappa
         self.length_scale = length_scale
         self.var_mode, self.theta_grid, self.device = var_mode, int(theta_grid), device
+        if candidate_backend not in ("torch", "numpy"):
+            raise ValueError("candidate_backend must be 'torch' (sampled on the device) or 'numpy'")
+        self.candidate_backend = candidate_backend
+        self._tgen = None
+        self._seed = random_state
         self.Xi, self.yi = [], []
+        self._Xt = []                 # transformed rows, appended on tell (the history is resent on every request)
         self._engine = engine
         self.last_best = None
 
@@ -46,8 +52,11 @@ class Optimizer:
             x, y = [x], [y]
         if len(x) != len(y):
             raise ValueError("x and y must have the same length")
-        self.Xi.extend([list(p) for p in x])
+        rows = [list(p) for p in x]
+        self.Xi.extend(rows)
         self.yi.extend([float(v) for v in y])
+        if rows:
+            self._Xt.extend(self.space.transform(rows))
 
     def _get_engine(self, ls):
         from .gp import GPEngine
@@ -65,7 +74,10 @@ class Optimizer:
     def _ask_one(self, X, y):
         if len(y) < max(self.n_initial_points, 1):
             return self.space.inverse_transform(self.space.rvs_transformed(1, self.rng, np.float64))[0]
-        Xt = self.space.transform(X)
+        n_told = len(self._Xt)
+        Xt = np.asarray(self._Xt, dtype=np.float64).reshape(n_told, self.space.transformed_n_dims)
+        if len(X) > n_told:          # constant-liar rows appended by ask(n_points=k)
+            Xt = np.concatenate([Xt, self.space.transform(X[n_told:])])
         ya = np.asarray(y, dtype=np.float64)
         base = np.atleast_1d(np.asarray(self._default_ls(), dtype=np.float64))
         eng = self._get_engine(base)
@@ -81,10 +93,21 @@ class Optimizer:
                     lmls.append(-np.inf)
             eng.length_scale = base * mults[int(np.argmax(lmls))]
         eng.tell(Xt, ya)
-        cand = self.space.rvs_transformed(self.n_points, self.rng, np.float32)
-        best = eng.ask(cand)
+        if self.candidate_backend == "torch":
+            import torch
+            dev = torch.device("cuda", self.device)
+            if self._tgen is None:
+                self._tgen = torch.Generator(device=dev)
+                self._tgen.manual_seed(int(self._seed) if self._seed is not None else int(self.rng.integers(0, 2 ** 31)))
+            cand = self.space.rvs_transformed_torch(self.n_points, self._tgen, dev)
+            best = eng.ask(cand)
+            row = cand[best.index:best.index + 1].to(torch.float64).cpu().numpy()
+        else:
+            cand = self.space.rvs_transformed(self.n_points, self.rng, np.float32)
+            best = eng.ask(cand)
+            row = cand[best.index:best.index + 1].astype(np.float64)
         self.last_best = best
-        return self.space.inverse_transform(cand[best.index:best.index + 1].astype(np.float64))[0]
+        return self.space.inverse_transform(row)[0]
 
     def ask(self, n_points=None):
         if n_points is None:

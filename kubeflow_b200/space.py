@@ -102,3 +102,25 @@ class Space:
                     U[np.arange(n), c + k] = 1
             c += d.width
         return U
+
+    def rvs_transformed_torch(self, n: int, generator, device):
+        """Same distribution as ``rvs_transformed`` but sampled on the device with a seeded torch.Generator (float32 CUDA
+        tensor): at n = 1M, D = 32 the NumPy path costs ~0.25 s of host time plus a 128 MB H2D per request."""
+        import torch
+        U = torch.empty((n, self.transformed_n_dims), dtype=torch.float32, device=device)
+        c = 0
+        for d in self.dimensions:
+            if isinstance(d, Real):
+                U[:, c] = torch.rand(n, generator=generator, device=device)
+            elif isinstance(d, Integer):
+                span = d.high - d.low
+                U[:, c] = torch.randint(0, span + 1, (n,), generator=generator, device=device).to(torch.float32) / span
+            else:
+                k = torch.randint(0, len(d.categories), (n,), generator=generator, device=device)
+                if d.width == 1:
+                    U[:, c] = k.to(torch.float32)
+                else:
+                    U[:, c:c + d.width] = 0
+                    U[torch.arange(n, device=device), c + k] = 1
+            c += d.width
+        return U

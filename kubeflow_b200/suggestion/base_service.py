@@ -43,8 +43,9 @@ class BaseSkoptService:
             if trial.name in self.told_trials:
                 continue
             row = []
+            by_name = {a.name: a.value for a in trial.assignments}
             for param in self.search_space.params:
-                value = next((a.value for a in trial.assignments if a.name == param.name), None)
+                value = by_name.get(param.name)
                 if value is None:
                     raise ValueError(f"trial {trial.name!r} has no assignment for parameter {param.name!r}")
                 row.append(int(value) if param.type == INTEGER else float(value) if param.type == DOUBLE else value)

@@ -37,7 +37,9 @@ def add_suggestion_servicer(servicer, server: grpc.Server):
 
 
 def serve(servicer, port: int = DEFAULT_PORT, max_workers: int = 4, host: str = "0.0.0.0"):
-    server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
+    # a cfg3-sized request (8192 trials × 32 parameters as strings) is ~11 MB: lift gRPC's 4 MB default
+    server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers),
+                         options=[("grpc.max_receive_message_length", 1 << 28), ("grpc.max_send_message_length", 1 << 28)])
     add_suggestion_servicer(servicer, server)
     bound = server.add_insecure_port(f"{host}:{port}")
     server.start()

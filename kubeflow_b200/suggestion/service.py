@@ -23,7 +23,7 @@ logger = logging.getLogger(__name__)
 
 SKOPT_SETTINGS = ("base_estimator", "n_initial_points", "acq_func", "acq_optimizer", "random_state")
 ENGINE_SETTINGS = {"n_points": int, "kernel": str, "length_scale": float, "amplitude": float, "noise": float, "xi": float,
-                   "kappa": float, "var_mode": str, "theta_grid": int, "device": int}
+                   "kappa": float, "var_mode": str, "theta_grid": int, "device": int, "candidate_backend": str}
 
 
 def validate_skopt_settings(settings: dict) -> dict:
@@ -59,6 +59,8 @@ def validate_skopt_settings(settings: dict) -> dict:
                     raise AlgorithmSettingsError(f"kernel {v} must be rbf or matern52")
                 if name == "var_mode" and v not in ("tc", "f64", "auto"):
                     raise AlgorithmSettingsError(f"var_mode {v} must be tc, f64 or auto")
+                if name == "candidate_backend" and v not in ("torch", "numpy"):
+                    raise AlgorithmSettingsError(f"candidate_backend {v} must be torch or numpy")
                 if name in ("n_points", "theta_grid") and v < 1:
                     raise AlgorithmSettingsError(f"{name} must be >= 1, got {value}")
                 if name in ("length_scale", "amplitude") and not v > 0:
@@ -136,9 +138,9 @@ class SkoptService(_Base):
             raise AlgorithmSettingsError(f"unknown algorithm name {exp.spec.algorithm.algorithm_name}")
         search_space = HyperParameterSearchSpace.convert(exp)
         settings = validate_skopt_settings(parse_settings(exp))
-        trials = Trial.convert(request.trials)
         with self._lock:
             svc = self._services.get(exp.name)
+            trials = Trial.convert(request.trials, skip_names=svc.told_trials if svc is not None else None)
             if svc is None:
                 kw = dict(self.engine_defaults)
                 kw.update(settings)

@@ -176,6 +176,44 @@ def test_tc_variance_kernel_raw(rows, Npad, k_span):
     lib.kbo_destroy(h)
 
 
+@pytest.mark.parametrize("var_mode,tol", [("f64", 2e-7), ("tc", TOL_TC)])
+def test_multi_chunk_sweep_matches_oracle(var_mode, tol):
+    """Force the candidate grid through several scratch chunks with a ragged tail (64 MiB scratch: 16 384-row chunks in tc
+    mode at Npad = 1024, 8 192-row chunks in f64 mode) and compare every candidate with the oracle."""
+    N, M, D = 1000, 40_003, 6
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    ref = O.suggest(X, y, Xc, kind="matern52", acq="ei", **th)
+    eng = _engine(dict(kind="matern52", acq="ei", **th), var_mode, scratch_limit=64 << 20)
+    eng.tell(X, y)
+    best, mu, std, a = eng.ask(Xc, return_arrays=True)
+    err = np.abs(a.cpu().numpy() - ref["acq"]).max()
+    print(f"\n[{var_mode}] multi-chunk N={N} M={M}: max|d acq|={err:.3e}")
+    assert err <= tol
+    _check_argmax(best, ref["acq"], tol)
+    b_host, t = eng.suggest_host(X, y, Xc)
+    assert t["chunks"] >= 3 and b_host.index == eng.ask(Xc).index
+    eng.close()
+
+
+@pytest.mark.parametrize("D", [1, 17, 64, 130])
+def test_dimension_sweep(D):
+    """D below, across and above the 32-dimension slab of the K* kernel (and D > 128: two+ slabs with a ragged last one)."""
+    N, M = 150, 600
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    ls = np.linspace(0.7, 1.4, D) * th["length_scale"]          # anisotropic
+    kw = dict(th, length_scale=ls)
+    ref = O.suggest(X, y, Xc, kind="rbf", acq="ei", **kw)
+    for var_mode, tol in (("f64", 1e-8), ("tc", TOL_TC)):
+        eng = _engine(dict(kind="rbf", acq="ei", **kw), var_mode)
+        eng.tell(X, y)
+        best, mu, std, a = eng.ask(Xc, return_arrays=True)
+        np.testing.assert_allclose(a.cpu().numpy(), ref["acq"], rtol=0, atol=tol)
+        _check_argmax(best, ref["acq"], tol)
+        eng.close()
+
+
 def test_ties_duplicates_and_sharding():
     X, y, Xc = O.synthetic(96, 1000, 4)
     th = O.theta_of_record(4)

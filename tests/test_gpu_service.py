@@ -50,7 +50,8 @@ def test_optimizer_matches_oracle_argmax_on_transformed_space():
     from kubeflow_b200.space import Integer, Real, Space
     from oracle import gp_oracle as O
     sp = Space([Real(0.0, 2.0), Real(-1.0, 1.0), Integer(1, 9)])
-    opt = Optimizer(sp, n_initial_points=5, acq_func="EI", random_state=11, n_points=5000, kernel="matern52", noise=1e-3)
+    opt = Optimizer(sp, n_initial_points=5, acq_func="EI", random_state=11, n_points=5000, kernel="matern52", noise=1e-3,
+                    candidate_backend="numpy")
     r = np.random.default_rng(0)
     pts = [[float(r.uniform(0, 2)), float(r.uniform(-1, 1)), int(r.integers(1, 10))] for _ in range(20)]
     ys = [(p[0] - 1.2) ** 2 + p[1] ** 2 + 0.05 * (p[2] - 4) ** 2 for p in pts]
@@ -92,3 +93,25 @@ def test_cmaes_over_grpc():
     assert ei.value.code() == grpc.StatusCode.INVALID_ARGUMENT
     ch.close()
     server.stop(0)
+
+
+def test_optimizer_device_candidates_match_oracle():
+    """Default candidate backend: sampled on the device with a seeded torch.Generator; the same stream re-drawn here must
+    give the oracle the same winner."""
+    import torch
+    from kubeflow_b200.optimizer import Optimizer
+    from kubeflow_b200.space import Categorical, Integer, Real, Space
+    from oracle import gp_oracle as O
+    sp = Space([Real(0.0, 2.0), Integer(1, 9), Categorical(["a", "b", "c"])])
+    opt = Optimizer(sp, n_initial_points=4, acq_func="LCB", random_state=5, n_points=4096, kernel="rbf", noise=1e-3)
+    r = np.random.default_rng(1)
+    pts = [[float(r.uniform(0, 2)), int(r.integers(1, 10)), ["a", "b", "c"][int(r.integers(0, 3))]] for _ in range(16)]
+    ys = [(p[0] - 1.0) ** 2 + 0.1 * p[1] + (0.5 if p[2] == "b" else 0.0) for p in pts]
+    opt.tell(pts, ys)
+    x = opt.ask()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    cand = sp.rvs_transformed_torch(4096, g, torch.device("cuda", 0)).cpu().numpy().astype(np.float64)
+    assert np.allclose(cand[:, 2:5].sum(1), 1.0) and np.allclose(cand[:, 1] * 8, np.round(cand[:, 1] * 8), atol=1e-5)
+    ref = O.suggest(sp.transform(pts), np.asarray(ys), cand, kind="rbf", acq="lcb", length_scale=0.3 * np.sqrt(5), amplitude=1.0, noise=1e-3)
+    assert opt.last_best.index == ref["index"] and abs(opt.last_best.value - ref["value"]) < 1e-7
+    assert x == sp.inverse_transform(cand[ref["index"]:ref["index"] + 1])[0]
