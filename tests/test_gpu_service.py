@@ -115,3 +115,25 @@ def test_optimizer_device_candidates_match_oracle():
     ref = O.suggest(sp.transform(pts), np.asarray(ys), cand, kind="rbf", acq="lcb", length_scale=0.3 * np.sqrt(5), amplitude=1.0, noise=1e-3)
     assert opt.last_best.index == ref["index"] and abs(opt.last_best.value - ref["value"]) < 1e-7
     assert x == sp.inverse_transform(cand[ref["index"]:ref["index"] + 1])[0]
+
+
+def test_theta_grid_picks_higher_lml_length_scale():
+    """SURVEY.md §8(f)1 (first step): length scale chosen among a grid by the GPU-computed log-marginal likelihood."""
+    from kubeflow_b200.gp import GPEngine
+    from kubeflow_b200.optimizer import Optimizer
+    from kubeflow_b200.space import Real, Space
+    from oracle import gp_oracle as O
+    r = np.random.default_rng(0)
+    sp = Space([Real(0.0, 1.0), Real(0.0, 1.0)])
+    pts = r.random((60, 2)).tolist()
+    ys = [float(np.sin(25 * p[0]) + np.cos(19 * p[1])) for p in pts]        # wiggly: the default ℓ = 0.3·√2 is far too long
+    opt = Optimizer(sp, n_initial_points=5, acq_func="EI", random_state=1, n_points=2048, theta_grid=7, noise=1e-4)
+    opt.tell(pts, ys)
+    opt.ask()
+    chosen = float(opt._engine.length_scale[0])
+    base = 0.3 * np.sqrt(2)
+    assert chosen < base * 0.6
+    lml = lambda ls: O.gp_fit(np.asarray(pts), np.asarray(ys), kind="matern52", length_scale=ls, noise=1e-4)["lml"]
+    assert lml(chosen) > lml(base) + 1.0
+    grid = base * np.geomspace(0.25, 4.0, 7)
+    assert abs(chosen - grid[int(np.argmax([lml(g) for g in grid]))]) < 1e-12      # same pick as the oracle's LML over the same grid
