@@ -13,7 +13,7 @@
 #define CMA_MAXD 128
 
 struct kbo_cma {
-  int D = 0, lambda = 0, mu = 0, lam_pow2 = 0;
+  int D = 0, lambda = 0, mu = 0, lam_pow2 = 0, lam_pad = 0;  // lam_pad: λ rounded up to the 256-wide split-K slices
   uint64_t seed = 0;
   long long gen = 0;
   // strategy parameters (host copies)
@@ -122,15 +122,19 @@ __global__ void __launch_bounds__(1024) cma_sort_kernel(const double* __restrict
 }
 
 // Ys[r] = Y[order[r]];  YwT[d][r] = w°_r·Ys[r][d],  w°_r = w_r (w_r ≥ 0) or w_r·n/(‖z‖²+ε)
+// rows r >= lambda (padding up to lam_pad) are written as zeros so the split-K GEMM can use uniform 256-wide slices
 __global__ void cma_gather_kernel(const double* __restrict__ Y, const int* __restrict__ order, const double* __restrict__ w,
-                                  const double* __restrict__ zn2, int lambda, int D, double* __restrict__ Ys, double* __restrict__ YwT) {
-  const int r = blockIdx.x, src = order[r];
-  const double wr = w[r];
+                                  const double* __restrict__ zn2, int lambda, int lam_pad, int D, double* __restrict__ Ys,
+                                  double* __restrict__ YwT) {
+  const int r = blockIdx.x;
+  const bool live = r < lambda;
+  const int src = live ? order[r] : 0;
+  const double wr = live ? w[r] : 0.0;
   const double wio = wr >= 0.0 ? wr : wr * (double)D / (zn2[src] + CMA_EPS);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const double v = Y[(size_t)src * D + d];
+    const double v = live ? Y[(size_t)src * D + d] : 0.0;
     Ys[(size_t)r * D + d] = v;
-    YwT[(size_t)d * lambda + r] = wio * v;
+    YwT[(size_t)d * lam_pad + r] = wio * v;
   }
 }
 
@@ -199,13 +203,18 @@ __global__ void __launch_bounds__(1024) cma_update_kernel(const double* __restri
   }
 }
 // C ← a·C + c1·p_c p_cᵀ + cμ·R, symmetrised ((C+Cᵀ)/2 as the reference does before its eigendecomposition)
-__global__ void cma_c_finalize_kernel(double* __restrict__ C, const double* __restrict__ R, const double* __restrict__ pc,
+// R arrives as `nsl` split-K partial sums (D×D each), added here in slice order (deterministic)
+__global__ void cma_c_finalize_kernel(double* __restrict__ C, const double* __restrict__ R, int nsl, const double* __restrict__ pc,
                                       const double* __restrict__ scal, int D, double c1, double cmu) {
   const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= D || j > i) return;
   const double a = scal[CS_ALPHA_C];
-  const double v = a * 0.5 * (C[(size_t)i * D + j] + C[(size_t)j * D + i]) + c1 * pc[i] * pc[j] +
-                   cmu * 0.5 * (R[(size_t)i * D + j] + R[(size_t)j * D + i]);
+  double rij = 0.0, rji = 0.0;
+  for (int z = 0; z < nsl; z++) {
+    rij += R[(size_t)z * D * D + (size_t)i * D + j];
+    rji += R[(size_t)z * D * D + (size_t)j * D + i];
+  }
+  const double v = a * 0.5 * (C[(size_t)i * D + j] + C[(size_t)j * D + i]) + c1 * pc[i] * pc[j] + cmu * 0.5 * (rij + rji);
   C[(size_t)i * D + j] = v;
   C[(size_t)j * D + i] = v;
 }
@@ -213,6 +222,7 @@ __global__ void cma_c_finalize_kernel(double* __restrict__ C, const double* __re
 // ------------------------------------------------------------------------------------------------ eigendecomposition
 // One-sided (Hestenes) Jacobi on the columns of G = C·B_prev in shared memory (column-major, one column contiguous).
 // Round-robin ordering: D/2 disjoint column pairs per step, 16 threads per pair.  On exit column j of G is λ_j·b_j.
+// Rotations stop at |g_a·g_b| ≤ 1e-13·‖g_a‖‖g_b‖ (orthogonality of B to ~1e-13; the last quadratic sweep to 1e-16 buys nothing).
 __global__ void __launch_bounds__(1024) cma_jacobi_kernel(const double* __restrict__ G, int D, double* __restrict__ B, double* __restrict__ Dv,
                                                           double* __restrict__ scal, int max_sweeps) {
   extern __shared__ double Gt[];  // [Dp][D+1], Dp = D rounded up to even
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(1024) cma_jacobi_kernel(const double* __restri
           be += __shfl_xor_sync(0xffffffffu, be, o);
           ga_ += __shfl_xor_sync(0xffffffffu, ga_, o);
         }
-        if (real && fabs(ga_) > 1e-15 * sqrt(al * be) && al > 0.0 && be > 0.0) {
+        if (real && fabs(ga_) > 1e-13 * sqrt(al * be) && al > 0.0 && be > 0.0) {
           const double zeta = (be - al) / (2.0 * ga_);
           const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double c = rsqrt(1.0 + tt * tt), s = c * tt;
@@ -314,19 +324,22 @@ static int cma_generation_tell(kbo_handle* h, kbo_cma* c, const double* fitness,
   const int smem_sort = c->lam_pow2 * 12;
   cma_sort_kernel<<<1, 1024, smem_sort, s>>>(fitness, lam, c->lam_pow2, (int*)c->order.p, (double*)c->scal.p);
   KBO_LAUNCH_CHECK(h);
-  cma_gather_kernel<<<lam, 128, 0, s>>>((const double*)c->Y.p, (const int*)c->order.p, (const double*)c->weights.p, (const double*)c->zn2.p, lam, D,
-                                        (double*)c->Ys.p, (double*)c->YwT.p);
+  cma_gather_kernel<<<c->lam_pad, 128, 0, s>>>((const double*)c->Y.p, (const int*)c->order.p, (const double*)c->weights.p, (const double*)c->zn2.p, lam,
+                                               c->lam_pad, D, (double*)c->Ys.p, (double*)c->YwT.p);
   KBO_LAUNCH_CHECK(h);
   CmaConst k{c->mu_eff, c->c1, c->cmu, c->cm, c->c_sigma, c->d_sigma, c->cc, c->chi_n, c->wsum, c->mu, c->gen};
   cma_update_kernel<<<1, 1024, 0, s>>>((const double*)c->Ys.p, (const double*)c->weights.p, D, k, (double*)c->mean.p, (const double*)c->B.p,
                                        (const double*)c->Dv.p, (double*)c->ps.p, (double*)c->pc.p, (double*)c->scal.p, (double*)c->yw.p);
   KBO_LAUNCH_CHECK(h);
-  // R = Σ w°_i y_i y_iᵀ  (D×D = YwT[D×λ]·Ys[λ×D])
-  dgemm64_launch<false, EPI_STORE>(s, D, D, lam, (const double*)c->YwT.p, lam, (const double*)c->Ys.p, D, (double*)c->R.p, D, 1.0, 0.0, KM_FULL, 0,
-                                   TS_NONE);
+  // R = Σ w°_i y_i y_iᵀ  (D×D = YwT[D×λ]·Ys[λ×D]) as split-K over 256-sample slices: a 128×128 output is only two
+  // tiles of the GEMM, so without the split a K = 4096 product ran on 2 CTAs (337 µs); the slices fill 2·λ/256 CTAs
+  const int nsl = c->lam_pad / 256;
+  dgemm64_launch<false, EPI_STORE>(s, D, D, 256, (const double*)c->YwT.p, c->lam_pad, (const double*)c->Ys.p, D, (double*)c->R.p, D, 1.0, 0.0, KM_FULL,
+                                   0, TS_NONE, nsl, 256, 256LL * D, (long long)D * D);
   KBO_LAUNCH_CHECK(h);
   dim3 g((D + 127) / 128, D);
-  cma_c_finalize_kernel<<<g, 128, 0, s>>>((double*)c->C.p, (const double*)c->R.p, (const double*)c->pc.p, (const double*)c->scal.p, D, c->c1, c->cmu);
+  cma_c_finalize_kernel<<<g, 128, 0, s>>>((double*)c->C.p, (const double*)c->R.p, nsl, (const double*)c->pc.p, (const double*)c->scal.p, D, c->c1,
+                                          c->cmu);
   KBO_LAUNCH_CHECK(h);
   // G = C·B_prev, then Jacobi
   dgemm64_launch<false, EPI_STORE>(s, D, D, D, (const double*)c->C.p, D, (const double*)c->B.p, D, (double*)c->G.p, D, 1.0, 0.0, KM_FULL, 0, TS_NONE);
@@ -377,6 +390,7 @@ int kbo_cma_create(kbo_handle* h, kbo_cma** out, int32_t D, int32_t lambda, cons
   int p2 = 1;
   while (p2 < lambda) p2 <<= 1;
   c->lam_pow2 = p2;
+  c->lam_pad = round_up(lambda, 256);
   // strategy parameters (tutorial Table 1; active weights as in `cmaes`)
   std::vector<double> w(lambda);
   const int mu = c->mu, n = D;
@@ -405,12 +419,12 @@ int kbo_cma_create(kbo_handle* h, kbo_cma** out, int32_t D, int32_t lambda, cons
   c->d_sigma = 1 + 2 * (t > 0 ? t : 0) + c->c_sigma;
   c->cc = (4 + mu_eff / n) / (n + 4 + 2 * mu_eff / n);
   c->chi_n = sqrt((double)n) * (1.0 - 1.0 / (4.0 * n) + 1.0 / (21.0 * n * n));
-  const size_t LD = (size_t)lambda * D;
+  const size_t LD = (size_t)lambda * D, LPD = (size_t)c->lam_pad * D;
   int r = KBO_OK;
   auto R_ = [&](DevBuf& b, size_t bytes) { if (r == KBO_OK) r = kbo_reserve(h, b, bytes); };
   R_(c->mean, 8 * D); R_(c->C, 8 * (size_t)D * D); R_(c->B, 8 * (size_t)D * D); R_(c->Dv, 8 * D); R_(c->ps, 8 * D); R_(c->pc, 8 * D);
-  R_(c->weights, 8 * lambda); R_(c->Z, 8 * (LD + 2)); R_(c->Zs, 8 * LD); R_(c->Y, 8 * LD); R_(c->Ys, 8 * LD); R_(c->YwT, 8 * LD);
-  R_(c->zn2, 8 * lambda); R_(c->order, 4 * lambda); R_(c->R, 8 * (size_t)D * D); R_(c->G, 8 * (size_t)D * D); R_(c->scal, 8 * CS_COUNT);
+  R_(c->weights, 8 * lambda); R_(c->Z, 8 * (LD + 2)); R_(c->Zs, 8 * LD); R_(c->Y, 8 * LD); R_(c->Ys, 8 * LPD); R_(c->YwT, 8 * LPD);
+  R_(c->zn2, 8 * lambda); R_(c->order, 4 * lambda); R_(c->R, 8 * (size_t)D * D * (c->lam_pad / 256)); R_(c->G, 8 * (size_t)D * D); R_(c->scal, 8 * CS_COUNT);
   R_(c->yw, 8 * D);
   if (r != KBO_OK) { delete c; return r; }
   double sc[CS_COUNT] = {sigma0, 0, 0, 0, 0, 0, 0, 0};

@@ -14,11 +14,14 @@
 // shared stores are conflict-free, and the next 32-dimension slab is prefetched into registers while the current one
 // is consumed (one __syncthreads per slab).  Epilogue per element: d² → branch-free FP64 kernel value (ktab.cuh) → μ FMA →
 // MODE 0: fp64 K* (chunk × ldks)   MODE 1: fp16 hi/lo planes (chunk_pad × Npad).
+#ifndef KBO_CM_MINB
+#define KBO_CM_MINB 2
+#endif
 #define CM_BM 128
 #define CM_BN 64
 #define CM_DC 32
 template <typename XT, typename MT, int MODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, KBO_CM_MINB)
 cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* __restrict__ inv_ls, int n_ls,
                   const double* __restrict__ XsT, int ldx, const double* __restrict__ nx, int N, const double* __restrict__ alpha, int kind,
                   double amp, double* __restrict__ Ks64, int ldks, __half* __restrict__ Ksh,
