@@ -63,8 +63,14 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                          "(nvcc, sm_100a). There is no CPU fallback.")
+        # a fresh checkout has no built library (it is git-ignored): build it in-tree if nvcc is here, else fail loudly
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing and could not be built: run `python -c 'import __graft_entry__ as g; "
+                              "g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     pd = C.POINTER(C.c_double)

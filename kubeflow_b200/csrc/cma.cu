@@ -223,8 +223,11 @@ __global__ void cma_c_finalize_kernel(double* __restrict__ C, const double* __re
 // One-sided (Hestenes) Jacobi on the columns of G = C·B_prev in shared memory (column-major, one column contiguous).
 // Round-robin ordering: D/2 disjoint column pairs per step, 16 threads per pair.  On exit column j of G is λ_j·b_j.
 // Rotations stop at |g_a·g_b| ≤ 1e-13·‖g_a‖‖g_b‖ (orthogonality of B to ~1e-13; the last quadratic sweep to 1e-16 buys nothing).
-__global__ void __launch_bounds__(1024) cma_jacobi_kernel(const double* __restrict__ G, int D, double* __restrict__ B, double* __restrict__ Dv,
+// DT = compile-time D (128: fully unrolled 8-row loops, loads pipelined) or 0 = runtime D.
+template <int DT>
+__global__ void __launch_bounds__(1024) cma_jacobi_kernel(const double* __restrict__ G, int Drt, double* __restrict__ B, double* __restrict__ Dv,
                                                           double* __restrict__ scal, int max_sweeps) {
+  const int D = DT > 0 ? DT : Drt;
   extern __shared__ double Gt[];  // [Dp][D+1], Dp = D rounded up to even
   __shared__ int s_rot;
   const int Dp = (D + 1) & ~1, ldg = D + 1;
@@ -256,13 +259,15 @@ __global__ void __launch_bounds__(1024) cma_jacobi_kernel(const double* __restri
         double* ga = Gt + a * ldg;
         double* gb = Gt + b * ldg;
         double al = 0.0, be = 0.0, ga_ = 0.0;
-        if (real)
+        if (real) {
+#pragma unroll
           for (int i = q; i < D; i += 16) {
             const double x = ga[i], y = gb[i];
             al = fma(x, x, al);
             be = fma(y, y, be);
             ga_ = fma(x, y, ga_);
           }
+        }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
           al += __shfl_xor_sync(0xffffffffu, al, o);
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(1024) cma_jacobi_kernel(const double* __restri
           const double zeta = (be - al) / (2.0 * ga_);
           const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double c = rsqrt(1.0 + tt * tt), s = c * tt;
+#pragma unroll
           for (int i = q; i < D; i += 16) {
             const double x = ga[i], y = gb[i];
             ga[i] = c * x - s * y;
@@ -345,7 +351,10 @@ static int cma_generation_tell(kbo_handle* h, kbo_cma* c, const double* fitness,
   dgemm64_launch<false, EPI_STORE>(s, D, D, D, (const double*)c->C.p, D, (const double*)c->B.p, D, (double*)c->G.p, D, 1.0, 0.0, KM_FULL, 0, TS_NONE);
   KBO_LAUNCH_CHECK(h);
   const int Dp = (D + 1) & ~1;
-  cma_jacobi_kernel<<<1, 1024, sizeof(double) * Dp * (D + 1), s>>>((const double*)c->G.p, D, (double*)c->B.p, (double*)c->Dv.p, (double*)c->scal.p, 30);
+  if (D == 128)
+    cma_jacobi_kernel<128><<<1, 1024, sizeof(double) * Dp * (D + 1), s>>>((const double*)c->G.p, D, (double*)c->B.p, (double*)c->Dv.p, (double*)c->scal.p, 30);
+  else
+    cma_jacobi_kernel<0><<<1, 1024, sizeof(double) * Dp * (D + 1), s>>>((const double*)c->G.p, D, (double*)c->B.p, (double*)c->Dv.p, (double*)c->scal.p, 30);
   KBO_LAUNCH_CHECK(h);
   c->gen++;
   c->asked = false;
@@ -432,7 +441,8 @@ int kbo_cma_create(kbo_handle* h, kbo_cma** out, int32_t D, int32_t lambda, cons
   cudaMemcpy(c->weights.p, w.data(), 8 * lambda, cudaMemcpyHostToDevice);
   cudaMemcpy(c->scal.p, sc, sizeof sc, cudaMemcpyHostToDevice);
   cma_init_kernel<<<D, 128>>>((double*)c->C.p, (double*)c->B.p, (double*)c->Dv.p, (double*)c->ps.p, (double*)c->pc.p, D);
-  cudaFuncSetAttribute(cma_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CMA_MAXD * (CMA_MAXD + 1)));
+  cudaFuncSetAttribute(cma_jacobi_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CMA_MAXD * (CMA_MAXD + 1)));
+  cudaFuncSetAttribute(cma_jacobi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CMA_MAXD * (CMA_MAXD + 1)));
   cudaFuncSetAttribute(cma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
   KBO_CUDA(h, cudaDeviceSynchronize());
   *out = c;
