@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(1024) cma_update_kernel(const double* __restri
                                                           double* __restrict__ mean, const double* __restrict__ B,
                                                           const double* __restrict__ Dv, double* __restrict__ ps, double* __restrict__ pc,
                                                           double* __restrict__ scal, double* __restrict__ yw_out) {
-  __shared__ double yw[CMA_MAXD], u[CMA_MAXD], c2[CMA_MAXD], red[1024];
+  __shared__ double yw[CMA_MAXD], u[CMA_MAXD], red[1024];
   __shared__ double s_norm;
   const int t = threadIdx.x;
   // y_w = Σ_{r<μ} w_r Ys[r]: 1024/D threads per coordinate, fixed-order combine
@@ -180,7 +180,6 @@ __global__ void __launch_bounds__(1024) cma_update_kernel(const double* __restri
   if (t < D) {
     double a = 0.0;
     for (int j = 0; j < D; j++) a = fma(B[(size_t)t * D + j], u[j], a);
-    c2[t] = a;
     const double v = (1.0 - k.c_sigma) * ps[t] + sqrt(k.c_sigma * (2.0 - k.c_sigma) * k.mu_eff) * a;
     ps[t] = v;
     red[t] = v * v;
