@@ -63,13 +63,13 @@ class SuggestionStub:
 def main():
     from .cmaes_service import CmaesService
     from .hyperband import HyperbandService
-    from .service import DispatchService, RandomService, SkoptService
+    from .service import DispatchService, RandomService, SkoptService, SobolService
     ap = argparse.ArgumentParser()
     ap.add_argument("--port", type=int, default=DEFAULT_PORT)
     ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args()
     logging.basicConfig(level=logging.INFO)
-    server, port = serve(DispatchService([SkoptService({"device": args.device}), RandomService(), CmaesService(), HyperbandService()]), args.port)
+    server, port = serve(DispatchService([SkoptService({"device": args.device}), RandomService(), SobolService(), CmaesService(), HyperbandService()]), args.port)
     logging.info("api.v1.beta1.Suggestion listening on :%d", port)
     server.wait_for_termination()
 

@@ -193,6 +193,67 @@ class RandomService(_Base):
         return _reply_from([BaseSkoptService.convert(ss, p) for p in pts])
 
 
+class SobolService(_Base):
+    """Quasi-random search over the feasible space (Katib algorithm ``sobol``, the second sampler of the goptuna service;
+    SURVEY.md §2 row 18).  Scrambled Sobol points from SciPy's QMC engine, mapped through the same space transform as every
+    other algorithm here; stateless across calls by skipping the points already handed out (= number of trials seen +
+    number requested so far).  CPU only — there is no arithmetic to accelerate."""
+    algorithm_names = ("sobol",)
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._issued = {}
+
+    def validate(self, experiment):
+        if experiment.spec.algorithm.algorithm_name != "sobol":
+            raise AlgorithmSettingsError(f"unknown algorithm name {experiment.spec.algorithm.algorithm_name}")
+        ss = HyperParameterSearchSpace.convert(experiment)
+        for p in ss.params:
+            if p.type in ("categorical", "discrete") and len(p.list) < 1:
+                raise AlgorithmSettingsError(f"parameter {p.name!r}: empty feasible list")
+        for k, v in parse_settings(experiment).items():
+            if k != "random_state":
+                raise AlgorithmSettingsError(f"unknown setting {k} for algorithm sobol")
+            try:
+                if int(v) < 0:
+                    raise ValueError
+            except ValueError:
+                raise AlgorithmSettingsError(f"random_state should be great or equal than zero, got {v}")
+
+    def get_suggestions(self, request):
+        from scipy.stats import qmc
+        from ..space import Categorical, Integer, Real, Space
+        from .base_service import BaseSkoptService
+        from .internal import DOUBLE, INTEGER
+        exp = request.experiment
+        ss = HyperParameterSearchSpace.convert(exp)
+        st = parse_settings(exp)
+        n = max(int(request.current_request_number), 0)
+        with self._lock:
+            start = self._issued.get(exp.name, 0)
+            self._issued[exp.name] = start + n
+        if n == 0:
+            return _reply_from([])
+        eng = qmc.Sobol(d=len(ss.params), scramble=True, seed=int(st.get("random_state", 0)))
+        if start:
+            eng.fast_forward(start)
+        U = eng.random(n)
+        dims = [Integer(int(p.min), int(p.max), p.name) if p.type == INTEGER else Real(float(p.min), float(p.max), p.name)
+                if p.type == DOUBLE else Categorical(list(p.list), p.name) for p in ss.params]
+        pts = []
+        for u in U:
+            pt = []
+            for d, v in zip(dims, u):
+                if isinstance(d, Categorical):
+                    pt.append(d.categories[min(int(v * len(d.categories)), len(d.categories) - 1)])
+                elif isinstance(d, Integer):
+                    pt.append(min(d.low + int(v * (d.high - d.low + 1)), d.high))
+                else:
+                    pt.append(d.low + float(v) * (d.high - d.low))
+            pts.append(pt)
+        return _reply_from([BaseSkoptService.convert(ss, p) for p in pts])
+
+
 class DispatchService(_Base):
     """One endpoint for several algorithms (upstream runs one Deployment per algorithm image; this routes by name)."""
 
