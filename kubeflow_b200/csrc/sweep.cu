@@ -218,6 +218,11 @@ __device__ __forceinline__ T acq_value(T mun, T varn, int acq, T ymean, T ystd, 
 //   Numerical Recipes §6.2 (`erfcc`): FRACTIONAL error ≤ 1.2e-7 everywhere, so candidates whose EI is ~1e-30 still rank
 //   correctly (an absolute-error Φ — Abramowitz–Stegun 26.2.17 — mis-ranked that tail; tests/test_gpu_parity.py edge cases),
 //   at ~16 instructions instead of erfcf's ~35.  |ΔEI| ≲ 3e-7 for |imp| ≲ 4; the fp64 instantiation keeps erfc/exp.
+__device__ __forceinline__ float kbo_ex2_ftz(float x) {   // MUFU.EX2 alone; results below 2^-126 flush to zero
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float kbo_erfc_nonneg_f32(float x) {
   const float t = __fdividef(1.f, fmaf(0.5f, x, 1.f));
   float p = 0.17087277f;
@@ -230,7 +235,7 @@ __device__ __forceinline__ float kbo_erfc_nonneg_f32(float x) {
   p = fmaf(p, t, 0.37409196f);
   p = fmaf(p, t, 1.00002368f);
   p = fmaf(p, t, -1.26551223f);
-  return t * exp2f(1.44269504088896340736f * fmaf(-x, x, p));
+  return t * kbo_ex2_ftz(1.44269504088896340736f * fmaf(-x, x, p));
 }
 template <int ACQ>
 __device__ __forceinline__ float acq_value_f32(float mun, float varn, float ymean, float ystd, float yopt, float xi, float kappa) {
@@ -244,7 +249,7 @@ __device__ __forceinline__ float acq_value_f32(float mun, float varn, float ymea
   const float q = 0.5f * kbo_erfc_nonneg_f32(0.70710678118654752440f * fabsf(z));   // tail beyond |z|
   const float cdf = z <= 0.f ? q : 1.f - q;
   if (ACQ == KBO_ACQ_PI) return cdf;
-  const float pdf = 0.3989422804014327f * exp2f(-0.72134752044448170368f * z * z);
+  const float pdf = 0.3989422804014327f * kbo_ex2_ftz(-0.72134752044448170368f * z * z);
   return fmaf(imp, cdf, sd * pdf);
 }
 
@@ -294,6 +299,28 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
   auto process4 = [&](int64_t base, const T (&m4)[4], const T (&v4)[4]) {
     if (base >= M) return;
     const bool full = base + 3 < M;
+    if (fast32 && full) {
+      // the hot path: four values, one vector store, ONE compare against the running best per group (the first maximum
+      // inside the group is located only when the group wins) — ~40 instructions per candidate in total
+      float a4[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        a4[q] = acq_value_f32<(FAST_ACQ >= 0 ? FAST_ACQ : 0)>((float)m4[q], (float)v4[q], (float)ym, (float)ys, (float)yo, (float)x, (float)kp);
+      if (acq_out32) __stcs(reinterpret_cast<float4*>(acq_out32 + base), make_float4(a4[0], a4[1], a4[2], a4[3]));
+      if (acq_out) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) acq_out[base + q] = (double)a4[q];
+      }
+      const float gm = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));   // fmaxf ignores NaN operands
+      if ((T)gm > tbest || tidx == 0x7fffffffffffffffLL) {
+        const int q = a4[0] == gm ? 0 : a4[1] == gm ? 1 : a4[2] == gm ? 2 : a4[3] == gm ? 3 : -1;   // −1: all four are NaN
+        if (q >= 0) {
+          tbest = (T)gm;
+          tidx = base + q;
+        }
+      }
+      return;
+    }
     float o4[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -326,13 +353,25 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
       }
     }
   };
-  for (int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; base < M; base += 2 * stride) {
+  // software-pipelined stream: the loads of trip t+1 (two groups of 4 candidates, 4×16 B) are in flight while trip t is computed
+  {
+    int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     T ma[4], va[4], mb[4], vb[4];
-    load4(base, ma, va);
-    const int64_t base2 = base + stride;
-    if (base2 < M) load4(base2, mb, vb);
-    process4(base, ma, va);
-    if (base2 < M) process4(base2, mb, vb);
+    if (base < M) load4(base, ma, va);
+    if (base + stride < M) load4(base + stride, mb, vb);
+    while (base < M) {
+      const int64_t nbase = base + 2 * stride;
+      T na[4], nva[4], nb[4], nvb[4];
+      if (nbase < M) load4(nbase, na, nva);
+      if (nbase + stride < M) load4(nbase + stride, nb, nvb);
+      process4(base, ma, va);
+      if (base + stride < M) process4(base + stride, mb, vb);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        ma[q] = na[q]; va[q] = nva[q]; mb[q] = nb[q]; vb[q] = nvb[q];
+      }
+      base = nbase;
+    }
   }
   if (tidx != 0x7fffffffffffffffLL) {
     bv = (double)tbest;
@@ -417,8 +456,8 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
 }
 
 static int acq_grid(kbo_handle* h, int64_t M) {
-  int64_t g = (M + 2047) / 2048;   // two groups of 4 candidates per thread per trip
-  const int64_t cap = (int64_t)h->sm_count * 4;
+  int64_t g = (M + 1023) / 1024;   // small grids: one group of 4 candidates per thread (shortest dependent chain); large: capped, streamed
+  const int64_t cap = (int64_t)h->sm_count * 8;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
