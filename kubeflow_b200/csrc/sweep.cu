@@ -456,7 +456,7 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
 }
 
 static int acq_grid(kbo_handle* h, int64_t M) {
-  int64_t g = (M + 1023) / 1024;   // small grids: one group of 4 candidates per thread (shortest dependent chain); large: capped, streamed
+  int64_t g = (M + 2047) / 2048;   // two groups of 4 candidates per thread per trip (1024 per CTA measured slower at 1M: more partials/atomics)
   const int64_t cap = (int64_t)h->sm_count * 8;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
