@@ -49,8 +49,13 @@ def tc_traffic(rows_per_launch):
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
-    return {"bytes_per_launch": (d["dram_read_bytes"] + d["dram_write_bytes"]) * rows_per_launch / d["rows"], "source": d["source"],
-            "captured_rows_per_launch": d["rows"]}
+    out = {"bytes_per_launch": (d["dram_read_bytes"] + d["dram_write_bytes"]) * rows_per_launch / d["rows"], "source": d["source"],
+           "captured_rows_per_launch": d["rows"]}
+    for k in ("algorithmic_bytes_per_launch", "ncu_tensor_pipe_active_pct_of_active", "ncu_dram_pct_of_peak", "ncu_l2_hit_pct",
+              "why_traffic_exceeds_algorithmic"):
+        if k in d:
+            out[k] = d[k]
+    return out
 
 
 class ClockSampler:
