@@ -370,7 +370,7 @@ def main():
                     "h2d_bytes_per_step": int(X.nbytes + y.nbytes + Xc.nbytes), "d2h_bytes_per_step": 32},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "tc_variance_kernel", "achieved": achieved_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "tc_variance_pair_kernel" if os.environ.get("KBO_TC_PAIR", "1") != "0" else "tc_variance_kernel", "achieved": achieved_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s",
                          "frac": achieved_tf / pk["tf_sus"], "peak_source": f"bf16_tflops_sustained, {pk['src']}",
                          "issued_mma_tflops": 3.0 * achieved_tf * (1.0 + 256.0 / N), "traffic": tc_traffic(rows_per_launch),
                          "launch_ms": var_launch_ms, "launches_per_step": chunks, "flops_per_launch": flops_launch},

@@ -7,7 +7,9 @@
 // fp32 TMEM accumulator: bf16/fp16 single-pass moves σ² by 1e-2 and bf16×3 by 1e-5..1e-4 (measured,
 // DESIGN.md §numerics) — fp16×3 stays at ~3e-7.
 //
-// CTA = 128 candidate rows (TMEM lanes) × all j-tiles of 256 trial columns, walked in order; for j-tile t only
+// Two kernels share the pipeline below: tc_variance_kernel (one CTA per 128-row panel, all j-tiles) and the default
+// tc_variance_pair_kernel (a 2-CTA cluster per panel, j-tiles split by parity, K* chunks TMA-multicast to both CTAs).
+// CTA = 128 candidate rows (TMEM lanes) × its j-tiles of 256 trial columns, walked in order; for j-tile t only
 // k < 256(t+1) is issued (W is lower triangular).  K is consumed in 32-wide chunks, 4-stage TMA→smem ring:
 //   warp 0     TMA producer (A hi/lo 128×32, B hi/lo 256×32 per stage, SWIZZLE_64B, mbarrier expect_tx)
 //   warp 1     MMA issuer  (single thread, tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16)
@@ -18,6 +20,7 @@
 //              contention between the drains and the MMAs' own accumulator traffic, not epilogue latency (8 vs 16
 //              epilogue warps time the same), so k_span trades accuracy against tensor time directly.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "kbo_internal.cuh"
 
@@ -275,6 +278,213 @@ tc_variance_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Cluster variant: TWO CTAs (a 2-CTA cluster, one SM each) share one 128-row candidate panel.  The j-tiles are split by
+// parity (CTA r owns tiles 2p + r) and both CTAs walk the K chunks of a tile pair in lockstep, so every A (K*) chunk is
+// fetched ONCE and TMA-multicast into both CTAs' shared memory (each CTA issues the load for its 64-row half with
+// ctaMask = 0b11); B (W) chunks stay private.  That halves the K* panel re-reads — the kernel's dominant DRAM/L2 traffic.
+//   full[st]  (per CTA): 1 arrival (own producer's expect_tx) + A bytes from both multicast halves + own B bytes
+//   empty[st] (per CTA): 2 arrivals — each CTA's MMA thread commits with .multicast::cluster to BOTH CTAs' barrier, so a
+//             stage is refilled only when both consumers are done with it.
+// Per-row Σv² of the two CTAs' tile sets goes to part[rank][row]; tc_pair_finish_kernel adds them in a fixed order.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_variance_pair_kernel(const __grid_constant__ CUtensorMap tmAh64, const __grid_constant__ CUtensorMap tmAl64,
+                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int n_jtiles,
+                        int span_chunks, double* __restrict__ part /* [2][rows] raw Σv² (scaled units) */, int64_t rows) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* ring = (unsigned char*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  TcSmem* S = (TcSmem*)(ring + TC_STAGES * TC_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = (blockIdx.x >> 1) * TC_BM;
+  const int n_pairs = (n_jtiles + 1) >> 1;
+  constexpr int CPT = TC_BN / TC_BK;  // chunks per 256-column block of K
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh64) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl64) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+    for (int i = 0; i < TC_STAGES; i++) {
+      mbar_init(smem_u32(&S->full[i]), 1);
+      mbar_init(smem_u32(&S->empty[i]), 2);  // both CTAs' MMA threads release a stage
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(smem_u32(&S->tmem_full[i]), 1);
+      mbar_init(smem_u32(&S->tmem_empty[i]), TC_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything is multicast into them
+  tc_fence_after();
+  const uint32_t tmem_base = S->tmem_base;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ===========================================
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int p = 0; p < n_pairs; p++) {
+        const int my_tile = 2 * p + (int)rank;
+        const int my_nch = my_tile < n_jtiles ? (my_tile + 1) * CPT : 0;
+        const int nch = min(2 * p + 2, n_jtiles) * CPT;  // the pair streams the longer of its two K ranges
+        for (int ch = 0; ch < nch; ch++, c++) {
+          const uint32_t st = c % TC_STAGES, use = c / TC_STAGES;
+          mbar_wait(smem_u32(&S->empty[st]), (use & 1) ^ 1, 11);
+          const uint32_t bar = smem_u32(&S->full[st]);
+          mbar_expect_tx(bar, 2 * TC_A_BYTES + (ch < my_nch ? 2 * TC_B_BYTES : 0));
+          const uint32_t base = smem_u32(ring + st * TC_STAGE_BYTES);
+          const int k0 = ch * TC_BK;
+          const uint32_t half_off = rank * (TC_A_BYTES / 2);  // rows 64·rank … of the 128-row A tile
+          tma_load_2d_mc(base + half_off, &tmAh64, bar, k0, m0 + 64 * (int)rank, (uint16_t)3);
+          tma_load_2d_mc(base + TC_A_BYTES + half_off, &tmAl64, bar, k0, m0 + 64 * (int)rank, (uint16_t)3);
+          if (ch < my_nch) {
+            tma_load_2d(base + 2 * TC_A_BYTES, &tmBh, bar, k0, my_tile * TC_BN);
+            tma_load_2d(base + 2 * TC_A_BYTES + TC_B_BYTES, &tmBl, bar, k0, my_tile * TC_BN);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =============================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16_m128_n256();
+      uint32_t c = 0, span = 0;
+      for (int p = 0; p < n_pairs; p++) {
+        const int my_tile = 2 * p + (int)rank;
+        const int my_nch = my_tile < n_jtiles ? (my_tile + 1) * CPT : 0;
+        const int nch = min(2 * p + 2, n_jtiles) * CPT;
+        for (int ch0 = 0; ch0 < nch; ch0 += span_chunks) {
+          const int che = min(nch, ch0 + span_chunks);
+          const bool live = ch0 < my_nch;  // this span holds MMAs of my tile
+          uint32_t buf = 0, d_tmem = 0;
+          if (live) {
+            buf = span & 1;
+            mbar_wait(smem_u32(&S->tmem_empty[buf]), ((span >> 1) & 1) ^ 1, 12);
+            tc_fence_after();
+            d_tmem = tmem_base + buf * TC_BN;
+          }
+          for (int ch = ch0; ch < che; ch++, c++) {
+            const uint32_t st = c % TC_STAGES, suse = c / TC_STAGES;
+            mbar_wait(smem_u32(&S->full[st]), suse & 1, 13);
+            tc_fence_after();
+            if (ch < my_nch) {
+              const uint32_t base = smem_u32(ring + st * TC_STAGE_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; k++) {
+                const uint32_t koff = k * 32;
+                const uint64_t ah = umma_desc_sw64(base + koff);
+                const uint64_t al = umma_desc_sw64(base + TC_A_BYTES + koff);
+                const uint64_t bh = umma_desc_sw64(base + 2 * TC_A_BYTES + koff);
+                const uint64_t bl = umma_desc_sw64(base + 2 * TC_A_BYTES + TC_B_BYTES + koff);
+                umma_f16(d_tmem, al, bh, idesc, (ch > ch0 || k > 0) ? 1u : 0u);
+                umma_f16(d_tmem, ah, bl, idesc, 1u);
+                umma_f16(d_tmem, ah, bh, idesc, 1u);
+              }
+            }
+            umma_commit_mc(smem_u32(&S->empty[st]), (uint16_t)3);  // release the stage in BOTH CTAs
+          }
+          if (live) {
+            umma_commit(smem_u32(&S->tmem_full[buf]));
+            span++;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue warps =========================================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int cg = ew >> 2;
+    const int row = quarter * 32 + lane;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) acc[i] = 0.f;
+    double rowacc = 0.0;
+    uint32_t span = 0;
+    for (int p = 0; p < n_pairs; p++) {
+      const int my_tile = 2 * p + (int)rank;
+      if (my_tile >= n_jtiles) break;
+      const int my_nch = (my_tile + 1) * CPT;
+      for (int ch0 = 0; ch0 < my_nch; ch0 += span_chunks, span++) {
+        const uint32_t buf = span & 1, use = span >> 1;
+        mbar_wait(smem_u32(&S->tmem_full[buf]), use & 1, 14);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC_BN + cg * 64;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint32_t r[16];
+          tmem_ld16(taddr + q * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i++) acc[q * 16 + i] += __uint_as_float(r[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&S->tmem_empty[buf]));
+      }
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        s0 = fmaf(acc[i], acc[i], s0);
+        s1 = fmaf(acc[i + 1], acc[i + 1], s1);
+        s2 = fmaf(acc[i + 2], acc[i + 2], s2);
+        s3 = fmaf(acc[i + 3], acc[i + 3], s3);
+        acc[i] = acc[i + 1] = acc[i + 2] = acc[i + 3] = 0.f;
+      }
+      rowacc += (double)((s0 + s1) + (s2 + s3));
+    }
+    __shared__ double partsum[4][TC_BM];
+    partsum[cg][row] = rowacc;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+    if (cg == 0) part[(size_t)rank * rows + m0 + row] = ((partsum[0][row] + partsum[1][row]) + partsum[2][row]) + partsum[3][row];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+__global__ void tc_pair_finish_kernel(const double* __restrict__ part, int64_t rows, const double* __restrict__ w_scale, double amp,
+                                      float* __restrict__ var_out, double* __restrict__ sumsq_out) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const double sc = w_scale[1];
+  const double tot = (part[m] + part[rows + m]) * sc * sc;
+  var_out[m] = (float)(amp - tot);
+  if (sumsq_out) sumsq_out[m] = tot;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -313,7 +523,22 @@ int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows,
   KBO_TRY(encode_map(h, &tmBl, Wl, (uint64_t)Npad, (uint64_t)Npad, TC_BN));
   if (!h->attr_tc) {
     KBO_CUDA(h, cudaFuncSetAttribute(tc_variance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    KBO_CUDA(h, cudaFuncSetAttribute(tc_variance_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     h->attr_tc = true;
+  }
+  // default: the 2-CTA cluster / TMA-multicast kernel (half the K* panel re-reads); KBO_TC_PAIR=0 selects the single-CTA one
+  static const int pair_mode = getenv("KBO_TC_PAIR") ? atoi(getenv("KBO_TC_PAIR")) : 1;
+  if (pair_mode) {
+    CUtensorMap tmAh64, tmAl64;
+    KBO_TRY(encode_map(h, &tmAh64, Ksh, (uint64_t)Npad, (uint64_t)rows, 64));
+    KBO_TRY(encode_map(h, &tmAl64, Ksl, (uint64_t)Npad, (uint64_t)rows, 64));
+    KBO_TRY(kbo_reserve(h, h->part, sizeof(double) * 2 * (size_t)rows));
+    tc_variance_pair_kernel<<<(unsigned)(2 * (rows / TC_BM)), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh64, tmAl64, tmBh, tmBl, Npad / TC_BN, span_chunks,
+                                                                                             (double*)h->part.p, rows);
+    KBO_LAUNCH_CHECK(h);
+    tc_pair_finish_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>((const double*)h->part.p, rows, w_scale_dev, amp, var_out, sumsq_out);
+    KBO_LAUNCH_CHECK(h);
+    return KBO_OK;
   }
   tc_variance_kernel<<<(unsigned)(rows / TC_BM), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh, tmAl, tmBh, tmBl, Npad / TC_BN, span_chunks, w_scale_dev,
                                                                                 amp, var_out, sumsq_out);
