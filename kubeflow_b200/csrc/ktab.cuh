@@ -32,12 +32,12 @@ __device__ __forceinline__ double kbo_exp_nonpos(double x) {
   return ni < -1020 ? 0.0 : r;
 }
 
-// branch-free sqrt for x >= 0: fp32 MUFU.RSQ seed (23 bits), two Newton steps in FP64, one final correction (≤ 1 ulp).
+// branch-free sqrt for x >= 0: fp32 MUFU.RSQ seed (~2^-22), ONE Newton step for 1/sqrt in FP64 (→ ~1e-13), then the
+// Newton correction on s = x·y itself, which squares the error again (≤ 1 ulp).
 // x is floored at 1e-30 so the seed is finite; sqrt(0) comes out as 1e-15, i.e. k(0) = 1 − O(1e-30).
 __device__ __forceinline__ double kbo_sqrt_nonneg(double x) {
   x = fmax(x, 1e-30);
   double y = (double)rsqrtf((float)x);
-  y = y * fma(-0.5 * x, y * y, 1.5);
   y = y * fma(-0.5 * x, y * y, 1.5);
   const double s = x * y;
   return fma(fma(-s, s, x), 0.5 * y, s);
