@@ -102,6 +102,10 @@ const char* kbo_last_error(const kbo_handle* h);
 /* cap (bytes) on the per-sweep K* scratch; default 4 GiB.  Determines the candidate chunk size (rounded down to a
  * multiple of sm_count*128 rows so every launch is a whole number of waves). */
 int kbo_set_scratch_limit(kbo_handle* h, uint64_t bytes);
+/* tensor-core variance kernel variant: 1 (default) = 2-CTA cluster per 128-row panel with TMA multicast of the K* chunks,
+ * 0 = one CTA per panel.  Same arithmetic, same results to the last bit per j-tile; the default halves the DRAM re-reads.
+ * The environment variable KBO_TC_PAIR sets the initial value for new handles. */
+int kbo_set_tc_pair(kbo_handle* h, int enabled);
 
 /* ---- tell: GaussianProcessRegressor.fit at fixed θ ($SK/_gpr.py:275-280, 349-368) ---------------
  * X: N×D fp64, y: N fp64, device pointers (x_on_host = 0) or host pointers (x_on_host = 1).

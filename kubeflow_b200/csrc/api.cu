@@ -1,5 +1,7 @@
 // extern "C" surface of libkbo.so (include/kbo.h).  No exceptions cross this boundary; every failure is a
 // negative kbo_status plus kbo_last_error() text.  There is no CPU path: without a device kbo_create fails.
+#include <stdlib.h>
+
 #include "kbo_internal.cuh"
 
 static const char* kNoHandle = "kbo: null handle";
@@ -21,6 +23,7 @@ int kbo_create(kbo_handle** out, int device) {
   if (!h) return KBO_ERR_NOMEM;
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("KBO_TC_PAIR")) h->tc_pair = atoi(e) != 0;
   if (prop.major != 10) {
     // sm_100a cubin only: refuse politely instead of failing at the first launch
     h->err = "libkbo is built for sm_100a (B200) only";
@@ -54,6 +57,12 @@ int kbo_set_scratch_limit(kbo_handle* h, uint64_t bytes) {
   if (!h) return KBO_ERR_INVALID;
   if (bytes < (64ull << 20)) KBO_FAIL(h, KBO_ERR_INVALID, "scratch limit must be >= 64 MiB");
   h->scratch_limit = bytes;
+  return KBO_OK;
+}
+
+int kbo_set_tc_pair(kbo_handle* h, int enabled) {
+  if (!h) return KBO_ERR_INVALID;
+  h->tc_pair = enabled != 0;
   return KBO_OK;
 }
 

@@ -50,7 +50,8 @@ struct kbo_handle {
   size_t ev_var_used = 0, ev_cross_used = 0, ev_acq_used = 0;
   int launches = 0;
   bool time_kernels = false;
-  bool attr_fit = false, attr_tc = false;  // cudaFuncSetAttribute done for this handle's device
+  bool attr_fit = false, attr_tc = false;
+  int tc_pair = 1;  // variance kernel variant (kbo_set_tc_pair)  // cudaFuncSetAttribute done for this handle's device
 };
 
 enum ScalIdx { S_YMEAN = 0, S_YSTD = 1, S_YOPT = 2, S_LML = 3, S_LOGDET = 4, S_QUAD = 5, S_COUNT = 8 };

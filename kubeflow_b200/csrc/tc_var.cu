@@ -526,9 +526,8 @@ int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows,
     KBO_CUDA(h, cudaFuncSetAttribute(tc_variance_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     h->attr_tc = true;
   }
-  // default: the 2-CTA cluster / TMA-multicast kernel (half the K* panel re-reads); KBO_TC_PAIR=0 selects the single-CTA one
-  static const int pair_mode = getenv("KBO_TC_PAIR") ? atoi(getenv("KBO_TC_PAIR")) : 1;
-  if (pair_mode) {
+  // default: the 2-CTA cluster / TMA-multicast kernel (half the K* panel re-reads); kbo_set_tc_pair(h, 0) selects the single-CTA one
+  if (h->tc_pair) {
     CUtensorMap tmAh64, tmAl64;
     KBO_TRY(encode_map(h, &tmAh64, Ksh, (uint64_t)Npad, (uint64_t)rows, 64));
     KBO_TRY(encode_map(h, &tmAl64, Ksl, (uint64_t)Npad, (uint64_t)rows, 64));

@@ -27,7 +27,8 @@ class Best:
 class GPEngine:
     def __init__(self, device: int = 0, *, kernel: str = "matern52", length_scale=1.0, amplitude: float = 1.0,
                  noise: float = 1e-10, acq: str = "ei", xi: float = 0.01, kappa: float = 1.96,
-                 normalize_y: bool = True, var_mode: str = "auto", tc_k_span: int = 0, scratch_limit: int | None = None):
+                 normalize_y: bool = True, var_mode: str = "auto", tc_k_span: int = 0, scratch_limit: int | None = None,
+                 tc_pair: bool | None = None):
         if kernel not in L.KERNELS:
             raise ValueError(f"kernel must be one of {sorted(L.KERNELS)}, got {kernel!r}")
         if acq not in L.ACQS:
@@ -49,6 +50,8 @@ class GPEngine:
         self.N = self.D = 0
         if scratch_limit is not None:
             L.check(self.lib, self._h, self.lib.kbo_set_scratch_limit(self._h, int(scratch_limit)))
+        if tc_pair is not None:
+            L.check(self.lib, self._h, self.lib.kbo_set_tc_pair(self._h, int(bool(tc_pair))))
         self._best_dev = torch.empty(4, dtype=torch.float64, device=f"cuda:{self.device}")
 
     # -- plumbing ----------------------------------------------------------------------------------

@@ -123,6 +123,23 @@ def test_oracle_midsize(N, M, D, kind, acq, var_mode, tol):
     eng.close()
 
 
+def test_both_variance_kernel_variants_agree_bitwise():
+    """The cluster/multicast kernel and the single-CTA kernel issue the same MMAs in the same order per j-tile and add the
+    tiles in the same order per parity class — the per-candidate variances may differ only by the final fp64 add order."""
+    X, y, Xc = O.synthetic(700, 3000, 9)
+    th = O.theta_of_record(9)
+    outs = []
+    for pair in (1, 0):
+        eng = _engine(dict(kind="matern52", acq="ei", **th), "tc", tc_pair=bool(pair))
+        eng.tell(X, y)
+        b, mu, std, a = eng.ask(Xc, return_arrays=True)
+        outs.append((b, std.cpu().numpy(), a.cpu().numpy()))
+        eng.close()
+    assert outs[0][0].index == outs[1][0].index
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=0, atol=1e-7)
+
+
 def test_cfg3_full_size_history_candidate_subsample():
     """BASELINE cfg3 at its full trial count (N=8192, D=32, Matern-5/2, EI), tensor-core mode, on a 4096-candidate slice of
     the 1M grid (the oracle needs ~1 s per 2048 candidates at this N): acquisition within 1e-5, same argmax."""
@@ -142,15 +159,17 @@ def test_cfg3_full_size_history_candidate_subsample():
     eng.close()
 
 
+@pytest.mark.parametrize("pair", [1, 0])
 @pytest.mark.parametrize("k_span", [32, 256, 1024, 1 << 20])
-@pytest.mark.parametrize("rows,Npad", [(128, 256), (256, 1024), (384, 2048)])
-def test_tc_variance_kernel_raw(rows, Npad, k_span):
+@pytest.mark.parametrize("rows,Npad", [(128, 256), (256, 1024), (384, 2048), (128, 768)])
+def test_tc_variance_kernel_raw(rows, Npad, k_span, pair):
     """The tcgen05 kernel alone: fp16 hi/lo planes in, Σ_j (Σ_{k<=j} A[m,k]·B[j,k])² out, vs fp64 NumPy on the same planes."""
     import ctypes as C
     from kubeflow_b200 import _lib as Lb
     lib = Lb.load()
     h = C.c_void_p()
     assert lib.kbo_create(C.byref(h), 0) == 0
+    assert lib.kbo_set_tc_pair(h, pair) == 0      # 1: 2-CTA cluster + TMA multicast (default), 0: one CTA per panel
     r = np.random.default_rng(rows * 7 + Npad)
     A = r.random((rows, Npad)) * 0.9 + 0.05
     B = np.tril(r.standard_normal((Npad, Npad)) * 40.0)
@@ -171,7 +190,7 @@ def test_tc_variance_kernel_raw(rows, Npad, k_span):
     torch.cuda.synchronize()
     got = ssq.cpu().numpy()
     rel = np.abs(got - ref) / ref
-    print(f"\nrows={rows} Npad={Npad} k_span={k_span}: max rel err Σv² = {rel.max():.3e}, mean signed = {((got-ref)/ref).mean():+.3e}")
+    print(f"\npair={pair} rows={rows} Npad={Npad} k_span={k_span}: max rel err Σv² = {rel.max():.3e}, mean signed = {((got-ref)/ref).mean():+.3e}")
     assert rel.max() < 2e-5
     lib.kbo_destroy(h)
 
@@ -211,6 +230,33 @@ def test_dimension_sweep(D):
         best, mu, std, a = eng.ask(Xc, return_arrays=True)
         np.testing.assert_allclose(a.cpu().numpy(), ref["acq"], rtol=0, atol=tol)
         _check_argmax(best, ref["acq"], tol)
+        eng.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_ragged_shapes(seed):
+    """Seeded random shapes around every tile boundary of the path (64-row Cholesky blocks, 128×64 K* tiles, 256-column
+    j-tiles, 4-candidate acquisition groups), random kernel / acquisition / ARD, fp32 or fp64 candidates, both modes."""
+    r = np.random.default_rng(1000 + seed)
+    N = int(r.choice([1, 2, 63, 64, 65, 127, 128, 129, 255, 256, 257, 300, 511, 513]))
+    M = int(r.choice([1, 2, 3, 4, 5, 127, 128, 129, 1000, 2049]))
+    D = int(r.choice([1, 2, 3, 7, 16, 31, 32, 33, 40]))
+    kind = str(r.choice(["rbf", "matern52"]))
+    acq = str(r.choice(["ei", "pi", "lcb"]))
+    X, y, Xc = O.synthetic(N, M, D)
+    ls = (0.3 * np.sqrt(D)) * (r.uniform(0.7, 1.5, D) if r.random() < 0.5 else 1.0)
+    kw = dict(length_scale=ls, amplitude=float(r.uniform(0.5, 2.0)), noise=1e-3, xi=0.01, kappa=1.96)
+    if r.random() < 0.5:
+        Xc = Xc.astype(np.float32)
+    ref = O.suggest(X, y, np.asarray(Xc, dtype=np.float64), kind=kind, acq=acq, **kw)
+    for var_mode, tol in (("f64", 1e-7), ("tc", 5e-5 if acq == "lcb" else TOL_TC)):
+        eng = _engine(dict(kind=kind, acq=acq, **kw), var_mode)
+        eng.tell(X, y)
+        best, mu, std, a = eng.ask(Xc, return_arrays=True)
+        err = np.abs(a.cpu().numpy() - ref["acq"]).max()
+        assert err <= tol, (seed, N, M, D, kind, acq, var_mode, err)
+        _check_argmax(best, ref["acq"], tol)
+        _check_argmax(eng.ask(Xc), ref["acq"], max(tol, 1e-6))
         eng.close()
 
 
