@@ -4,7 +4,10 @@ requested assignment).  Differences, stated once:
 
 * θ is FIXED per request (length scales, amplitude, noise are settings), where skopt refits them by L-BFGS on the
   log-marginal likelihood ($SK/_gpr.py:299-339) — bit-reproducing that optimiser is outside the 1e-5 contract
-  (SURVEY.md §7).  ``theta_grid`` > 1 picks the best of a small length-scale grid by the GPU-computed LML instead.
+  (SURVEY.md §7).  Two GPU-side substitutes, both maximising the device-computed LML (one FP64 fit per candidate θ):
+  ``theta_grid`` = G > 1 tries G multiples of the length scale (geometric, 0.25×…4×); ``theta_search`` = K > 0 additionally
+  draws K random (length-scale multiple, noise) pairs log-uniformly from [0.2, 5] × [1e-6, 1e-1] (seeded) — the gradient-free
+  analogue of skopt's restarts.
 * ``acq_optimizer`` is "sampling" over ``n_points`` candidates (skopt default 10 000; here 65 536 by default and
   millions are cheap) — ``lbfgs`` polishing and ``gp_hedge`` are accepted by ValidateAlgorithmSettings and mapped to
   sampling / EI.
@@ -20,7 +23,7 @@ from .space import Space
 class Optimizer:
     def __init__(self, dimensions, base_estimator="GP", n_initial_points=10, acq_func="EI", acq_optimizer="sampling",
                  random_state=None, *, n_points=65536, kernel="matern52", length_scale=None, amplitude=1.0, noise=1e-3, xi=0.01,
-                 kappa=1.96, var_mode="auto", theta_grid=1, device=0, engine=None, candidate_backend="torch"):
+                 kappa=1.96, var_mode="auto", theta_grid=1, theta_search=0, device=0, engine=None, candidate_backend="torch"):
         if str(base_estimator).upper() != "GP":
             raise ValueError("base_estimator must be GP (RF/ET/GBRT are not part of the GPU path)")
         self.space = dimensions if isinstance(dimensions, Space) else Space(dimensions)
@@ -35,7 +38,8 @@ class Optimizer:
         self.n_points = int(n_points)
         self.kernel, self.amplitude, self.noise, self.xi, self.kappa = kernel, amplitude, noise, xi, kappa
         self.length_scale = length_scale
-        self.var_mode, self.theta_grid, self.device = var_mode, int(theta_grid), device
+        self.var_mode, self.theta_grid, self.theta_search, self.device = var_mode, int(theta_grid), int(theta_search), device
+        self.last_theta = None
         if candidate_backend not in ("torch", "numpy"):
             raise ValueError("candidate_backend must be 'torch' (sampled on the device) or 'numpy'")
         self.candidate_backend = candidate_backend
@@ -81,17 +85,24 @@ class Optimizer:
         ya = np.asarray(y, dtype=np.float64)
         base = np.atleast_1d(np.asarray(self._default_ls(), dtype=np.float64))
         eng = self._get_engine(base)
-        if self.theta_grid > 1:   # choose ℓ-multiplier by GPU log-marginal likelihood
-            mults = np.geomspace(0.25, 4.0, self.theta_grid)
-            lmls = []
-            for m in mults:
-                eng.length_scale = base * m
+        if self.theta_grid > 1 or self.theta_search > 0:   # choose θ by the GPU log-marginal likelihood
+            cands = [(float(m), self.noise) for m in (np.geomspace(0.25, 4.0, self.theta_grid) if self.theta_grid > 1 else [1.0])]
+            if self.theta_search > 0:
+                tr = np.random.default_rng(0 if self._seed is None else int(self._seed) + 17)
+                cands += [(float(np.exp(tr.uniform(np.log(0.2), np.log(5.0)))), float(np.exp(tr.uniform(np.log(1e-6), np.log(1e-1)))))
+                          for _ in range(self.theta_search)]
+            best_lml, best_t = -np.inf, (1.0, self.noise)
+            for m, nz in cands:
+                eng.length_scale, eng.noise = base * m, nz
                 eng.tell(Xt, ya)
                 try:
-                    lmls.append(eng.fit_info()["lml"])
-                except Exception:
-                    lmls.append(-np.inf)
-            eng.length_scale = base * mults[int(np.argmax(lmls))]
+                    lml = eng.fit_info()["lml"]
+                except Exception:   # not positive definite at this θ
+                    continue
+                if lml > best_lml:
+                    best_lml, best_t = lml, (m, nz)
+            eng.length_scale, eng.noise = base * best_t[0], best_t[1]
+            self.last_theta = dict(length_scale=eng.length_scale.copy(), noise=eng.noise, lml=best_lml)
         eng.tell(Xt, ya)
         if self.candidate_backend == "torch":
             import torch

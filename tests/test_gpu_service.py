@@ -137,3 +137,22 @@ def test_theta_grid_picks_higher_lml_length_scale():
     assert lml(chosen) > lml(base) + 1.0
     grid = base * np.geomspace(0.25, 4.0, 7)
     assert abs(chosen - grid[int(np.argmax([lml(g) for g in grid]))]) < 1e-12      # same pick as the oracle's LML over the same grid
+
+
+def test_theta_search_improves_lml_over_default():
+    """Random (length scale, noise) search by GPU LML: never worse than the default θ, and clearly better on a noisy wiggly target."""
+    from kubeflow_b200.optimizer import Optimizer
+    from kubeflow_b200.space import Real, Space
+    from oracle import gp_oracle as O
+    r = np.random.default_rng(3)
+    sp = Space([Real(0.0, 1.0), Real(0.0, 1.0), Real(0.0, 1.0)])
+    pts = r.random((120, 3)).tolist()
+    ys = [float(np.sin(9 * p[0]) * np.cos(7 * p[1]) + 0.5 * p[2] + 0.2 * r.standard_normal()) for p in pts]
+    opt = Optimizer(sp, n_initial_points=5, acq_func="EI", random_state=2, n_points=1024, theta_search=24)
+    opt.tell(pts, ys)
+    opt.ask()
+    th = opt.last_theta
+    base = O.gp_fit(np.asarray(pts), np.asarray(ys), kind="matern52", length_scale=0.3 * np.sqrt(3), noise=1e-3)["lml"]
+    chosen = O.gp_fit(np.asarray(pts), np.asarray(ys), kind="matern52", length_scale=th["length_scale"], noise=th["noise"])["lml"]
+    assert abs(chosen - th["lml"]) < 1e-6 * abs(chosen)          # the GPU LML that drove the choice equals the oracle's at that θ
+    assert chosen > base + 5.0 and th["noise"] > 1e-3            # the data are noisy: a larger noise level wins
