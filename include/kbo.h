@@ -117,6 +117,9 @@ int kbo_fit(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t 
 /* synchronises; any out pointer may be NULL.  info = 0 or 1-based index of the failed pivot. */
 int kbo_fit_info(kbo_handle* h, double* lml, double* y_mean, double* y_std, double* y_opt, int32_t* info,
                  void* stream);
+/* Gradient of the log-marginal likelihood of the last kbo_fit w.r.t. θ = (log amplitude, log noise, log ℓ_1..ℓ_P), P =
+ * n_length_scale of that fit ($SK/_gpr.py:621-653).  grad_host: n_out = 2 + P doubles.  Synchronises. */
+int kbo_lml_grad(kbo_handle* h, double* grad_host, int32_t n_out, void* stream);
 /* copies the fit state into caller-owned DEVICE buffers (any may be NULL): L_out, W_out are N×N row-major
  * (L: lower Cholesky factor, strict upper part zeroed; W = L^-1), alpha_out has N entries. For parity tests. */
 int kbo_fit_state(kbo_handle* h, double* L_out, double* W_out, double* alpha_out, void* stream);

@@ -50,7 +50,7 @@ class KboNotPositiveDefinite(KboError):
 
 # every symbol include/kbo.h declares (tests/test_abi.py checks the .so exports exactly these)
 EXPORTS = ["kbo_version", "kbo_create", "kbo_destroy", "kbo_last_error", "kbo_set_scratch_limit", "kbo_set_tc_pair", "kbo_fit",
-           "kbo_fit_info", "kbo_fit_state", "kbo_sweep", "kbo_best_to_host", "kbo_suggest_host", "kbo_last_timings",
+           "kbo_fit_info", "kbo_lml_grad", "kbo_fit_state", "kbo_sweep", "kbo_best_to_host", "kbo_suggest_host", "kbo_last_timings",
            "kbo_gram", "kbo_potrf", "kbo_trtri", "kbo_acq_argmax",
            "kbo_cma_create", "kbo_cma_destroy", "kbo_cma_ask", "kbo_cma_tell", "kbo_cma_state", "kbo_cma_run_synthetic"]
 
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
     lib.kbo_fit.argtypes = [vp, vp, vp, i32, i32, C.POINTER(KboParams), C.c_int, vp]
     lib.kbo_fit_info.argtypes = [vp, pd, pd, pd, pd, C.POINTER(i32), vp]
     lib.kbo_fit_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.kbo_lml_grad.argtypes = [vp, pd, i32, vp]
     lib.kbo_sweep.argtypes = [vp, vp, i32, i64, i64, C.c_int, vp, vp, vp, vp, vp]
     lib.kbo_best_to_host.argtypes = [vp, vp, C.POINTER(KboBest), vp]
     lib.kbo_suggest_host.argtypes = [vp, vp, vp, i32, i32, vp, i32, i64, i64, C.POINTER(KboParams), C.POINTER(KboBest),

@@ -5,7 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-enum { KM_FULL = 0, KM_UPTO_N = 1, KM_FROM_N = 2, KM_UPTO_M = 3 };
+enum { KM_FULL = 0, KM_UPTO_N = 1, KM_FROM_N = 2, KM_UPTO_M = 3, KM_FROM_M = 4 };
 enum { EPI_STORE = 0, EPI_ROWSUMSQ = 1 };
 enum { TS_NONE = 0, TS_LOWER = 1 };
 
@@ -34,6 +34,7 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   if (kmode == KM_UPTO_N) ke = min(K, n0 + DG_BN);
   if (kmode == KM_FROM_N) kb = max(kbegin, n0);
   if (kmode == KM_UPTO_M) ke = min(K, m0 + DG_BM);
+  if (kmode == KM_FROM_M) kb = max(kbegin, m0);
   kb = kb & ~(DG_BK - 1);
 
   double acc[8][4];

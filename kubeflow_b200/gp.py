@@ -110,6 +110,14 @@ class GPEngine:
         L.check(self.lib, self._h, rc)
         return dict(lml=lml.value, y_mean=ym.value, y_std=ys.value, y_opt=yo.value, info=info.value)
 
+    def lml_grad(self):
+        """(lml, grad) of the last tell; grad w.r.t. (log amplitude, log noise, log ℓ_1..ℓ_P) as a NumPy array."""
+        info = self.fit_info()
+        g = np.empty(2 + len(self.length_scale), dtype=np.float64)
+        rc = self.lib.kbo_lml_grad(self._h, g.ctypes.data_as(C.POINTER(C.c_double)), len(g), self._stream())
+        L.check(self.lib, self._h, rc)
+        return info["lml"], g
+
     def state(self):
         """Copies of L (lower), W = L^-1 and alpha as float64 CUDA tensors (parity tests)."""
         N, dev = self.N, f"cuda:{self.device}"

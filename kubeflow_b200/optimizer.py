@@ -7,7 +7,9 @@ requested assignment).  Differences, stated once:
   (SURVEY.md §7).  Two GPU-side substitutes, both maximising the device-computed LML (one FP64 fit per candidate θ):
   ``theta_grid`` = G > 1 tries G multiples of the length scale (geometric, 0.25×…4×); ``theta_search`` = K > 0 additionally
   draws K random (length-scale multiple, noise) pairs log-uniformly from [0.2, 5] × [1e-6, 1e-1] (seeded) — the gradient-free
-  analogue of skopt's restarts.
+  analogue of skopt's restarts; ``theta_fit="lbfgs"`` then polishes (log ℓ — per dimension with ``ard=True`` —, log noise)
+  with SciPy's L-BFGS-B exactly as sklearn does ($SK/_gpr.py:658-667), every objective/gradient evaluation being one
+  device fit + ``kbo_lml_grad``.
 * ``acq_optimizer`` is "sampling" over ``n_points`` candidates (skopt default 10 000; here 65 536 by default and
   millions are cheap) — ``lbfgs`` polishing and ``gp_hedge`` are accepted by ValidateAlgorithmSettings and mapped to
   sampling / EI.
@@ -23,7 +25,8 @@ from .space import Space
 class Optimizer:
     def __init__(self, dimensions, base_estimator="GP", n_initial_points=10, acq_func="EI", acq_optimizer="sampling",
                  random_state=None, *, n_points=65536, kernel="matern52", length_scale=None, amplitude=1.0, noise=1e-3, xi=0.01,
-                 kappa=1.96, var_mode="auto", theta_grid=1, theta_search=0, device=0, engine=None, candidate_backend="torch"):
+                 kappa=1.96, var_mode="auto", theta_grid=1, theta_search=0, theta_fit=None, theta_fit_maxiter=25, ard=False, device=0, engine=None,
+                 candidate_backend="torch"):
         if str(base_estimator).upper() != "GP":
             raise ValueError("base_estimator must be GP (RF/ET/GBRT are not part of the GPU path)")
         self.space = dimensions if isinstance(dimensions, Space) else Space(dimensions)
@@ -39,6 +42,9 @@ class Optimizer:
         self.kernel, self.amplitude, self.noise, self.xi, self.kappa = kernel, amplitude, noise, xi, kappa
         self.length_scale = length_scale
         self.var_mode, self.theta_grid, self.theta_search, self.device = var_mode, int(theta_grid), int(theta_search), device
+        if theta_fit not in (None, "lbfgs"):
+            raise ValueError("theta_fit must be None or 'lbfgs'")
+        self.theta_fit, self.theta_fit_maxiter, self.ard = theta_fit, int(theta_fit_maxiter), bool(ard)
         self.last_theta = None
         if candidate_backend not in ("torch", "numpy"):
             raise ValueError("candidate_backend must be 'torch' (sampled on the device) or 'numpy'")
@@ -103,6 +109,25 @@ class Optimizer:
                     best_lml, best_t = lml, (m, nz)
             eng.length_scale, eng.noise = base * best_t[0], best_t[1]
             self.last_theta = dict(length_scale=eng.length_scale.copy(), noise=eng.noise, lml=best_lml)
+        if self.theta_fit == "lbfgs":
+            from scipy.optimize import minimize
+            Dt = self.space.transformed_n_dims
+            ls0 = np.broadcast_to(np.atleast_1d(eng.length_scale), (Dt,)).copy() if self.ard else np.atleast_1d(eng.length_scale)[:1].copy()
+            x0 = np.concatenate([np.log(ls0), [np.log(max(eng.noise, 1e-8))]])
+            bounds = [(np.log(1e-2), np.log(1e2))] * len(ls0) + [(np.log(1e-8), np.log(1.0))]
+
+            def negative_lml(t):
+                eng.length_scale, eng.noise = np.exp(t[:-1]), float(np.exp(t[-1]))
+                eng.tell(Xt, ya)
+                try:
+                    lml, g = eng.lml_grad()            # g: (log amp, log noise, log ℓ…)
+                except Exception:                       # not positive definite at this θ
+                    return 1e25, np.zeros_like(t)
+                return -lml, -np.concatenate([g[2:], g[1:2]])
+
+            res = minimize(negative_lml, x0, jac=True, method="L-BFGS-B", bounds=bounds, options=dict(maxiter=self.theta_fit_maxiter))
+            eng.length_scale, eng.noise = np.exp(res.x[:-1]), float(np.exp(res.x[-1]))
+            self.last_theta = dict(length_scale=eng.length_scale.copy(), noise=eng.noise, lml=-float(res.fun), nfev=int(res.nfev))
         eng.tell(Xt, ya)
         if self.candidate_backend == "torch":
             import torch

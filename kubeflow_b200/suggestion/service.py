@@ -23,7 +23,7 @@ logger = logging.getLogger(__name__)
 
 SKOPT_SETTINGS = ("base_estimator", "n_initial_points", "acq_func", "acq_optimizer", "random_state")
 ENGINE_SETTINGS = {"n_points": int, "kernel": str, "length_scale": float, "amplitude": float, "noise": float, "xi": float,
-                   "kappa": float, "var_mode": str, "theta_grid": int, "theta_search": int, "device": int, "candidate_backend": str}
+                   "kappa": float, "var_mode": str, "theta_grid": int, "theta_search": int, "theta_fit": str, "theta_fit_maxiter": int, "ard": int, "device": int, "candidate_backend": str}
 
 
 def validate_skopt_settings(settings: dict) -> dict:
@@ -61,6 +61,8 @@ def validate_skopt_settings(settings: dict) -> dict:
                     raise AlgorithmSettingsError(f"var_mode {v} must be tc, f64 or auto")
                 if name == "candidate_backend" and v not in ("torch", "numpy"):
                     raise AlgorithmSettingsError(f"candidate_backend {v} must be torch or numpy")
+                if name == "theta_fit" and v != "lbfgs":
+                    raise AlgorithmSettingsError(f"theta_fit {v} must be lbfgs")
                 if name == "theta_search" and v < 0:
                     raise AlgorithmSettingsError(f"theta_search must be >= 0, got {value}")
                 if name in ("n_points", "theta_grid") and v < 1:

@@ -13,9 +13,9 @@ kubeflow/katib ``pkg/suggestion/v1beta1/skopt`` -> scikit-optimize (``Optimizer.
 ``skopt.acquisition.gaussian_{ei,lcb,pi}``) -> scikit-learn ``GaussianProcessRegressor``.
 scikit-optimize is not installable here; scikit-learn 1.9.0 *is* importable, so this file is a
 plain NumPy/SciPy fp64 restatement of the published algorithm (Rasmussen & Williams Alg. 2.1 as
-coded in scikit-learn) and ``oracle/sk_check.py`` pins it against the real
-``sklearn.gaussian_process.GaussianProcessRegressor`` run in this container; the resulting golden
-vectors are committed under ``tests/golden/`` (generator: ``oracle/make_golden.py``).
+coded in scikit-learn); it is pinned against the real ``sklearn.gaussian_process.GaussianProcessRegressor``
+run in this container: the golden vectors are committed under ``tests/golden/`` (generators:
+``oracle/make_golden.py``, ``oracle/make_golden_lmlgrad.py``) and checked by ``tests/test_oracle.py``.
 
 Line references: ``$SK`` = site-packages/sklearn/gaussian_process (scikit-learn 1.9.0).
 """
@@ -172,3 +172,28 @@ def synthetic(N, M, D, *, m_offset=0, m_total=None):
 def theta_of_record(D):
     """amplitude 1, ℓ_d = 0.3·√D, noise 1e-3, ξ = 0.01, κ = 1.96."""
     return dict(length_scale=0.3 * np.sqrt(D), amplitude=1.0, noise=1e-3, xi=0.01, kappa=1.96)
+
+
+def lml_and_grad(X, y, *, kind=KERNEL_MATERN52, length_scale=1.0, amplitude=1.0, noise=1e-10, normalize_y=True):
+    """Log-marginal likelihood and its gradient w.r.t. θ = (log amplitude, log noise, log ℓ_1..ℓ_P) at fixed data
+    ($SK/_gpr.py:541-655: ``0.5·einsum((ααᵀ − K⁻¹), ∂K/∂θ)``; kernel gradients $SK/kernels.py:1571-1591 (RBF),
+    :1731-1745 (Matérn ν=2.5), :1296 (Constant), :1421 (White)).  P = 1 (isotropic) or D."""
+    fit = gp_fit(X, y, kind=kind, length_scale=length_scale, amplitude=amplitude, noise=noise, normalize_y=normalize_y)
+    Xs = fit["X"] / fit["length_scale"]
+    n = len(fit["yn"])
+    Kinv = cho_solve((fit["L"], True), np.eye(n), check_finite=False)
+    G = np.outer(fit["alpha"], fit["alpha"]) - Kinv
+    diff2 = (Xs[:, None, :] - Xs[None, :, :]) ** 2          # (n, n, D) scaled squared differences
+    r2 = diff2.sum(-1)
+    if kind == KERNEL_RBF:
+        k = np.exp(-0.5 * r2)
+        q = k                                              # ∂k/∂log ℓ_d = k · Δ_d²
+    else:
+        s = np.sqrt(5.0 * r2)
+        k = (1 + s + s * s / 3) * np.exp(-s)
+        q = (5.0 / 3.0) * (1 + s) * np.exp(-s)             # ∂k/∂log ℓ_d = (5/3)(1+s)e^{-s} · Δ_d²
+    g_amp = 0.5 * np.sum(G * (amplitude * k))
+    g_noise = 0.5 * noise * np.trace(G)
+    per_dim = 0.5 * amplitude * np.einsum("ij,ij,ijd->d", G, q, diff2)
+    g_ls = per_dim if np.ndim(length_scale) and len(np.atleast_1d(length_scale)) > 1 else np.array([per_dim.sum()])
+    return fit["lml"], np.concatenate([[g_amp, g_noise], g_ls])

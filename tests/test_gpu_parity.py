@@ -260,6 +260,32 @@ def test_fuzz_ragged_shapes(seed):
         eng.close()
 
 
+def test_lml_gradient_matches_sklearn_golden_and_oracle():
+    """kbo_lml_grad vs the real scikit-learn `log_marginal_likelihood(eval_gradient=True)` (tests/golden/lmlgrad_cases.npz)
+    and vs the oracle at a size that spans several 64×64 pair tiles, isotropic and ARD."""
+    import os
+    from kubeflow_b200.gp import GPEngine
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lmlgrad_cases.npz"), allow_pickle=False)
+    for n in sorted({k.split("__")[0] for k in z.files}):
+        ls = z[f"{n}__ls"]
+        eng = GPEngine(0, kernel=str(z[f"{n}__kind"]), length_scale=ls, amplitude=float(z[f"{n}__amp"]), noise=float(z[f"{n}__noise"]), var_mode="f64")
+        eng.tell(z[f"{n}__X"], z[f"{n}__y"])
+        lml, g = eng.lml_grad()
+        assert abs(lml - float(z[f"{n}__lml"])) < 1e-9
+        np.testing.assert_allclose(g, z[f"{n}__grad"], rtol=0, atol=1e-8)
+        eng.close()
+    for kind, ard in (("matern52", True), ("rbf", False)):
+        X, y, _ = O.synthetic(333, 1, 7)
+        ls = 0.3 * np.sqrt(7) * (np.linspace(0.8, 1.3, 7) if ard else 1.0)
+        ref_lml, ref_g = O.lml_and_grad(X, y, kind=kind, length_scale=ls, amplitude=1.4, noise=2e-3)
+        eng = GPEngine(0, kernel=kind, length_scale=ls, amplitude=1.4, noise=2e-3, var_mode="f64")
+        eng.tell(X, y)
+        lml, g = eng.lml_grad()
+        assert abs(lml - ref_lml) < 1e-8 * abs(ref_lml)
+        np.testing.assert_allclose(g, ref_g, rtol=1e-8, atol=1e-7)
+        eng.close()
+
+
 def test_ties_duplicates_and_sharding():
     X, y, Xc = O.synthetic(96, 1000, 4)
     th = O.theta_of_record(4)

@@ -1,5 +1,7 @@
 """CPU: pin oracle/gp_oracle.py against the golden vectors produced by the real scikit-learn GPR
 (oracle/make_golden.py) and against self-authored known-answer checks."""
+import os
+
 import numpy as np
 import pytest
 
@@ -84,3 +86,15 @@ def test_properties():
     # EI -> 0 when sigma -> 0 and mu > y_opt
     assert O.acquisition(np.array([2.0]), np.array([1e-12]), 1.0)[0] < 1e-300 + 1e-12
     assert O.acquisition(np.array([2.0]), np.array([0.0]), 1.0)[0] == 0.0
+
+
+def test_lml_gradient_matches_sklearn_golden():
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lmlgrad_cases.npz"), allow_pickle=False)
+    names = sorted({k.split("__")[0] for k in z.files})
+    assert len(names) == 4
+    for n in names:
+        ls = z[f"{n}__ls"]
+        lml, g = O.lml_and_grad(z[f"{n}__X"], z[f"{n}__y"], kind=str(z[f"{n}__kind"]), length_scale=ls if len(ls) > 1 else float(ls[0]),
+                                amplitude=float(z[f"{n}__amp"]), noise=float(z[f"{n}__noise"]))
+        assert abs(lml - float(z[f"{n}__lml"])) < 1e-9
+        np.testing.assert_allclose(g, z[f"{n}__grad"], rtol=0, atol=1e-9)
