@@ -2,7 +2,7 @@
 // (A Taylor-table variant was measured first: two data-dependent 16-byte loads per element made the kernel L1-gather
 //  bound — 104 ms vs 77 ms at cfg3 — so the table is gone; see profiles/README.md "r1 dead ends".)
 //   exp(x), x <= 0:  n = rint(x·log2e) by the 1.5·2⁵² trick, f = x·log2e − n (two-term log2e), 2^f by a degree-11
-//   polynomial in g = f·ln2 (|g| ≤ 0.3466, truncation 6e-15 relative), scaled by 2ⁿ through the exponent bits.
+//   polynomial in f (|f·ln2| ≤ 0.3466, truncation 6e-15 relative), scaled by 2ⁿ through the exponent bits.
 //   Results below 2⁻¹⁰²⁰ flush to 0 (irrelevant next to the 1e-5 contract).
 #pragma once
 #include <cuda_runtime.h>
@@ -14,19 +14,19 @@ __device__ __forceinline__ double kbo_exp_nonpos(double x) {
   const double nf = u - 6755399441055744.0;
   double f = fma(x, 1.4426950408889634, -nf);
   f = fma(x, 2.0355273740931033e-17, f);             // low part of log2(e)
-  const double g = f * 0.6931471805599453;
-  double p = 2.505210838544172e-08;                   // 1/11!
-  p = fma(p, g, 2.755731922398589e-07);               // 1/10!
-  p = fma(p, g, 2.7557319223985893e-06);              // 1/9!
-  p = fma(p, g, 2.48015873015873e-05);                // 1/8!
-  p = fma(p, g, 1.984126984126984e-04);               // 1/7!
-  p = fma(p, g, 1.388888888888889e-03);               // 1/6!
-  p = fma(p, g, 8.333333333333333e-03);               // 1/5!
-  p = fma(p, g, 4.1666666666666664e-02);              // 1/4!
-  p = fma(p, g, 1.6666666666666666e-01);              // 1/3!
-  p = fma(p, g, 0.5);
-  p = fma(p, g, 1.0);
-  p = fma(p, g, 1.0);
+  // 2^f = Σ (ln2)^k/k! · f^k, |f| ≤ 1/2 (the ln2 factor folded into the coefficients: one DMUL less per value)
+  double p = 4.44553827187081e-10;
+  p = fma(p, f, 7.054911620801121e-09);
+  p = fma(p, f, 1.0178086009239696e-07);
+  p = fma(p, f, 1.3215486790144305e-06);
+  p = fma(p, f, 1.5252733804059838e-05);
+  p = fma(p, f, 0.00015403530393381606);
+  p = fma(p, f, 0.0013333558146428441);
+  p = fma(p, f, 0.009618129107628477);
+  p = fma(p, f, 0.055504108664821576);
+  p = fma(p, f, 0.2402265069591007);
+  p = fma(p, f, 0.6931471805599453);
+  p = fma(p, f, 1.0);
   const int hi = __double2hiint(p) + (ni << 20);
   const double r = __hiloint2double(hi, __double2loint(p));
   return ni < -1020 ? 0.0 : r;

@@ -3,6 +3,8 @@
 //   skopt.acquisition.gaussian_ei / gaussian_lcb / gaussian_pi ; Optimizer._tell: X_cand[np.argmin(values)]
 // Per candidate chunk:  cross_mean_kernel (FP64: K*, μ = K*·alpha)  →  variance contraction (FP64 SIMT GEMM with a
 // fused Σv² epilogue, or the tcgen05 kernel in tc_var.cu)  →  once per sweep: acquisition + argmax.
+#include <type_traits>
+
 #include "kbo_internal.cuh"
 #include "dgemm.cuh"
 #include "ktab.cuh"
@@ -112,44 +114,48 @@ cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* 
       }
     }
     if (dchunk == nd - 1) {
-      // branch-free epilogue: all 32 kernel values are computed unconditionally (inputs are always finite) and masked at
-      // the end, so the whole block is one scheduling region with 32 independent FP64 dependency chains to interleave
+      // branch-free epilogue: all 32 kernel values are computed unconditionally (inputs are always finite), so the whole
+      // block is one scheduling region with 32 independent FP64 dependency chains to interleave.  Interior tiles (the
+      // overwhelming majority) skip the row/column masks altogether; edge tiles mask the results at the end.
       const int n0 = tile * CM_BN, tb = tile & 1;
       double nxv[4], alv[4];
-      bool cok[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int c = tx + 16 * j;
         nxv[j] = nxs[tb * CM_BN + c];
         alv[j] = als[tb * CM_BN + c];
-        cok[j] = n0 + c < N;
       }
+      auto epilogue = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int r = ty + 16 * i;
-        const bool rok = m0 + r < rows;
-        const double ncr = nc[r];
-        double kv[4];
+        for (int i = 0; i < 8; i++) {
+          const int r = ty + 16 * i;
+          const bool rok = !MASKED || m0 + r < rows;
+          const double ncr = nc[r];
+          double kv[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) kv[j] = amp * kbo_kernel_exact(fma(-2.0, acc[i][j], ncr + nxv[j]), kind);
+          for (int j = 0; j < 4; j++) kv[j] = amp * kbo_kernel_exact(fma(-2.0, acc[i][j], ncr + nxv[j]), kind);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          kv[j] = (rok && cok[j]) ? kv[j] : 0.0;
-          musum[i] = fma(kv[j], alv[j], musum[i]);   // alpha is zero-padded past N, kv is masked: padding adds exactly 0
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = tx + 16 * j;
-          if (MODE == 0) {
-            if (rok && cok[j]) Ks64[(size_t)(m0 + r) * ldks + n0 + c] = kv[j];
-          } else {  // 16 lanes × 2 B = one full 32-byte sector per (row, 16-column group): no staging needed
-            const __half hi = __double2half(kv[j]);
-            const size_t g = (size_t)(m0 + r) * Npad + n0 + c;
-            Ksh[g] = hi;
-            Ksl[g] = __double2half(kv[j] - (double)__half2float(hi));
+          for (int j = 0; j < 4; j++) {
+            const bool ok = !MASKED || (rok && n0 + tx + 16 * j < N);
+            if (MASKED) kv[j] = ok ? kv[j] : 0.0;
+            musum[i] = fma(kv[j], alv[j], musum[i]);   // alpha is zero-padded past N, kv is masked: padding adds exactly 0
+            const int c = tx + 16 * j;
+            if (MODE == 0) {
+              if (ok) Ks64[(size_t)(m0 + r) * ldks + n0 + c] = kv[j];
+            } else {  // 16 lanes × 2 B = one full 32-byte sector per (row, 16-column group): no staging needed
+              const __half hi = __double2half(kv[j]);
+              const size_t g = (size_t)(m0 + r) * Npad + n0 + c;
+              Ksh[g] = hi;
+              Ksl[g] = __double2half(kv[j] - (double)__half2float(hi));
+            }
           }
         }
-      }
+      };
+      if (m0 + CM_BM <= rows && n0 + CM_BN <= N)
+        epilogue(std::false_type{});
+      else
+        epilogue(std::true_type{});
     }
     if (it + 1 < total) commit(it + 1);
     __syncthreads();
