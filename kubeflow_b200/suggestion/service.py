@@ -124,10 +124,11 @@ class _Base:
 class SkoptService(_Base):
     algorithm_names = ("bayesianoptimization",)
 
-    def __init__(self, engine_defaults: dict | None = None):
-        self._lock = threading.Lock()       # one GPU engine per service; handlers may run concurrently
-        self._services = {}                 # experiment name -> BaseSkoptService
+    def __init__(self, engine_defaults: dict | None = None, max_experiments: int = 8):
+        self._lock = threading.Lock()       # handlers may run concurrently (grpc thread pool): GPU work is serialised here
+        self._services = {}                 # experiment name -> BaseSkoptService, least-recently-used first
         self.engine_defaults = dict(engine_defaults or {})
+        self.max_experiments = int(max_experiments)   # each experiment owns a libkbo handle (K, W, scratch): bound the device memory
 
     def validate(self, experiment):
         name = experiment.spec.algorithm.algorithm_name
@@ -151,6 +152,14 @@ class SkoptService(_Base):
                 from .base_service import BaseSkoptService
                 svc = BaseSkoptService(search_space=search_space, **kw)
                 self._services[exp.name] = svc
+                while len(self._services) > self.max_experiments:       # evict the least recently used experiment's engine
+                    old_name = next(iter(self._services))
+                    old = self._services.pop(old_name)
+                    eng = getattr(old.skopt_optimizer, "_engine", None)
+                    if eng is not None:
+                        eng.close()
+            else:
+                self._services[exp.name] = self._services.pop(exp.name)  # mark as most recently used
             lists = svc.getSuggestions(trials, max(int(request.current_request_number), 0))
         return _reply_from(lists)
 

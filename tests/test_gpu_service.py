@@ -180,3 +180,35 @@ def test_theta_lbfgs_polish_uses_gpu_gradients():
     assert t["lml"] > o1.last_theta["lml"] + 1.0 > base + 1.0
     assert t["length_scale"][0] < t["length_scale"][2]                   # ARD found the relevant dimension
     assert np.abs(ref_g[1:]).max() < 2.0                                 # near-stationary in (noise, ℓ) after ≤ 40 iterations
+
+
+def test_concurrent_requests_and_lru_eviction():
+    """Four client threads hit the server at once for different experiments (handlers run on a thread pool; GPU work is
+    serialised by the service lock); with max_experiments = 2 older experiments' engines are evicted and rebuilt on demand."""
+    import threading
+    svc = SkoptService(max_experiments=2)
+    server, port = serve(DispatchService([svc]), port=0, host="127.0.0.1")
+    errors, results = [], {}
+
+    def client(k):
+        try:
+            ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+            stub = SuggestionStub(ch)
+            exp = make_experiment("bayesianoptimization", {"n_initial_points": 2, "acq_func": "EI", "random_state": k, "n_points": 2000}, name=f"c{k}")
+            req = api.GetSuggestionsRequest(experiment=exp, current_request_number=1)
+            for i in range(6):
+                rep = stub.GetSuggestions(req)
+                vals = {a.name: float(a.value) for a in rep.parameter_assignments[0].assignments}
+                add_trial(req, f"c{k}-t{i}", vals, _f(vals))
+            results[k] = len(req.trials)
+            ch.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=client, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    assert not errors, errors
+    assert results == {0: 6, 1: 6, 2: 6, 3: 6}
+    assert len(svc._services) <= 2
+    server.stop(0)
