@@ -1,4 +1,4 @@
-// FP64 SIMT GEMM building block (B200 keeps a full-rate FP64 pipe: 64 DFMA/clk/SM).
+// FP64 GEMM building block on the FP64 tensor cores (DMMA m8n8k4).
 // C[M×N] = alpha · A[M×K] · op(B) + beta · C, with per-tile K-range clipping for triangular operands.
 // Used by the blocked Cholesky (syrk trailing update), the triangular inverse and the FP64
 // (checker-precision) variance contraction.
@@ -12,11 +12,19 @@ enum { TS_NONE = 0, TS_LOWER = 1 };
 #define DG_BM 128
 #define DG_BN 64
 #define DG_BK 16
+#define DG_LDA (DG_BM + 8)   // ≡ 8 (mod 32) doubles: the 32 lanes of a DMMA fragment load (4 k-rows × 8 consecutive m) hit 32
+#define DG_LDB (DG_BN + 8)   // distinct 8-byte words → 2 shared-memory wavefronts, conflict-free
+
+// FP64 tensor-core MMA (DMMA), warp-level: D(8×8) += A(8×4)·B(4×8).  Fragments (lane = 4g + t): a = A[g][t], b = B[t][g],
+// c/d = C[g][2t], C[g][2t+1].  B200's FP64 tensor rate is about twice its vector DFMA rate, and a fragment load feeds 256
+// FMAs, so the FP64 GEMM-shaped work (potrf/trtri updates, FP64 variance contraction, CMA-ES products) runs here.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 
 // TRANSB = true : B is N×K row-major (C = A·Bᵀ, "NT");  false: B is K×N row-major ("NN").
-// 128×64 tile, 8×4 outputs per thread: 12 LDS per 32 DFMA, so the FP64 pipe — not shared memory — is the limiter
-// (the first version's 4×4 tile ran at 16 TFLOP/s, shared-memory bound).  The next K-slab is prefetched into registers
-// while the current one is consumed.
+// 128×64 CTA tile, 8 warps in a 4×2 grid, each warp a 32×32 sub-tile = 4×4 DMMA tiles (32 accumulator doubles per
+// thread).  The next K-slab is prefetched into registers while the current one is consumed.
 template <bool TRANSB, int EPI>
 __global__ void __launch_bounds__(256, 2)
 dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
@@ -25,11 +33,13 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   A += (long long)blockIdx.z * strideA;
   B += (long long)blockIdx.z * strideB;
   C += (long long)blockIdx.z * strideC;
-  __shared__ double As[DG_BK][DG_BM + 2];
-  __shared__ double Bs[DG_BK][DG_BN + 2];
+  __shared__ double As[DG_BK][DG_LDA];
+  __shared__ double Bs[DG_BK][DG_LDB];
   const int m0 = blockIdx.y * DG_BM, n0 = blockIdx.x * DG_BN;
   if (tileskip == TS_LOWER && n0 > m0 + DG_BM - 1) return;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;   // this warp's sub-tile origin inside the CTA tile
   int kb = kbegin, ke = K;
   if (kmode == KM_UPTO_N) ke = min(K, n0 + DG_BN);
   if (kmode == KM_FROM_N) kb = max(kbegin, n0);
@@ -37,11 +47,11 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   if (kmode == KM_FROM_M) kb = max(kbegin, m0);
   kb = kb & ~(DG_BK - 1);
 
-  double acc[8][4];
+  double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   double pa[8], pb[4];
   auto prefetch = [&](int k0) {
@@ -91,49 +101,56 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
     const bool more = k0 + DG_BK < ke;
     if (more) prefetch(k0 + DG_BK);
 #pragma unroll
-    for (int k = 0; k < DG_BK; k++) {
-      double a[8], b[4];
+    for (int k4 = 0; k4 < DG_BK; k4 += 4) {
+      double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 8; i++) a[i] = As[k][ty + 16 * i];
+      for (int i = 0; i < 4; i++) a[i] = As[k4 + t][wm + 8 * i + g];
 #pragma unroll
-      for (int j = 0; j < 4; j++) b[j] = Bs[k][tx + 16 * j];
+      for (int j = 0; j < 4; j++) b[j] = Bs[k4 + t][wn + 8 * j + g];
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncthreads();
     if (more) commit();
     __syncthreads();
   }
 
+  // accumulator (i, j, e) is C[m0 + wm + 8i + g][n0 + wn + 8j + 2t + e]
   if (EPI == EPI_STORE) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int gm = m0 + ty + 16 * i;
+    for (int i = 0; i < 4; i++) {
+      const int gm = m0 + wm + 8 * i + g;
       if (gm >= M) continue;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int gn = n0 + tx + 16 * j;
-        if (gn >= N) continue;
-        double* c = C + (size_t)gm * ldc + gn;
-        *c = (beta == 0.0) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * (*c);
-      }
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int gn = n0 + wn + 8 * j + 2 * t + e;
+          if (gn >= N) continue;
+          double* c = C + (size_t)gm * ldc + gn;
+          *c = (beta == 0.0) ? alpha * acc[i][j][e] : alpha * acc[i][j][e] + beta * (*c);
+        }
     }
   } else {  // EPI_ROWSUMSQ: C is part[M × ldc], column = this block's n-tile; fixed reduction order
+    __shared__ double rs[2][DG_BM];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 4; i++) {
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int gn = n0 + tx + 16 * j;
-        if (gn < N) s = fma(acc[i][j], acc[i][j], s);
-      }
+      for (int j = 0; j < 4; j++)
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const int gm = m0 + ty + 16 * i;
-      if (tx == 0 && gm < M) C[(size_t)gm * ldc + blockIdx.x] = s;
+        for (int e = 0; e < 2; e++) {
+          const int gn = n0 + wn + 8 * j + 2 * t + e;
+          if (gn < N) s = fma(acc[i][j][e], acc[i][j][e], s);
+        }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);   // the 4 lanes of a row group
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (t == 0) rs[warp & 1][wm + 8 * i + g] = s;
     }
+    __syncthreads();
+    if (tid < DG_BM && m0 + tid < M) C[(size_t)(m0 + tid) * ldc + blockIdx.x] = rs[0][tid] + rs[1][tid];
   }
 }
 
