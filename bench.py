@@ -365,7 +365,8 @@ def main():
             "config": {"workload": f"cfg3: GP({KERNEL}) N={N} D={D}, {ACQ.upper()} sweep over M={M} candidates per GPU (grid {world * M}), fixed theta "
                                    f"(amp 1, ls 0.3*sqrt(D), noise 1e-3), one suggestion per step",
                        "kernel": KERNEL, "acq": ACQ, "per_gpu_candidates": M, "grid_candidates": world * M, "var_mode": args.var_mode,
-                       "l2": "inputs larger than L2 (Xc 128 MiB, W planes 256 MiB, K* scratch ~2 GiB per chunk)", "argmax_index": best.index},
+                       "l2": "inputs larger than L2 (Xc 128 MiB, W planes 256 MiB, K* scratch ~2 GiB per chunk)", "argmax_index": best.index,
+                       "fp64_refined_contenders": eng.last_contenders() if args.var_mode == "tc" else None},
             "e2e": {"value": world * 1e3 / ms_step_e2e, "unit": "suggestions/s", "ms_per_step": ms_step_e2e,
                     "h2d_bytes_per_step": int(X.nbytes + y.nbytes + Xc.nbytes), "d2h_bytes_per_step": 32},
             "gpu_launches": int(launches),

@@ -106,6 +106,12 @@ int kbo_set_scratch_limit(kbo_handle* h, uint64_t bytes);
  * 0 = one CTA per panel.  Same arithmetic, same results to the last bit per j-tile; the default halves the DRAM re-reads.
  * The environment variable KBO_TC_PAIR sets the initial value for new handles. */
 int kbo_set_tc_pair(kbo_handle* h, int enabled);
+/* Tensor-core mode only: re-evaluate on the FP64 path every candidate whose fp32 acquisition value is within 2e-4 of the
+ * maximum (at most 4096 of them) and take the first-index argmax over those FP64 values, so the returned suggestion (index,
+ * value, mu, std) has FP64 accuracy.  Default on; costs one extra pass over (mu, sigma²) and one stream synchronisation.
+ * kbo_last_contenders returns how many candidates the last sweep refined (> 4096: refinement skipped). */
+int kbo_set_tc_refine(kbo_handle* h, int enabled);
+int kbo_last_contenders(kbo_handle* h);
 
 /* ---- tell: GaussianProcessRegressor.fit at fixed θ ($SK/_gpr.py:275-280, 349-368) ---------------
  * X: N×D fp64, y: N fp64, device pointers (x_on_host = 0) or host pointers (x_on_host = 1).

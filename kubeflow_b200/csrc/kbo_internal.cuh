@@ -44,6 +44,9 @@ struct kbo_handle {
   DevBuf varn;          // M (same dtype as mun)
   DevBuf blockbest;     // per-block argmax partials
   DevBuf best;          // one kbo_best for suggest_host
+  DevBuf refine, refine_x;  // contender list / gathered rows of the FP64 refinement (tensor-core mode)
+  int last_contenders = 0;
+  bool tc_refine = true;
   kbo_timings tim{};
   cudaEvent_t ev[8] = {};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_var, ev_cross, ev_acq;

@@ -461,6 +461,147 @@ acq_kernel(const T* __restrict__ mun, const T* __restrict__ varn, int64_t M, int
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 refinement of the suggestion in tensor-core mode.  The sweep's fp32 acquisition values carry the ~1e-6 error of the
+// fp16×3 contraction; a near-tie could therefore pick a different index than the fp64 reference.  Every candidate whose
+// (recomputed, bit-identical) fp32 value is within `delta` of the maximum is a contender: its row goes through the FP64
+// K*/variance path again and the first-index argmax is taken over those FP64 values.  Contenders are a handful, so this is
+// one 14 µs pass plus a few small launches; the arrays returned for parity tests are not touched.
+#define KBO_REFINE_CAP 4096
+__global__ void __launch_bounds__(256)
+contender_kernel(const float* __restrict__ mun, const float* __restrict__ varn, int64_t M, int acq, const double* __restrict__ scal, double xi,
+                 double kappa, const kbo_best* __restrict__ best, int64_t goff, double delta, int* __restrict__ list, int* __restrict__ count) {
+  const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
+  const float thr = (float)(best->value - delta);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256) {
+    const float a = acq == KBO_ACQ_EI    ? acq_value_f32<KBO_ACQ_EI>(mun[i], varn[i], ym, ys, yo, x, kp)
+                    : acq == KBO_ACQ_LCB ? acq_value_f32<KBO_ACQ_LCB>(mun[i], varn[i], ym, ys, yo, x, kp)
+                                         : acq_value_f32<KBO_ACQ_PI>(mun[i], varn[i], ym, ys, yo, x, kp);
+    if (a >= thr) {
+      const int slot = atomicAdd(count, 1);
+      if (slot < KBO_REFINE_CAP) list[slot] = (int)i;
+    }
+  }
+}
+// ascending sort of the contender indices (single CTA, bitonic, padded with INT_MAX) so "first maximum" = lowest index
+__global__ void __launch_bounds__(1024) sort_contenders_kernel(int* __restrict__ list, const int* __restrict__ count) {
+  __shared__ int v[KBO_REFINE_CAP];
+  const int n = min(*count, KBO_REFINE_CAP);
+  for (int i = threadIdx.x; i < KBO_REFINE_CAP; i += 1024) v[i] = i < n ? list[i] : 0x7fffffff;
+  __syncthreads();
+  for (int k = 2; k <= KBO_REFINE_CAP; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < KBO_REFINE_CAP; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const int a = v[i], b = v[l];
+          if ((a > b) == up) {
+            v[i] = b;
+            v[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += 1024) list[i] = v[i];
+}
+template <typename XT>
+__global__ void gather_rows_kernel(const XT* __restrict__ Xc, int D, const int* __restrict__ list, int n, double* __restrict__ Xg) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const int64_t src = list[r];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) Xg[(size_t)r * D + d] = (double)Xc[src * D + d];
+}
+// fp64 acquisition over the n contenders (sorted by index): first maximum wins; writes the refined suggestion
+__global__ void __launch_bounds__(1024)
+refine_best_kernel(const double* __restrict__ mun, const double* __restrict__ varn, const int* __restrict__ list, int n, int acq,
+                   const double* __restrict__ scal, double xi, double kappa, int64_t goff, kbo_best* __restrict__ best) {
+  __shared__ double sv[1024];
+  __shared__ int sp[1024];
+  const double ym = scal[S_YMEAN], ys = scal[S_YSTD], yo = scal[S_YOPT];
+  double bv = -INFINITY;
+  int bp = 0x7fffffff;
+  for (int p = threadIdx.x; p < n; p += 1024) {
+    double mu, sd;
+    const double a = acq_value<double>(mun[p], varn[p], acq, ym, ys, yo, xi, kappa, &mu, &sd);
+    if (a > bv || (bp == 0x7fffffff && a == a)) {   // positions only grow inside a thread: first maximum kept
+      bv = a;
+      bp = p;
+    }
+  }
+  sv[threadIdx.x] = bv;
+  sp[threadIdx.x] = bp;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double ov = sv[threadIdx.x + o];
+      const int op = sp[threadIdx.x + o];
+      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && op < sp[threadIdx.x])) {
+        sv[threadIdx.x] = ov;
+        sp[threadIdx.x] = op;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && sp[0] != 0x7fffffff) {
+    const int p = sp[0];
+    double mu, sd;
+    const double a = acq_value<double>(mun[p], varn[p], acq, ym, ys, yo, xi, kappa, &mu, &sd);
+    best->value = a;
+    best->index = goff + list[p];
+    best->mu = mu;
+    best->std = sd;
+  }
+}
+
+// Σ_i (W k*)_i² for a handful of contender rows: CTA (bx, by) takes W rows [64·bx, 64·bx+64) and contenders [8·by, 8·by+8);
+// a warp owns one W row at a time, lanes stride the columns, butterfly reduction — the summation order depends on neither
+// the contender's position nor their number, so a candidate's refined value is bit-reproducible however the grid is sharded.
+#define KBO_RV_C 8
+__global__ void __launch_bounds__(256)
+refine_var_kernel(const double* __restrict__ W, int ld, int N, const double* __restrict__ Ks, int n, double* __restrict__ part, int nblk) {
+  __shared__ double ssq[8][KBO_RV_C];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * KBO_RV_C;
+  const double* ks[KBO_RV_C];
+#pragma unroll
+  for (int c = 0; c < KBO_RV_C; c++) ks[c] = Ks + (size_t)min(c0 + c, n - 1) * ld;
+  double sq[KBO_RV_C];
+#pragma unroll
+  for (int c = 0; c < KBO_RV_C; c++) sq[c] = 0.0;
+  for (int r = 0; r < 8; r++) {
+    const int i = blockIdx.x * 64 + warp * 8 + r;
+    if (i >= N) break;
+    const double* w = W + (size_t)i * ld;
+    double acc[KBO_RV_C];
+#pragma unroll
+    for (int c = 0; c < KBO_RV_C; c++) acc[c] = 0.0;
+#pragma unroll 4
+    for (int j = lane; j <= i; j += 32) {
+      const double wv = w[j];
+#pragma unroll
+      for (int c = 0; c < KBO_RV_C; c++) acc[c] = fma(wv, ks[c][j], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < KBO_RV_C; c++) {
+      double v = acc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      sq[c] = fma(v, v, sq[c]);
+    }
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < KBO_RV_C; c++) ssq[warp][c] = sq[c];
+  __syncthreads();
+  if (threadIdx.x < KBO_RV_C && c0 + threadIdx.x < n) {
+    double t = 0.0;
+    for (int w8 = 0; w8 < 8; w8++) t += ssq[w8][threadIdx.x];
+    part[(size_t)(c0 + threadIdx.x) * nblk + blockIdx.x] = t;
+  }
+}
+
 static int acq_grid(kbo_handle* h, int64_t M) {
   int64_t g = (M + 2047) / 2048;   // two groups of 4 candidates per thread per trip (1024 per CTA measured slower at 1M: more partials/atomics)
   const int64_t cap = (int64_t)h->sm_count * 8;
@@ -540,6 +681,46 @@ static cudaEvent_t* ev_pair(kbo_handle* h, std::vector<std::pair<cudaEvent_t, cu
   }
 #define KBO_TIME_END()                                 \
   if (_ev) cudaEventRecord((&_ev[0])[1], s);
+
+static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, kbo_best* best_dev, cudaStream_t s) {
+  const int N = h->N, D = h->D, ld = h->ld;
+  const double* scal = (const double*)h->scal.p;
+  KBO_TRY(kbo_reserve(h, h->refine, sizeof(int) * (KBO_REFINE_CAP + 16)));
+  int* list = (int*)h->refine.p;
+  int* count = list + KBO_REFINE_CAP;
+  KBO_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int), s));
+  const double delta = 2e-4;   // ≥ 10× the tensor-core mode's acquisition error bound
+  contender_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa,
+                                                  best_dev, goff, delta, list, count);
+  KBO_LAUNCH_CHECK(h);
+  int n = 0;
+  KBO_CUDA(h, cudaMemcpyAsync(&n, count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaStreamSynchronize(s));
+  h->last_contenders = n;
+  if (n < 1 || n > KBO_REFINE_CAP) return KBO_OK;   // more near-ties than the cap: keep the tensor-core pick (n is reported)
+  sort_contenders_kernel<<<1, 1024, 0, s>>>(list, count);
+  KBO_LAUNCH_CHECK(h);
+  const int njt = (N + 63) / 64;
+  KBO_TRY(kbo_reserve(h, h->refine_x, sizeof(double) * (size_t)n * D));
+  KBO_TRY(kbo_reserve(h, h->Ks64, sizeof(double) * (size_t)n * ld));
+  KBO_TRY(kbo_reserve(h, h->part, sizeof(double) * ((size_t)n * njt + 2 * (size_t)n)));
+  double* Xg = (double*)h->refine_x.p;
+  double* mun64 = (double*)h->part.p + (size_t)n * njt;
+  double* varn64 = mun64 + n;
+  if (xc_dtype == KBO_F64)
+    gather_rows_kernel<double><<<n, 64, 0, s>>>((const double*)Xc, D, list, n, Xg);
+  else
+    gather_rows_kernel<float><<<n, 64, 0, s>>>((const float*)Xc, D, list, n, Xg);
+  KBO_LAUNCH_CHECK(h);
+  KBO_TRY((launch_cross<double, double, 0>(h, Xg, n, n, (double*)h->Ks64.p, ld, nullptr, nullptr, mun64, s)));
+  refine_var_kernel<<<dim3(njt, (n + KBO_RV_C - 1) / KBO_RV_C), 256, 0, s>>>((const double*)h->W.p, ld, N, (const double*)h->Ks64.p, n, (double*)h->part.p, njt);
+  KBO_LAUNCH_CHECK(h);
+  var_from_parts_kernel<<<(n + 255) / 256, 256, 0, s>>>((const double*)h->part.p, n, njt, h->prm.amplitude, varn64);
+  KBO_LAUNCH_CHECK(h);
+  refine_best_kernel<<<1, 1024, 0, s>>>(mun64, varn64, list, n, h->prm.acq, scal, h->prm.xi, h->prm.kappa, goff, best_dev);
+  KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
 
 int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out, double* acq_out,
                 kbo_best* best_dev, cudaStream_t s) {
@@ -622,10 +803,11 @@ int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t 
   // acquisition over the whole grid; y statistics are read from the fit's device scalars (no host sync)
   {
     KBO_TIME_BEGIN(ev_acq, ev_acq_used);
-    if (tc)
+    if (tc) {
       KBO_TRY(launch_acq<float>(h, (const float*)h->mun.p, (const float*)h->varn.p, M, goff, h->prm.acq, 0.0, 1.0, 0.0, scal, h->prm.xi,
                                 h->prm.kappa, mu_out, std_out, acq_out, nullptr, best_dev, s));
-    else
+      if (h->tc_refine && M < 0x7fffffff) KBO_TRY(refine_suggestion(h, Xc, xc_dtype, M, goff, best_dev, s));
+    } else
       KBO_TRY(launch_acq<double>(h, (const double*)h->mun.p, (const double*)h->varn.p, M, goff, h->prm.acq, 0.0, 1.0, 0.0, scal, h->prm.xi,
                                  h->prm.kappa, mu_out, std_out, acq_out, nullptr, best_dev, s));
     KBO_TIME_END();

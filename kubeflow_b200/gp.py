@@ -28,7 +28,7 @@ class GPEngine:
     def __init__(self, device: int = 0, *, kernel: str = "matern52", length_scale=1.0, amplitude: float = 1.0,
                  noise: float = 1e-10, acq: str = "ei", xi: float = 0.01, kappa: float = 1.96,
                  normalize_y: bool = True, var_mode: str = "auto", tc_k_span: int = 0, scratch_limit: int | None = None,
-                 tc_pair: bool | None = None):
+                 tc_pair: bool | None = None, tc_refine: bool | None = None):
         if kernel not in L.KERNELS:
             raise ValueError(f"kernel must be one of {sorted(L.KERNELS)}, got {kernel!r}")
         if acq not in L.ACQS:
@@ -52,6 +52,8 @@ class GPEngine:
             L.check(self.lib, self._h, self.lib.kbo_set_scratch_limit(self._h, int(scratch_limit)))
         if tc_pair is not None:
             L.check(self.lib, self._h, self.lib.kbo_set_tc_pair(self._h, int(bool(tc_pair))))
+        if tc_refine is not None:
+            L.check(self.lib, self._h, self.lib.kbo_set_tc_refine(self._h, int(bool(tc_refine))))
         self._best_dev = torch.empty(4, dtype=torch.float64, device=f"cuda:{self.device}")
 
     # -- plumbing ----------------------------------------------------------------------------------
@@ -109,6 +111,10 @@ class GPEngine:
         rc = self.lib.kbo_fit_info(self._h, C.byref(lml), C.byref(ym), C.byref(ys), C.byref(yo), C.byref(info), self._stream())
         L.check(self.lib, self._h, rc)
         return dict(lml=lml.value, y_mean=ym.value, y_std=ys.value, y_opt=yo.value, info=info.value)
+
+    def last_contenders(self) -> int:
+        """How many candidates the last tensor-core sweep re-evaluated in FP64 (kbo_set_tc_refine)."""
+        return int(self.lib.kbo_last_contenders(self._h))
 
     def lml_grad(self):
         """(lml, grad) of the last tell; grad w.r.t. (log amplitude, log noise, log ℓ_1..ℓ_P) as a NumPy array."""

@@ -286,6 +286,50 @@ def test_lml_gradient_matches_sklearn_golden_and_oracle():
         eng.close()
 
 
+def test_tc_mode_suggestion_is_refined_in_fp64(golden):
+    """Tensor-core mode re-evaluates every candidate within 2e-4 of its fp32 maximum on the FP64 path (kbo_set_tc_refine):
+    the returned suggestion must then equal the FP64 mode's — same index as the oracle's first-index argmax, value / mu / std
+    to FP64 accuracy — even where the arrays of the tensor-core sweep are only 1e-5 accurate.  With the refinement off the
+    suggestion falls back to the fp32 pick."""
+    e64 = _engine(golden, "f64"); e64.tell(golden["X"], golden["y"])
+    b64 = e64.ask(golden["Xc"])
+    etc = _engine(golden, "tc"); etc.tell(golden["X"], golden["y"])
+    btc = etc.ask(golden["Xc"])
+    n = etc.last_contenders()
+    assert 1 <= n <= 4096
+    i_ref = int(np.argmax(golden["acq"]))
+    assert btc.index == b64.index == i_ref
+    assert abs(btc.value - b64.value) <= 1e-12 * max(1.0, abs(b64.value)) and abs(btc.value - golden["acq"][i_ref]) <= TOL_F64
+    assert abs(btc.mu - b64.mu) <= 1e-12 * max(1.0, abs(b64.mu)) and abs(btc.std - b64.std) <= 1e-10
+    raw = _engine(golden, "tc", tc_refine=False); raw.tell(golden["X"], golden["y"])
+    braw = raw.ask(golden["Xc"])
+    _check_argmax(braw, golden["acq"], 5e-5 if golden["acq_kind"] == "lcb" else TOL_TC)
+    for e in (e64, etc, raw):
+        e.close()
+
+
+def test_tc_refinement_resolves_near_ties_like_the_oracle():
+    """Candidates that differ by less than the tensor-core error: copies of the winner nudged by 1e-9 in one coordinate have
+    acquisition values ~1e-9 apart, far below what the fp16x3 variance resolves.  The refined pick must be the oracle's."""
+    X, y, Xc = O.synthetic(512, 20000, 6)
+    th = O.theta_of_record(6)
+    ref = O.suggest(X, y, Xc, kind="matern52", acq="ei", **th)
+    rng = np.random.default_rng(7)
+    near = Xc[ref["index"]][None, :] + 1e-9 * rng.standard_normal((64, 6))
+    Xn = np.concatenate([Xc[:9000], near[:32], Xc[9000:], near[32:]])
+    refn = O.suggest(X, y, Xn, kind="matern52", acq="ei", **th)
+    eng = _engine(dict(kind="matern52", acq="ei", **th), "tc"); eng.tell(X, y)
+    b = eng.ask(Xn)
+    assert eng.last_contenders() >= 65
+    assert b.index == refn["index"] and abs(b.value - refn["value"]) <= TOL_F64
+    # sharded over 4 ranks: every shard refines its own contenders, the (value, lowest index) maximum is the same point
+    q = len(Xn) // 4
+    parts = [eng.ask(Xn[s:s + q + 3], global_offset=s) for s in range(0, len(Xn), q + 3)]
+    win = max(parts, key=lambda p: (p.value, -p.index))
+    assert (win.index, win.value) == (b.index, b.value)
+    eng.close()
+
+
 def test_ties_duplicates_and_sharding():
     X, y, Xc = O.synthetic(96, 1000, 4)
     th = O.theta_of_record(4)
