@@ -120,6 +120,15 @@ int kbo_last_contenders(kbo_handle* h);
  * non-positive pivot is reported by the next synchronising call (kbo_fit_info / kbo_best_to_host). */
 int kbo_fit(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, const kbo_params* p,
             int x_on_host, void* stream);
+/* Append ONE trial (x: D doubles, y) to the fitted history at the same theta without refactorising: the bordered Cholesky
+ * row l = W k, d = sqrt(amp + noise - l.l), the matching row of W = L^-1, then the y statistics, alpha, LML and the fp16
+ * planes are brought up to date — O(N^2) instead of O(N^3) (skopt's constant-liar `ask(n_points=k)` tells
+ * k-1 lies one after another, `Optimizer.tell` refits each time).  Works in place while the history fits its 64-row pitch:
+ * kbo_fit_room() says how many more trials can be appended (0: call kbo_fit with the whole history).  Not positive definite
+ * is reported by kbo_fit_info like after a fit; the handle then needs a kbo_fit.  Results equal a refit's to ~1e-12. */
+int kbo_fit_append(kbo_handle* h, const double* x, double y, int x_on_host, void* stream);
+int kbo_fit_room(kbo_handle* h);
+
 /* synchronises; any out pointer may be NULL.  info = 0 or 1-based index of the failed pivot. */
 int kbo_fit_info(kbo_handle* h, double* lml, double* y_mean, double* y_std, double* y_opt, int32_t* info,
                  void* stream);

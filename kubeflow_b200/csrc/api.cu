@@ -38,7 +38,7 @@ void kbo_destroy(kbo_handle* h) {
   cudaSetDevice(h->device);
   DevBuf* bufs[] = {&h->d_inv_ls, &h->Xs, &h->nx, &h->yn, &h->K, &h->W, &h->Linv, &h->T, &h->alpha, &h->z, &h->Wh, &h->Wl,
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
-                    &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x};
+                    &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : h->ev)
@@ -90,6 +90,22 @@ int kbo_fit(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t 
   }
   return kbo_i_fit(h, X, y, N, D, p, s);
 }
+
+int kbo_fit_append(kbo_handle* h, const double* x, double y, int x_on_host, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!x) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit_append: null argument");
+  if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_append: call kbo_fit first");
+  cudaStream_t s = (cudaStream_t)stream;
+  KBO_CUDA(h, cudaSetDevice(h->device));
+  if (x_on_host) {
+    KBO_TRY(kbo_reserve(h, h->stage_X, sizeof(double) * (size_t)h->D));
+    KBO_CUDA(h, cudaMemcpyAsync(h->stage_X.p, x, sizeof(double) * (size_t)h->D, cudaMemcpyHostToDevice, s));
+    x = (const double*)h->stage_X.p;
+  }
+  return kbo_i_fit_append(h, x, y, s);
+}
+
+int kbo_fit_room(kbo_handle* h) { return (h && h->fitted) ? h->ld - h->N : 0; }
 
 int kbo_fit_info(kbo_handle* h, double* lml, double* y_mean, double* y_std, double* y_opt, int32_t* info, void* stream) {
   if (!h) return KBO_ERR_INVALID;

@@ -448,60 +448,15 @@ int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double
   return KBO_OK;
 }
 
-int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, const kbo_params* p, cudaStream_t s) {
-  if (N < 1 || D < 1 || D > 512) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: need N >= 1 and 1 <= D <= 512 (got N=%d D=%d)", N, D);
-  if (p->n_length_scale != 1 && p->n_length_scale != D)
-    KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: n_length_scale must be 1 or D=%d (got %d)", D, p->n_length_scale);
-  if (!(p->noise >= 0.0) || !(p->amplitude > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: amplitude must be > 0 and noise >= 0");
-  if (p->var_mode < KBO_VAR_F64 || p->var_mode > KBO_VAR_AUTO) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: unknown var_mode %d", p->var_mode);
-  if (p->kernel != KBO_KERNEL_RBF && p->kernel != KBO_KERNEL_MATERN52) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: unknown kernel %d", p->kernel);
-  for (int d = 0; d < p->n_length_scale; d++)
-    if (!(p->length_scale[d] > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: length_scale[%d] must be > 0", d);
-  h->fitted = false;
-  h->have_planes = false;
-  h->N = N;
-  h->D = D;
-  h->ld = round_up(N, 64);
-  h->Npad = round_up(N, 256);
-  h->prm = *p;
-  h->inv_ls.resize(p->n_length_scale);
-  for (int d = 0; d < p->n_length_scale; d++) h->inv_ls[d] = 1.0 / p->length_scale[d];
-  h->prm.length_scale = nullptr;
-  const int ld = h->ld;
-  KBO_TRY(kbo_reserve(h, h->d_inv_ls, sizeof(double) * 512));
-  KBO_TRY(kbo_reserve(h, h->Xs, sizeof(double) * (size_t)N * D));
-  KBO_TRY(kbo_reserve(h, h->XsT, sizeof(double) * (size_t)D * ld));
-  KBO_TRY(kbo_reserve(h, h->nx, sizeof(double) * N));
-  KBO_TRY(kbo_reserve(h, h->yn, sizeof(double) * N));
-  KBO_TRY(kbo_reserve(h, h->K, sizeof(double) * (size_t)N * ld));
-  KBO_TRY(kbo_reserve(h, h->W, sizeof(double) * (size_t)N * ld));
-  KBO_TRY(kbo_reserve(h, h->alpha, sizeof(double) * N));
-  KBO_TRY(kbo_reserve(h, h->z, sizeof(double) * N));
-  KBO_TRY(kbo_reserve(h, h->scal, sizeof(double) * 16));
-  KBO_TRY(kbo_reserve(h, h->info, sizeof(int) * 4));
-  // inv_ls is tiny: stage through pageable memory is fine, but keep it async-safe by copying from the vector we own
-  KBO_CUDA(h, cudaMemcpyAsync(h->d_inv_ls.p, h->inv_ls.data(), sizeof(double) * h->inv_ls.size(), cudaMemcpyHostToDevice, s));
-  prep_x_kernel<<<(N + 127) / 128, 128, 0, s>>>(X, N, D, (const double*)h->d_inv_ls.p, p->n_length_scale, (double*)h->Xs.p, (double*)h->XsT.p, ld, (double*)h->nx.p);
-  KBO_LAUNCH_CHECK(h);
-  prep_y_kernel<<<1, 1024, 0, s>>>(y, N, p->normalize_y, (double*)h->yn.p, (double*)h->scal.p);
-  KBO_LAUNCH_CHECK(h);
-  // KBO_FIT_TRACE=1: per-phase CUDA-event timings on stderr (debug aid; adds stream syncs)
-  static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
-  cudaEvent_t te[6];
-  if (trace)
-    for (auto& e : te) cudaEventCreate(&e);
-  if (trace) cudaEventRecord(te[0], s);
-  KBO_TRY(kbo_i_gram(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, s));
-  if (trace) cudaEventRecord(te[1], s);
-  KBO_TRY(kbo_i_potrf(h, (double*)h->K.p, N, ld, (int*)h->info.p, s));
-  if (trace) cudaEventRecord(te[2], s);
-  KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
-  if (trace) cudaEventRecord(te[3], s);
+// alpha = Wᵀ(W yn), LML, and (when the tensor-core sweep may be used) the fp16 hi/lo planes of W — shared by fit and append
+static int fit_finish(kbo_handle* h, cudaStream_t s) {
+  const int N = h->N, ld = h->ld;
+  const kbo_params* p = &h->prm;
   trmv_lower_kernel<<<(N + 7) / 8, 256, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->yn.p, (double*)h->z.p);
   KBO_LAUNCH_CHECK(h);
   {
     const int nslab = (N + 255) / 256;
-    KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ld));  // reuse the trtri scratch for the slab partials
+    KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)nslab * N));  // the trtri scratch doubles as the slab partials
     dim3 g((N + 127) / 128, nslab);
     trmv_lower_t_kernel<<<g, 128, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->z.p, (double*)h->T.p);
     KBO_LAUNCH_CHECK(h);
@@ -523,6 +478,63 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
     split_w_kernel<<<g, 256, 0, s>>>((const double*)h->W.p, N, ld, Npad, amax, (__half*)h->Wh.p, (__half*)h->Wl.p, (double*)h->scal.p + 6);
     KBO_LAUNCH_CHECK(h);
   }
+  return KBO_OK;
+}
+
+int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, const kbo_params* p, cudaStream_t s) {
+  if (N < 1 || D < 1 || D > 512) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: need N >= 1 and 1 <= D <= 512 (got N=%d D=%d)", N, D);
+  if (p->n_length_scale != 1 && p->n_length_scale != D)
+    KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: n_length_scale must be 1 or D=%d (got %d)", D, p->n_length_scale);
+  if (!(p->noise >= 0.0) || !(p->amplitude > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: amplitude must be > 0 and noise >= 0");
+  if (p->var_mode < KBO_VAR_F64 || p->var_mode > KBO_VAR_AUTO) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: unknown var_mode %d", p->var_mode);
+  if (p->kernel != KBO_KERNEL_RBF && p->kernel != KBO_KERNEL_MATERN52) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: unknown kernel %d", p->kernel);
+  for (int d = 0; d < p->n_length_scale; d++)
+    if (!(p->length_scale[d] > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: length_scale[%d] must be > 0", d);
+  h->fitted = false;
+  h->have_planes = false;
+  h->N = N;
+  h->D = D;
+  h->ld = round_up(N, 64);
+  h->Npad = round_up(N, 256);
+  h->prm = *p;
+  h->inv_ls.resize(p->n_length_scale);
+  for (int d = 0; d < p->n_length_scale; d++) h->inv_ls[d] = 1.0 / p->length_scale[d];
+  h->prm.length_scale = nullptr;
+  const int ld = h->ld;
+  KBO_TRY(kbo_reserve(h, h->d_inv_ls, sizeof(double) * 512));
+  // rows are reserved up to the pitch (ld = N rounded up to 64) so kbo_fit_append can add trials in place until the next
+  // 64-boundary; past it the caller refits (which also bounds how many appended rows ever stack on one factorisation)
+  KBO_TRY(kbo_reserve(h, h->Xs, sizeof(double) * (size_t)ld * D));
+  KBO_TRY(kbo_reserve(h, h->XsT, sizeof(double) * (size_t)D * ld));
+  KBO_TRY(kbo_reserve(h, h->nx, sizeof(double) * ld));
+  KBO_TRY(kbo_reserve(h, h->yn, sizeof(double) * ld));
+  KBO_TRY(kbo_reserve(h, h->yraw, sizeof(double) * ld));
+  KBO_TRY(kbo_reserve(h, h->K, sizeof(double) * (size_t)ld * ld));
+  KBO_TRY(kbo_reserve(h, h->W, sizeof(double) * (size_t)ld * ld));
+  KBO_TRY(kbo_reserve(h, h->alpha, sizeof(double) * ld));
+  KBO_TRY(kbo_reserve(h, h->z, sizeof(double) * ld));
+  KBO_CUDA(h, cudaMemcpyAsync(h->yraw.p, y, sizeof(double) * N, cudaMemcpyDeviceToDevice, s));
+  KBO_TRY(kbo_reserve(h, h->scal, sizeof(double) * 16));
+  KBO_TRY(kbo_reserve(h, h->info, sizeof(int) * 4));
+  // inv_ls is tiny: stage through pageable memory is fine, but keep it async-safe by copying from the vector we own
+  KBO_CUDA(h, cudaMemcpyAsync(h->d_inv_ls.p, h->inv_ls.data(), sizeof(double) * h->inv_ls.size(), cudaMemcpyHostToDevice, s));
+  prep_x_kernel<<<(N + 127) / 128, 128, 0, s>>>(X, N, D, (const double*)h->d_inv_ls.p, p->n_length_scale, (double*)h->Xs.p, (double*)h->XsT.p, ld, (double*)h->nx.p);
+  KBO_LAUNCH_CHECK(h);
+  prep_y_kernel<<<1, 1024, 0, s>>>(y, N, p->normalize_y, (double*)h->yn.p, (double*)h->scal.p);
+  KBO_LAUNCH_CHECK(h);
+  // KBO_FIT_TRACE=1: per-phase CUDA-event timings on stderr (debug aid; adds stream syncs)
+  static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
+  cudaEvent_t te[6];
+  if (trace)
+    for (auto& e : te) cudaEventCreate(&e);
+  if (trace) cudaEventRecord(te[0], s);
+  KBO_TRY(kbo_i_gram(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, s));
+  if (trace) cudaEventRecord(te[1], s);
+  KBO_TRY(kbo_i_potrf(h, (double*)h->K.p, N, ld, (int*)h->info.p, s));
+  if (trace) cudaEventRecord(te[2], s);
+  KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
+  if (trace) cudaEventRecord(te[3], s);
+  KBO_TRY(fit_finish(h, s));
   if (trace) {
     cudaEventRecord(te[4], s);
     cudaEventSynchronize(te[4]);
@@ -535,5 +547,111 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
     for (auto& e : te) cudaEventDestroy(e);
   }
   h->fitted = true;
+  return KBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kbo_fit_append: one more trial at the fitted θ without refactorising (constant-liar asks and the
+// steady state of a Katib experiment, where each request adds a trial or two to a history the service already holds).
+// With W = L⁻¹ resident the bordered factorisation is three matrix-vector passes:
+//   k = amp·k(X, x) ;  l = W k ;  d = sqrt(amp + noise − l·l) ;  L ← [[L,0],[lᵀ,d]] ;  W ← [[W,0],[−(Wᵀl)ᵀ/d, 1/d]]
+// followed by the same finish as a fit (y statistics change with every trial, so yn, alpha and the LML are recomputed).
+__global__ void append_x_kernel(const double* __restrict__ x, int D, const double* __restrict__ inv_ls, int n_ls, double* __restrict__ Xs,
+                                double* __restrict__ XsT, int ldx, double* __restrict__ nx, int row, double y, double* __restrict__ yraw) {
+  for (int d = threadIdx.x; d < D; d += 256) {
+    const double v = x[d] * inv_ls[n_ls == 1 ? 0 : d];
+    Xs[(size_t)row * D + d] = v;
+    XsT[(size_t)d * ldx + row] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;   // same left-to-right fma chain over d as prep_x_kernel: nx is bit-identical to a refit's
+    for (int d = 0; d < D; d++) {
+      const double v = Xs[(size_t)row * D + d];
+      t = fma(v, v, t);
+    }
+    nx[row] = t;
+    yraw[row] = y;
+  }
+}
+// k_j = amp·k(x_row, x_j) for j < row, written into row `row` of the K/L buffer (exact differences, like gram_kernel)
+__global__ void gram_row_kernel(const double* __restrict__ Xs, int D, int row, int kind, double amp, double* __restrict__ Krow) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= row) return;
+  double d2 = 0.0;
+  for (int d = 0; d < D; d++) {
+    const double df = Xs[(size_t)row * D + d] - Xs[(size_t)j * D + d];
+    d2 = fma(df, df, d2);
+  }
+  Krow[j] = amp * kbo_kernel_exact(d2, kind);
+}
+// after l = W k: d² = amp + noise − Σ l², L row ← (l, d, 0…), and the info flag if the bordered matrix is not PD
+__global__ void __launch_bounds__(1024) append_diag_kernel(const double* __restrict__ l, int row, int ld, double knn, double* __restrict__ Lrow,
+                                                          double* __restrict__ dinv, int* __restrict__ info) {
+  __shared__ double red[1024];
+  const int t = threadIdx.x;
+  double a = 0.0;
+  for (int j = t; j < row; j += 1024) a = fma(l[j], l[j], a);
+  red[t] = a;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  const double d2 = knn - red[0];
+  const bool ok = d2 > 0.0;
+  const double d = ok ? sqrt(d2) : 1.0;
+  for (int j = t; j < ld; j += 1024) Lrow[j] = j < row ? l[j] : (j == row ? d : 0.0);
+  if (t == 0) {
+    *dinv = 1.0 / d;
+    if (!ok && *info == 0) *info = row + 1;
+  }
+}
+// W row ← (−(Wᵀl)/d, 1/d, 0…)
+__global__ void append_wrow_kernel(const double* __restrict__ wtl, int row, int ld, const double* __restrict__ dinv, double* __restrict__ Wrow) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ld) return;
+  const double di = *dinv;
+  Wrow[j] = j < row ? -wtl[j] * di : (j == row ? di : 0.0);
+}
+
+int kbo_i_fit_append(kbo_handle* h, const double* x_dev, double y, cudaStream_t s) {
+  if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_append: call kbo_fit first");
+  const int row = h->N, ld = h->ld, D = h->D;
+  if (row + 1 > ld) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_append: no room (N=%d fills its %d-row pitch): call kbo_fit with the whole history", row, ld);
+  double* Krow = (double*)h->K.p + (size_t)row * ld;
+  double* Wrow = (double*)h->W.p + (size_t)row * ld;
+  KBO_TRY(kbo_reserve(h, h->lrow, sizeof(double) * (2 * (size_t)ld + 8)));
+  double* l = (double*)h->lrow.p;
+  double* wtl = l + ld;
+  double* dinv = wtl + ld;
+  append_x_kernel<<<1, 256, 0, s>>>(x_dev, D, (const double*)h->d_inv_ls.p, h->prm.n_length_scale, (double*)h->Xs.p, (double*)h->XsT.p, ld,
+                                    (double*)h->nx.p, row, y, (double*)h->yraw.p);
+  KBO_LAUNCH_CHECK(h);
+  if (row > 0) {
+    gram_row_kernel<<<(row + 127) / 128, 128, 0, s>>>((const double*)h->Xs.p, D, row, h->prm.kernel, h->prm.amplitude, Krow);
+    KBO_LAUNCH_CHECK(h);
+    trmv_lower_kernel<<<(row + 7) / 8, 256, 0, s>>>((const double*)h->W.p, row, ld, Krow, l);
+    KBO_LAUNCH_CHECK(h);
+  }
+  append_diag_kernel<<<1, 1024, 0, s>>>(l, row, ld, h->prm.amplitude + h->prm.noise, Krow, dinv, (int*)h->info.p);
+  KBO_LAUNCH_CHECK(h);
+  {
+    const int nslab = (row + 255) / 256;
+    KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)(nslab + 1) * ld));
+    if (row > 0) {
+      dim3 g((row + 127) / 128, nslab);
+      trmv_lower_t_kernel<<<g, 128, 0, s>>>((const double*)h->W.p, row, ld, l, (double*)h->T.p);
+      KBO_LAUNCH_CHECK(h);
+      trmv_t_reduce_kernel<<<(row + 127) / 128, 128, 0, s>>>((const double*)h->T.p, row, nslab, wtl);
+      KBO_LAUNCH_CHECK(h);
+    }
+    append_wrow_kernel<<<(ld + 255) / 256, 256, 0, s>>>(wtl, row, ld, dinv, Wrow);
+    KBO_LAUNCH_CHECK(h);
+  }
+  h->N = row + 1;
+  prep_y_kernel<<<1, 1024, 0, s>>>((const double*)h->yraw.p, h->N, h->prm.normalize_y, (double*)h->yn.p, (double*)h->scal.p);
+  KBO_LAUNCH_CHECK(h);
+  KBO_TRY(fit_finish(h, s));
   return KBO_OK;
 }

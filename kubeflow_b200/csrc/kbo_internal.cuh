@@ -32,6 +32,7 @@ struct kbo_handle {
   DevBuf d_inv_ls;             // D doubles
   DevBuf XsT;                  // Xs transposed: D × ld (coalesced trial-tile loads in the K* kernel)
   DevBuf Xs, nx, yn, K, W, Linv, T, alpha, z;
+  DevBuf yraw, lrow;   // raw y (re-normalised on append) and the append's work vectors
   DevBuf Wh, Wl;        // fp16 planes Npad×Npad (TC mode)
   DevBuf scal;          // device scalars, see ScalIdx
   DevBuf info;          // int32: potrf info
@@ -105,6 +106,7 @@ static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m 
 int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double amp, double noise, double* K, int ldk,
                cudaStream_t s);
 int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s);
+int kbo_i_fit_append(kbo_handle* h, const double* x_dev, double y, cudaStream_t s);
 int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int ldw, cudaStream_t s);
 int kbo_i_zero_upper(kbo_handle* h, double* A, int N, int lda, cudaStream_t s);
 int kbo_i_fit(kbo_handle* h, const double* X_dev, const double* y_dev, int N, int D, const kbo_params* p, cudaStream_t s);

@@ -106,6 +106,24 @@ class GPEngine:
         self.N, self.D = int(N), int(D)
         return self
 
+    def room(self) -> int:
+        """How many more trials `append` can add in place (0: `tell` the whole history again)."""
+        return int(self.lib.kbo_fit_room(self._h))
+
+    def append(self, x, y: float):
+        """One more trial at the fitted θ: bordered Cholesky row instead of a refit (kbo_fit_append; what skopt's constant-liar
+        `ask(n_points=k)` needs k-1 times per request, and what a steady Katib experiment needs once per finished trial)."""
+        if self.N == 0:
+            raise L.KboError(L.KBO_ERR_STATE, "append() before tell(): call tell(X, y) first")
+        x = self._as_host_f64(x).reshape(-1)
+        if x.shape[0] != self.D:
+            raise ValueError(f"x has {x.shape[0]} values, fit had D={self.D}")
+        with torch.cuda.device(self.device):
+            rc = self.lib.kbo_fit_append(self._h, x.ctypes.data, float(y), 1, self._stream())
+        L.check(self.lib, self._h, rc)
+        self.N += 1
+        return self
+
     def fit_info(self):
         lml, ym, ys, yo, info = C.c_double(), C.c_double(), C.c_double(), C.c_double(), C.c_int32()
         rc = self.lib.kbo_fit_info(self._h, C.byref(lml), C.byref(ym), C.byref(ys), C.byref(yo), C.byref(info), self._stream())

@@ -26,7 +26,7 @@ class Optimizer:
     def __init__(self, dimensions, base_estimator="GP", n_initial_points=10, acq_func="EI", acq_optimizer="sampling",
                  random_state=None, *, n_points=65536, kernel="matern52", length_scale=None, amplitude=1.0, noise=1e-3, xi=0.01,
                  kappa=1.96, var_mode="auto", theta_grid=1, theta_search=0, theta_fit=None, theta_fit_maxiter=25, ard=False, device=0, engine=None,
-                 candidate_backend="torch"):
+                 candidate_backend="torch", incremental=True):
         if str(base_estimator).upper() != "GP":
             raise ValueError("base_estimator must be GP (RF/ET/GBRT are not part of the GPU path)")
         self.space = dimensions if isinstance(dimensions, Space) else Space(dimensions)
@@ -54,6 +54,9 @@ class Optimizer:
         self.Xi, self.yi = [], []
         self._Xt = []                 # transformed rows, appended on tell (the history is resent on every request)
         self._engine = engine
+        self.incremental = bool(incremental)   # False: refit on every ask, as skopt does
+        self._fit_state = None        # (θ key, rows in the engine, digest of those rows): lets a request that only adds trials append
+        self.last_fit = None          # "fit" | "append" | "reuse": what the last ask did to the engine (diagnostics, tests)
         self.last_best = None
 
     # ------------------------------------------------------------------------------------------------------
@@ -78,6 +81,44 @@ class Optimizer:
         e.length_scale = np.atleast_1d(np.asarray(ls, dtype=np.float64))
         return e
 
+    @staticmethod
+    def _digest(Xt, ya, n):
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        h.update(np.ascontiguousarray(Xt[:n]).tobytes())
+        h.update(np.ascontiguousarray(ya[:n]).tobytes())
+        return h.digest()
+
+    def _tell_engine(self, eng, Xt, ya, max_append=16):
+        """Bring the engine to the history (Xt, ya) at its current θ.  Katib resends the whole history on every request and
+        the constant liar extends it one row at a time, so most calls differ from what the engine already holds by a few
+        appended rows: those go through kbo_fit_append (O(N²) each) instead of a refit (O(N³)) while there is room in the
+        64-row pitch; anything else — different θ, edited rows, a shorter history — refits."""
+        key = (eng.kernel, tuple(np.atleast_1d(eng.length_scale).tolist()), eng.amplitude, eng.noise, eng.normalize_y, eng.var_mode,
+               eng.acq, eng.xi, eng.kappa)
+        n, st = len(ya), self._fit_state
+        self._fit_state = None          # stays None if anything below raises: the engine state is then unknown
+        done = None
+        if self.incremental and st is not None and st[0] == key and st[1] <= n <= st[1] + max_append and self._digest(Xt, ya, st[1]) == st[2]:
+            if n == st[1]:
+                done = "reuse"
+            elif eng.room() >= n - st[1]:
+                for i in range(st[1], n):
+                    eng.append(Xt[i], ya[i])
+                done = "append"
+        if done is None:
+            eng.tell(Xt, ya)
+            done = "fit"
+        self.last_fit = done
+        self._fit_state = (key, n, self._digest(Xt, ya, n))
+
+    def _sweep(self, eng, cand):
+        try:
+            return eng.ask(cand)
+        except Exception:
+            self._fit_state = None      # e.g. an appended row made K singular: the next ask must refit from the history
+            raise
+
     def _default_ls(self):
         return 0.3 * np.sqrt(self.space.transformed_n_dims) if self.length_scale is None else self.length_scale
 
@@ -98,6 +139,7 @@ class Optimizer:
                 cands += [(float(np.exp(tr.uniform(np.log(0.2), np.log(5.0)))), float(np.exp(tr.uniform(np.log(1e-6), np.log(1e-1)))))
                           for _ in range(self.theta_search)]
             best_lml, best_t = -np.inf, (1.0, self.noise)
+            self._fit_state = None
             for m, nz in cands:
                 eng.length_scale, eng.noise = base * m, nz
                 eng.tell(Xt, ya)
@@ -116,6 +158,8 @@ class Optimizer:
             x0 = np.concatenate([np.log(ls0), [np.log(max(eng.noise, 1e-8))]])
             bounds = [(np.log(1e-2), np.log(1e2))] * len(ls0) + [(np.log(1e-8), np.log(1.0))]
 
+            self._fit_state = None
+
             def negative_lml(t):
                 eng.length_scale, eng.noise = np.exp(t[:-1]), float(np.exp(t[-1]))
                 eng.tell(Xt, ya)
@@ -128,7 +172,7 @@ class Optimizer:
             res = minimize(negative_lml, x0, jac=True, method="L-BFGS-B", bounds=bounds, options=dict(maxiter=self.theta_fit_maxiter))
             eng.length_scale, eng.noise = np.exp(res.x[:-1]), float(np.exp(res.x[-1]))
             self.last_theta = dict(length_scale=eng.length_scale.copy(), noise=eng.noise, lml=-float(res.fun), nfev=int(res.nfev))
-        eng.tell(Xt, ya)
+        self._tell_engine(eng, Xt, ya)
         if self.candidate_backend == "torch":
             import torch
             dev = torch.device("cuda", self.device)
@@ -136,11 +180,11 @@ class Optimizer:
                 self._tgen = torch.Generator(device=dev)
                 self._tgen.manual_seed(int(self._seed) if self._seed is not None else int(self.rng.integers(0, 2 ** 31)))
             cand = self.space.rvs_transformed_torch(self.n_points, self._tgen, dev)
-            best = eng.ask(cand)
+            best = self._sweep(eng, cand)
             row = cand[best.index:best.index + 1].to(torch.float64).cpu().numpy()
         else:
             cand = self.space.rvs_transformed(self.n_points, self.rng, np.float32)
-            best = eng.ask(cand)
+            best = self._sweep(eng, cand)
             row = cand[best.index:best.index + 1].astype(np.float64)
         self.last_best = best
         return self.space.inverse_transform(row)[0]

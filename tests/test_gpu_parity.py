@@ -436,3 +436,85 @@ def test_suggest_host_end_to_end():
     assert best.index == ref["index"] or abs(ref["acq"][best.index] - ref["value"]) < TOL_TC
     assert t["launches"] > 0 and t["total_ms"] > 0 and t["var_kernel_ms"] > 0
     eng.close()
+
+
+@pytest.mark.parametrize("N0,k,var_mode,kind", [(200, 5, "f64", "matern52"), (70, 3, "f64", "rbf"), (1100, 3, "tc", "matern52"), (1, 4, "f64", "rbf")])
+def test_fit_append_matches_refit_and_oracle(N0, k, var_mode, kind):
+    """kbo_fit_append (bordered Cholesky row + row of W) against a refit of the extended history and against the oracle:
+    factors, alpha, y statistics, LML and the suggestion must agree as if the history had been told in one go."""
+    D = 6
+    X, y, Xc = O.synthetic(N0 + k, 5000, D)
+    th = O.theta_of_record(D)
+    kw = dict(kind=kind, acq="ei", **th)
+    inc = _engine(kw, var_mode); inc.tell(X[:N0], y[:N0])
+    assert inc.room() == (-N0) % 64
+    for i in range(N0, N0 + k):
+        inc.append(X[i], y[i])
+    ref = _engine(kw, var_mode); ref.tell(X, y)
+    for a, b in zip(inc.state(), ref.state()):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=0, atol=2e-10)
+    ii, ir = inc.fit_info(), ref.fit_info()
+    for key in ("y_mean", "y_std", "y_opt"):
+        assert abs(ii[key] - ir[key]) <= 1e-13 * max(1.0, abs(ir[key]))
+    assert abs(ii["lml"] - ir["lml"]) <= 1e-9 * max(1.0, abs(ir["lml"]))
+    bi, mi, si, ai = inc.ask(Xc, return_arrays=True)
+    br, mr, sr, ar = ref.ask(Xc, return_arrays=True)
+    tol = 1e-9 if var_mode == "f64" else 2e-6
+    np.testing.assert_allclose(ai.cpu().numpy(), ar.cpu().numpy(), rtol=0, atol=tol)
+    np.testing.assert_allclose(mi.cpu().numpy(), mr.cpu().numpy(), rtol=0, atol=1e-9)
+    assert bi.index == br.index and abs(bi.value - br.value) <= 1e-9
+    orc = O.suggest(X, y, Xc, kind=kind, acq="ei", **th)
+    _check_argmax(bi, orc["acq"], TOL_F64)            # f64 natively, tc through the FP64 refinement of the contenders
+    gl, gg = inc.lml_grad()
+    rl, rg = ref.lml_grad()
+    np.testing.assert_allclose(gg, rg, rtol=1e-8, atol=1e-8)
+    inc.close(); ref.close()
+
+
+def test_fit_append_room_and_errors():
+    from kubeflow_b200 import _lib as Lb
+    X, y, _ = O.synthetic(64, 10, 3)
+    eng = _engine(dict(kind="rbf", acq="ei", **O.theta_of_record(3)), "f64")
+    with pytest.raises(Lb.KboError):
+        eng.append(X[0], 0.0)                   # before tell
+    eng.tell(X, y)
+    assert eng.room() == 0
+    with pytest.raises(Lb.KboError):
+        eng.append(X[0] + 0.5, 0.0)             # the 64-row pitch is full: the caller refits
+    eng.tell(X[:63], y[:63])
+    with pytest.raises(ValueError):
+        eng.append(X[63][:2], 0.0)
+    eng.append(X[63], y[63])
+    assert eng.room() == 0 and eng.N == 64
+    eng.close()
+
+
+def test_optimizer_constant_liar_appends_instead_of_refitting():
+    """ask(n_points=3) tells two constant lies: with `incremental` they are appended (kbo_fit_append), without it refitted as
+    skopt does — the three suggested points must be the same; and a later request that resends the history plus one finished
+    trial appends as well, while an edited history falls back to a refit."""
+    from kubeflow_b200.optimizer import Optimizer
+    from kubeflow_b200.space import Real
+    dims = [Real(0.0, 1.0, name=f"x{i}") for i in range(4)]
+    rng = np.random.default_rng(3)
+    X0 = rng.random((40, 4)).tolist()
+    y0 = [float(np.sin(3 * sum(r))) for r in X0]
+    outs, fits = [], []
+    for inc in (True, False):
+        opt = Optimizer(dims, n_initial_points=5, random_state=11, n_points=20000, incremental=inc)
+        opt.tell(X0, y0)
+        pts = opt.ask(n_points=3)
+        outs.append(np.asarray(pts))
+        fits.append(opt.last_fit)
+        if inc:
+            opt.tell([pts[0]], [0.123])
+            opt.ask()
+            # engine held history+2 lies; the real history is now history+1 real trial: rows differ -> refit, not a silent append
+            assert opt.last_fit == "fit"
+            opt.tell([pts[1]], [0.456])
+            opt.ask()
+            assert opt.last_fit == "append"
+            opt.ask()
+            assert opt.last_fit == "reuse"
+    assert fits == ["append", "fit"]
+    np.testing.assert_allclose(outs[0], outs[1], rtol=0, atol=0)
