@@ -128,6 +128,10 @@ int kbo_fit(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t 
  * is reported by kbo_fit_info like after a fit; the handle then needs a kbo_fit.  Results equal a refit's to ~1e-12. */
 int kbo_fit_append(kbo_handle* h, const double* x, double y, int x_on_host, void* stream);
 int kbo_fit_room(kbo_handle* h);
+/* Keep the first n_keep trials of the fitted history, optionally with new targets y[0..n_keep) (NULL: unchanged).  The
+ * leading blocks of L and L^-1 are the factors of the shorter history and y enters only through yn / alpha / LML, so this is
+ * O(N^2): it drops constant-liar rows before the real trials are appended and replaces a lie by the observed value. */
+int kbo_fit_rebase(kbo_handle* h, int32_t n_keep, const double* y, int y_on_host, void* stream);
 
 /* synchronises; any out pointer may be NULL.  info = 0 or 1-based index of the failed pivot. */
 int kbo_fit_info(kbo_handle* h, double* lml, double* y_mean, double* y_std, double* y_opt, int32_t* info,

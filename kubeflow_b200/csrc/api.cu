@@ -105,6 +105,20 @@ int kbo_fit_append(kbo_handle* h, const double* x, double y, int x_on_host, void
   return kbo_i_fit_append(h, x, y, s);
 }
 
+int kbo_fit_rebase(kbo_handle* h, int32_t n_keep, const double* y, int y_on_host, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_rebase: call kbo_fit first");
+  if (n_keep < 1 || n_keep > h->N) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit_rebase: need 1 <= n_keep <= N=%d (got %d)", h->N, n_keep);
+  cudaStream_t s = (cudaStream_t)stream;
+  KBO_CUDA(h, cudaSetDevice(h->device));
+  if (y && y_on_host) {
+    KBO_TRY(kbo_reserve(h, h->stage_y, sizeof(double) * (size_t)n_keep));
+    KBO_CUDA(h, cudaMemcpyAsync(h->stage_y.p, y, sizeof(double) * (size_t)n_keep, cudaMemcpyHostToDevice, s));
+    y = (const double*)h->stage_y.p;
+  }
+  return kbo_i_fit_rebase(h, n_keep, y, s);
+}
+
 int kbo_fit_room(kbo_handle* h) { return (h && h->fitted) ? h->ld - h->N : 0; }
 
 int kbo_fit_info(kbo_handle* h, double* lml, double* y_mean, double* y_std, double* y_opt, int32_t* info, void* stream) {

@@ -655,3 +655,23 @@ int kbo_i_fit_append(kbo_handle* h, const double* x_dev, double y, cudaStream_t 
   KBO_TRY(fit_finish(h, s));
   return KBO_OK;
 }
+
+// kbo_fit_rebase: keep the first n_keep trials of the fitted history (the leading blocks of L and W = L⁻¹ ARE the factors of
+// the shorter history), optionally with new y values — y enters only through yn/alpha/LML.  Drops constant-liar rows before
+// the real trials are appended, and replaces a lie by the observed value when the trial finishes.
+__global__ void clear_info_above_kernel(int* info, int n_keep) {
+  if (*info > n_keep) *info = 0;
+}
+int kbo_i_fit_rebase(kbo_handle* h, int n_keep, const double* y_dev, cudaStream_t s) {
+  if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_rebase: call kbo_fit first");
+  if (n_keep < 1 || n_keep > h->N) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit_rebase: need 1 <= n_keep <= N=%d (got %d)", h->N, n_keep);
+  if (y_dev) KBO_CUDA(h, cudaMemcpyAsync(h->yraw.p, y_dev, sizeof(double) * n_keep, cudaMemcpyDeviceToDevice, s));
+  h->N = n_keep;
+  h->Npad = round_up(n_keep, 256);
+  clear_info_above_kernel<<<1, 1, 0, s>>>((int*)h->info.p, n_keep);
+  KBO_LAUNCH_CHECK(h);
+  prep_y_kernel<<<1, 1024, 0, s>>>((const double*)h->yraw.p, h->N, h->prm.normalize_y, (double*)h->yn.p, (double*)h->scal.p);
+  KBO_LAUNCH_CHECK(h);
+  KBO_TRY(fit_finish(h, s));
+  return KBO_OK;
+}

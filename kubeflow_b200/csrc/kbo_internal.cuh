@@ -107,6 +107,7 @@ int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double
                cudaStream_t s);
 int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s);
 int kbo_i_fit_append(kbo_handle* h, const double* x_dev, double y, cudaStream_t s);
+int kbo_i_fit_rebase(kbo_handle* h, int n_keep, const double* y_dev, cudaStream_t s);
 int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int ldw, cudaStream_t s);
 int kbo_i_zero_upper(kbo_handle* h, double* A, int N, int lda, cudaStream_t s);
 int kbo_i_fit(kbo_handle* h, const double* X_dev, const double* y_dev, int N, int D, const kbo_params* p, cudaStream_t s);

@@ -124,6 +124,21 @@ class GPEngine:
         self.N += 1
         return self
 
+    def rebase(self, n_keep: int, y=None):
+        """Keep the first `n_keep` trials (optionally with new targets): drops constant-liar rows, swaps a lie for the
+        observed value — no refactorisation (kbo_fit_rebase)."""
+        yp = None
+        if y is not None:
+            y = self._as_host_f64(y).reshape(-1)
+            if y.shape[0] < n_keep:
+                raise ValueError(f"y has {y.shape[0]} values, need n_keep={n_keep}")
+            yp = y.ctypes.data
+        with torch.cuda.device(self.device):
+            rc = self.lib.kbo_fit_rebase(self._h, int(n_keep), yp, 1, self._stream())
+        L.check(self.lib, self._h, rc)
+        self.N = int(n_keep)
+        return self
+
     def fit_info(self):
         lml, ym, ys, yo, info = C.c_double(), C.c_double(), C.c_double(), C.c_double(), C.c_int32()
         rc = self.lib.kbo_fit_info(self._h, C.byref(lml), C.byref(ym), C.byref(ys), C.byref(yo), C.byref(info), self._stream())

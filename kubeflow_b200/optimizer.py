@@ -81,36 +81,36 @@ class Optimizer:
         e.length_scale = np.atleast_1d(np.asarray(ls, dtype=np.float64))
         return e
 
-    @staticmethod
-    def _digest(Xt, ya, n):
-        import hashlib
-        h = hashlib.blake2b(digest_size=16)
-        h.update(np.ascontiguousarray(Xt[:n]).tobytes())
-        h.update(np.ascontiguousarray(ya[:n]).tobytes())
-        return h.digest()
-
     def _tell_engine(self, eng, Xt, ya, max_append=16):
         """Bring the engine to the history (Xt, ya) at its current θ.  Katib resends the whole history on every request and
-        the constant liar extends it one row at a time, so most calls differ from what the engine already holds by a few
-        appended rows: those go through kbo_fit_append (O(N²) each) instead of a refit (O(N³)) while there is room in the
-        64-row pitch; anything else — different θ, edited rows, a shorter history — refits."""
+        the constant liar extends it one row at a time, so most calls differ from what the engine already holds only past a
+        long common prefix of rows: the engine keeps that prefix (kbo_fit_rebase — the leading blocks of L and L⁻¹ are the
+        factors of the shorter history; targets are replaced wholesale, so a lie that became an observation costs nothing) and
+        the few new rows are appended (kbo_fit_append, O(N²) each) while there is room in the 64-row pitch.  Anything else —
+        a different θ, an edited early row, many new rows — refits (O(N³)) as skopt does on every tell."""
         key = (eng.kernel, tuple(np.atleast_1d(eng.length_scale).tolist()), eng.amplitude, eng.noise, eng.normalize_y, eng.var_mode,
                eng.acq, eng.xi, eng.kappa)
         n, st = len(ya), self._fit_state
         self._fit_state = None          # stays None if anything below raises: the engine state is then unknown
         done = None
-        if self.incremental and st is not None and st[0] == key and st[1] <= n <= st[1] + max_append and self._digest(Xt, ya, st[1]) == st[2]:
-            if n == st[1]:
-                done = "reuse"
-            elif eng.room() >= n - st[1]:
-                for i in range(st[1], n):
-                    eng.append(Xt[i], ya[i])
-                done = "append"
+        if self.incremental and st is not None and st[0] == key and n >= 1:
+            Xh, yh = st[1], st[2]
+            m = min(n, len(yh))
+            diff = np.flatnonzero((Xt[:m] != Xh[:m]).any(axis=1))
+            p = int(diff[0]) if len(diff) else m          # rows [0, p) of the engine are rows [0, p) of the new history
+            if p >= 1 and n - p <= max_append and p + eng.room() + (len(yh) - p) >= n:
+                if p == n == len(yh) and np.array_equal(ya, yh):
+                    done = "reuse"
+                else:
+                    eng.rebase(p, ya[:p])
+                    for i in range(p, n):
+                        eng.append(Xt[i], ya[i])
+                    done = "append" if n > p else "rebase"
         if done is None:
             eng.tell(Xt, ya)
             done = "fit"
         self.last_fit = done
-        self._fit_state = (key, n, self._digest(Xt, ya, n))
+        self._fit_state = (key, np.array(Xt, dtype=np.float64, copy=True), np.array(ya, dtype=np.float64, copy=True))
 
     def _sweep(self, eng, cand):
         try:

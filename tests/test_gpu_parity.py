@@ -489,32 +489,66 @@ def test_fit_append_room_and_errors():
     eng.close()
 
 
+def test_fit_rebase_drops_rows_and_replaces_targets():
+    """kbo_fit_rebase keeps the leading rows of the factorisation (no refit) and takes new targets: state and suggestion must
+    equal a fresh fit of the shorter history with those targets; rows can then be appended again."""
+    D = 5
+    X, y, Xc = O.synthetic(150, 3000, D)
+    th = O.theta_of_record(D)
+    kw = dict(kind="matern52", acq="ei", **th)
+    eng = _engine(kw, "f64"); eng.tell(X[:140], y[:140])
+    y2 = y.copy(); y2[100:] = y2[100:] * 0.5 - 0.2
+    eng.rebase(130, y2[:130])
+    assert eng.N == 130 and eng.room() == 192 - 130
+    for i in range(130, 150):
+        eng.append(X[i], y2[i])
+    ref = _engine(kw, "f64"); ref.tell(X, y2)
+    for a_, b_ in zip(eng.state(), ref.state()):
+        np.testing.assert_allclose(a_.cpu().numpy(), b_.cpu().numpy(), rtol=0, atol=2e-10)
+    be, _, _, ae = eng.ask(Xc, return_arrays=True)
+    br, _, _, ar = ref.ask(Xc, return_arrays=True)
+    np.testing.assert_allclose(ae.cpu().numpy(), ar.cpu().numpy(), rtol=0, atol=1e-9)
+    assert be.index == br.index
+    _check_argmax(be, O.suggest(X, y2, Xc, kind="matern52", acq="ei", **th)["acq"], TOL_F64)
+    from kubeflow_b200 import _lib as Lb
+    with pytest.raises(Lb.KboInvalidArgument):
+        eng.rebase(0)
+    with pytest.raises(Lb.KboInvalidArgument):
+        eng.rebase(151)
+    eng.close(); ref.close()
+
+
 def test_optimizer_constant_liar_appends_instead_of_refitting():
     """ask(n_points=3) tells two constant lies: with `incremental` they are appended (kbo_fit_append), without it refitted as
-    skopt does — the three suggested points must be the same; and a later request that resends the history plus one finished
-    trial appends as well, while an edited history falls back to a refit."""
+    skopt does — the three suggested points must be the same.  The next request (history + one finished trial) drops the
+    lies, keeps the common prefix and appends; a lie that became an observation at the same x only swaps the target; an
+    edited early row falls back to a refit."""
     from kubeflow_b200.optimizer import Optimizer
     from kubeflow_b200.space import Real
     dims = [Real(0.0, 1.0, name=f"x{i}") for i in range(4)]
     rng = np.random.default_rng(3)
     X0 = rng.random((40, 4)).tolist()
     y0 = [float(np.sin(3 * sum(r))) for r in X0]
-    outs, fits = [], []
+    outs, fits, later = [], [], []
     for inc in (True, False):
         opt = Optimizer(dims, n_initial_points=5, random_state=11, n_points=20000, incremental=inc)
         opt.tell(X0, y0)
         pts = opt.ask(n_points=3)
         outs.append(np.asarray(pts))
         fits.append(opt.last_fit)
+        opt.tell([pts[0]], [0.123])          # engine: history + lie(pts0) + lie(pts1); new history: history + pts0 observed
+        a1 = opt.ask(); f1 = opt.last_fit
+        opt.tell([pts[2]], [0.456])          # a new row after the common prefix
+        a2 = opt.ask(); f2 = opt.last_fit
+        opt.ask(); f3 = opt.last_fit
+        later.append(np.asarray([a1, a2]))
         if inc:
-            opt.tell([pts[0]], [0.123])
+            assert (f1, f2, f3) == ("rebase", "append", "reuse")
+            opt.Xi[3] = [0.5] * 4; opt._Xt[3] = opt.space.transform([opt.Xi[3]])[0]
             opt.ask()
-            # engine held history+2 lies; the real history is now history+1 real trial: rows differ -> refit, not a silent append
             assert opt.last_fit == "fit"
-            opt.tell([pts[1]], [0.456])
-            opt.ask()
-            assert opt.last_fit == "append"
-            opt.ask()
-            assert opt.last_fit == "reuse"
+        else:
+            assert (f1, f2, f3) == ("fit", "fit", "fit")
     assert fits == ["append", "fit"]
     np.testing.assert_allclose(outs[0], outs[1], rtol=0, atol=0)
+    np.testing.assert_allclose(later[0], later[1], rtol=0, atol=0)
