@@ -306,7 +306,8 @@ def main():
             from kubeflow_b200.suggestion import api_pb as api
             from kubeflow_b200.suggestion.server import SuggestionStub, serve
             from kubeflow_b200.suggestion.service import SkoptService
-            server, port = serve(SkoptService({"device": local}), port=0, host="127.0.0.1")
+            skopt_svc = SkoptService({"device": local})
+            server, port = serve(skopt_svc, port=0, host="127.0.0.1")
             ch = grpc.insecure_channel(f"127.0.0.1:{port}", options=[("grpc.max_send_message_length", 1 << 28), ("grpc.max_receive_message_length", 1 << 28)])
             stub = SuggestionStub(ch)
             ex = api.Experiment()
@@ -344,6 +345,7 @@ def main():
                 add_trial(N - 3 + c_, X[min(N - 3 + c_, N - 1)], y[min(N - 3 + c_, N - 1)])
             other["grpc_cfg3_request"] = {"trials_in_request": N, "request_bytes": rq.ByteSize(), "n_points": M, "cold_call_ms": calls[0],
                                           "steady_call_ms": float(np.median(calls[1:])),
+                                          "engine_update_last_call": getattr(skopt_svc._services["bench-cfg3"].skopt_optimizer, "last_fit", None),
                                           "note": "in-process grpc.server, all finished trials resent as strings on every call; steady = one new trial per call"}
             ch.close()
             server.stop(0)

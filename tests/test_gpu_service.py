@@ -18,7 +18,8 @@ def _f(vals):   # a smooth objective with its minimum inside the box
 
 @pytest.mark.parametrize("objective", [api.MINIMIZE, api.MAXIMIZE])
 def test_bayesianoptimization_over_grpc(objective):
-    server, port = serve(DispatchService([SkoptService(), RandomService()]), port=0, host="127.0.0.1")
+    sk = SkoptService()
+    server, port = serve(DispatchService([sk, RandomService()]), port=0, host="127.0.0.1")
     ch = grpc.insecure_channel(f"127.0.0.1:{port}")
     stub = SuggestionStub(ch)
     settings = {"base_estimator": "GP", "n_initial_points": 8, "acq_func": "EI", "acq_optimizer": "sampling", "random_state": 3,
@@ -40,6 +41,8 @@ def test_bayesianoptimization_over_grpc(objective):
     # the model-based phase must beat the random phase on this smooth bowl
     assert min(losses[8:]) < min(losses[:8])
     assert np.mean(sorted(losses[8:])[:4]) < np.mean(sorted(losses[:8])[:4])
+    # steady state: each request drops the previous lie, appends the two finished trials, then appends the new lie — no refit
+    assert sk._services[f"bo-{objective}"].skopt_optimizer.last_fit == "append"
     ch.close()
     server.stop(0)
 
