@@ -345,6 +345,7 @@ def main():
                 add_trial(N - 3 + c_, X[min(N - 3 + c_, N - 1)], y[min(N - 3 + c_, N - 1)])
             other["grpc_cfg3_request"] = {"trials_in_request": N, "request_bytes": rq.ByteSize(), "n_points": M, "cold_call_ms": calls[0],
                                           "steady_call_ms": float(np.median(calls[1:])),
+                                          "ingest_last_call": skopt_svc.last_ingest,
                                           "engine_update_last_call": getattr(skopt_svc._services["bench-cfg3"].skopt_optimizer, "last_fit", None),
                                           "note": "in-process grpc.server, all finished trials resent as strings on every call; steady = one new trial per call"}
             ch.close()

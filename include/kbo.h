@@ -177,6 +177,30 @@ int kbo_acq_argmax(kbo_handle* h, const float* mu_n, const float* var_n, int64_t
                    int32_t acq, double y_mean, double y_std, double y_opt, double xi, double kappa,
                    float* acq_out, kbo_best* best_dev, void* stream);
 
+/* ---- request ingestion (host only) -------------------------------------------------------------------
+ * A serialized api.v1.beta1.GetSuggestionsRequest (kubeflow/katib pkg/apis/manager/v1beta1/api.proto; what grpc hands the
+ * suggestion service before `GetSuggestionsRequest.FromString`) scanned into flat arrays, replacing the walk over the parsed
+ * message that katib's pkg/suggestion/v1beta1/internal/trial.py `Trial.convert` + skopt/base_service.py `getSuggestions`
+ * do per request.  `bytes` must stay alive while the kbo_req is open; offsets are relative to it.
+ * kbo_req_trials fills one row per trial (any output pointer may be NULL), n_params columns in the order of param_names:
+ *   usable          condition SUCCEEDED/EARLYSTOPPED and the objective metric present (Trial.convert's filter)
+ *   objective       strtod of the objective metric value; objective_flags bit0 = plain decimal literal (else NaN)
+ *   values / flags  strtod of the assignment; bit0 = plain decimal literal, bit1 = integer literal (<= 15 digits);
+ *                   value_len 0xFFFFFFFF = the trial has no assignment of that name
+ * Values that are not plain literals are left to the caller (Python float()/int() semantics, categorical strings).
+ * select (NULL = all): per-trial mask; assignments of unselected trials are not looked at (their rows read as missing) —
+ * a steady request parses numbers only for the trials the service has not seen (strtod dominates the scan). */
+typedef struct kbo_req kbo_req;
+int kbo_req_open(const void* bytes, uint64_t len, kbo_req** out);
+void kbo_req_close(kbo_req* r);
+int kbo_req_header(const kbo_req* r, uint64_t* experiment_off, uint64_t* experiment_len, int32_t* current_request_number,
+                   int32_t* total_request_number, int32_t* n_trials);
+int kbo_req_trials(const kbo_req* r, int32_t n_params, const char* const* param_names, uint64_t* name_off, uint32_t* name_len,
+                   uint64_t* name_hash, int32_t* condition, uint8_t* usable, double* objective, uint8_t* objective_flags,
+                   uint64_t* objective_off, uint32_t* objective_len, double* values, uint8_t* value_flags, uint64_t* value_off,
+                   uint32_t* value_len, const uint8_t* select);
+uint64_t kbo_hash64(const void* bytes, uint64_t len);   /* the FNV-1a hash kbo_req_trials puts in name_hash */
+
 /* ---- CMA-ES (Katib algorithm `cmaes`, goptuna; N. Hansen's tutorial arXiv:1604.00772, active weights) ---------------
  * State (mean, sigma, C, evolution paths, eigenbasis) lives on the device.  One generation = ask + tell:
  *   kbo_cma_ask : X (lambda×D, device, fp64) = m + sigma·B·(d∘z); z from the built-in Philox stream (seed, generation) or,

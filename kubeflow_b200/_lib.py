@@ -52,6 +52,7 @@ class KboNotPositiveDefinite(KboError):
 EXPORTS = ["kbo_version", "kbo_create", "kbo_destroy", "kbo_last_error", "kbo_set_scratch_limit", "kbo_set_tc_pair", "kbo_set_tc_refine", "kbo_last_contenders", "kbo_fit", "kbo_fit_append", "kbo_fit_room", "kbo_fit_rebase",
            "kbo_fit_info", "kbo_lml_grad", "kbo_fit_state", "kbo_sweep", "kbo_best_to_host", "kbo_suggest_host", "kbo_last_timings",
            "kbo_gram", "kbo_potrf", "kbo_trtri", "kbo_acq_argmax",
+           "kbo_req_open", "kbo_req_close", "kbo_req_header", "kbo_req_trials", "kbo_hash64",
            "kbo_cma_create", "kbo_cma_destroy", "kbo_cma_ask", "kbo_cma_tell", "kbo_cma_state", "kbo_cma_run_synthetic"]
 
 _lib = None
@@ -85,6 +86,13 @@ def load() -> C.CDLL:
     lib.kbo_set_tc_refine.argtypes = [vp, C.c_int]
     lib.kbo_fit_append.argtypes = [vp, vp, C.c_double, C.c_int, vp]
     lib.kbo_fit_room.argtypes = [vp]
+    lib.kbo_req_open.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    lib.kbo_req_close.argtypes = [vp]
+    lib.kbo_req_close.restype = None
+    lib.kbo_req_header.argtypes = [vp] + [vp] * 5
+    lib.kbo_req_trials.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p)] + [vp] * 14
+    lib.kbo_hash64.argtypes = [vp, C.c_uint64]
+    lib.kbo_hash64.restype = C.c_uint64
     lib.kbo_fit_rebase.argtypes = [vp, C.c_int32, vp, C.c_int, vp]
     lib.kbo_last_contenders.argtypes = [vp]
     lib.kbo_fit.argtypes = [vp, vp, vp, i32, i32, C.POINTER(KboParams), C.c_int, vp]

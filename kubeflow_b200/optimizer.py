@@ -52,7 +52,7 @@ class Optimizer:
         self._tgen = None
         self._seed = random_state
         self.Xi, self.yi = [], []
-        self._Xt = []                 # transformed rows, appended on tell (the history is resent on every request)
+        self._Xt = np.empty((0, self.space.transformed_n_dims))   # transformed rows, one per told point
         self._engine = engine
         self.incremental = bool(incremental)   # False: refit on every ask, as skopt does
         self._fit_state = None        # (θ key, rows in the engine, digest of those rows): lets a request that only adds trials append
@@ -60,16 +60,20 @@ class Optimizer:
         self.last_best = None
 
     # ------------------------------------------------------------------------------------------------------
-    def tell(self, x, y):
+    def tell(self, x, y, xt=None):
+        """``xt``: the rows already in the transformed space (the request scan computes them column-wise); must equal
+        ``space.transform(x)``."""
         if len(x) and not isinstance(x[0], (list, tuple)):
             x, y = [x], [y]
+            xt = None if xt is None else np.atleast_2d(xt)
         if len(x) != len(y):
             raise ValueError("x and y must have the same length")
         rows = [list(p) for p in x]
         self.Xi.extend(rows)
         self.yi.extend([float(v) for v in y])
         if rows:
-            self._Xt.extend(self.space.transform(rows))
+            new = self.space.transform(rows) if xt is None else np.asarray(xt, dtype=np.float64).reshape(len(rows), -1)
+            self._Xt = np.concatenate([self._Xt, new])
 
     def _get_engine(self, ls):
         from .gp import GPEngine
@@ -126,7 +130,7 @@ class Optimizer:
         if len(y) < max(self.n_initial_points, 1):
             return self.space.inverse_transform(self.space.rvs_transformed(1, self.rng, np.float64))[0]
         n_told = len(self._Xt)
-        Xt = np.asarray(self._Xt, dtype=np.float64).reshape(n_told, self.space.transformed_n_dims)
+        Xt = self._Xt
         if len(X) > n_told:          # constant-liar rows appended by ask(n_points=k)
             Xt = np.concatenate([Xt, self.space.transform(X[n_told:])])
         ya = np.asarray(y, dtype=np.float64)

@@ -21,6 +21,7 @@ class BaseSkoptService:
         self.engine_settings = engine_settings
         self.skopt_optimizer = None
         self.told_trials = set()
+        self._told_hashes = set()     # kbo_hash64 of the told names: the request scan compares hashes, not strings
         self.create_optimizer()
 
     def create_optimizer(self):
@@ -59,6 +60,58 @@ class BaseSkoptService:
             self.skopt_optimizer.tell(skopt_suggested, loss_for_skopt)
         points = self.skopt_optimizer.ask(n_points=current_request_number)
         return [self.convert(self.search_space, p) for p in points]
+
+    def ingest(self, request) -> bool:
+        """Fast equivalent of the loop above for a ``LazyRequest``: tells the optimizer every usable trial it has not seen,
+        straight from the request scan's arrays.  Returns False — having told nothing — whenever a new trial needs the
+        reference's own conversion or error path (a value that is not a plain decimal literal, a missing assignment, an
+        objective that is not a number): the caller then walks the parsed messages as before."""
+        import numpy as np
+        from .ingest import MISSING, hash64
+        params = self.search_space.params
+        if len(self._told_hashes) != len(self.told_trials):       # names told through the message path: hash them once
+            self._told_hashes = {hash64(n) for n in self.told_trials}
+        head = request.trial_table([])                            # names, conditions, objective: no numbers parsed yet
+        told = np.fromiter(self._told_hashes, dtype=np.uint64, count=len(self._told_hashes))
+        idx = np.flatnonzero(head.usable & ~np.isin(head.name_hash, told))
+        if idx.size:
+            _, first = np.unique(head.name_hash[idx], return_index=True)  # a name sent twice in one request is told once
+            idx = idx[np.sort(first)]
+        if idx.size == 0:
+            return True
+        mask = np.zeros(head.n, dtype=bool)
+        mask[idx] = True
+        tab = request.trial_table([p.name for p in params], select=mask)   # assignments of the new trials only
+        flags, lens = tab.value_flags[idx], tab.value_len[idx]
+        if not (tab.objective_flags[idx] & 1).all() or (lens == MISSING).any():
+            return False
+        num_cols = [j for j, p in enumerate(params) if p.type in (INTEGER, DOUBLE)]
+        for j in num_cols:
+            if not (flags[:, j] & (2 if params[j].type == INTEGER else 1)).all():
+                return False
+        names = [request.text(tab.name_off[i], tab.name_len[i]) for i in idx]
+        vals = tab.values[idx]
+        cols, xt_cols = [], []
+        for j, (p, dim) in enumerate(zip(params, self.skopt_optimizer.space.dimensions)):
+            if p.type == INTEGER:
+                iv = vals[:, j].astype(np.int64)
+                cols.append(iv.tolist())
+                xt_cols.append(((iv - int(dim.low)).astype(np.float64) / float(dim.high - dim.low))[:, None])
+            elif p.type == DOUBLE:
+                cols.append(vals[:, j].tolist())
+                xt_cols.append(((vals[:, j] - dim.low) / (dim.high - dim.low))[:, None])
+            else:
+                sv = [request.text(tab.value_off[i, j], tab.value_len[i, j]) for i in idx]
+                cols.append(sv)
+                xt_cols.append(np.asarray([dim.to_unit(v) for v in sv], dtype=np.float64).reshape(len(sv), dim.width))
+        rows = [list(r) for r in zip(*cols)]
+        loss = tab.objective[idx]
+        if self.search_space.goal == MAX_GOAL:
+            loss = -1.0 * loss
+        self.skopt_optimizer.tell(rows, loss.tolist(), xt=np.concatenate(xt_cols, axis=1))
+        self.told_trials.update(names)
+        self._told_hashes.update(int(h) for h in tab.name_hash[idx])
+        return True
 
     @staticmethod
     def convert(search_space, skopt_suggested):

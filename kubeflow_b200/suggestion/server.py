@@ -14,6 +14,7 @@ from concurrent import futures
 import grpc
 
 from . import api_pb as api
+from .ingest import LazyRequest
 
 DEFAULT_PORT = 6789
 SERVICE_NAMES = (f"{api.PACKAGE}.Suggestion", f"{api.PACKAGE}.SuggestionService")
@@ -23,7 +24,7 @@ _HEALTH_SERVING = b"\x08\x01"   # HealthCheckResponse{status: SERVING}  (field 1
 def add_suggestion_servicer(servicer, server: grpc.Server):
     handlers = {
         "GetSuggestions": grpc.unary_unary_rpc_method_handler(
-            servicer.GetSuggestions, request_deserializer=api.GetSuggestionsRequest.FromString,
+            servicer.GetSuggestions, request_deserializer=LazyRequest.FromString,   # wire bytes kept: see ingest.py
             response_serializer=lambda m: m.SerializeToString()),
         "ValidateAlgorithmSettings": grpc.unary_unary_rpc_method_handler(
             servicer.ValidateAlgorithmSettings, request_deserializer=api.ValidateAlgorithmSettingsRequest.FromString,

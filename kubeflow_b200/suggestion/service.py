@@ -128,6 +128,7 @@ class SkoptService(_Base):
         self._lock = threading.Lock()       # handlers may run concurrently (grpc thread pool): GPU work is serialised here
         self._services = {}                 # experiment name -> BaseSkoptService, least-recently-used first
         self.engine_defaults = dict(engine_defaults or {})
+        self.last_ingest = None             # "scan" | "messages": how the last request's trials reached the optimizer
         self.max_experiments = int(max_experiments)   # each experiment owns a libkbo handle (K, W, scratch): bound the device memory
 
     def validate(self, experiment):
@@ -143,9 +144,10 @@ class SkoptService(_Base):
             raise AlgorithmSettingsError(f"unknown algorithm name {exp.spec.algorithm.algorithm_name}")
         search_space = HyperParameterSearchSpace.convert(exp)
         settings = validate_skopt_settings(parse_settings(exp))
+        from .ingest import LazyRequest
+        lazy = request if isinstance(request, LazyRequest) and request.scanned else None
         with self._lock:
             svc = self._services.get(exp.name)
-            trials = Trial.convert(request.trials, skip_names=svc.told_trials if svc is not None else None)
             if svc is None:
                 kw = dict(self.engine_defaults)
                 kw.update(settings)
@@ -160,6 +162,9 @@ class SkoptService(_Base):
                         eng.close()
             else:
                 self._services[exp.name] = self._services.pop(exp.name)  # mark as most recently used
+            # the wire scan tells the new trials from flat arrays; it declines (False) whenever a trial needs the message walk
+            self.last_ingest = "scan" if (lazy is not None and svc.ingest(lazy)) else "messages"
+            trials = [] if self.last_ingest == "scan" else Trial.convert(request.trials, skip_names=svc.told_trials)
             lists = svc.getSuggestions(trials, max(int(request.current_request_number), 0))
         return _reply_from(lists)
 

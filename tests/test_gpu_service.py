@@ -43,6 +43,7 @@ def test_bayesianoptimization_over_grpc(objective):
     assert np.mean(sorted(losses[8:])[:4]) < np.mean(sorted(losses[:8])[:4])
     # steady state: each request drops the previous lie, appends the two finished trials, then appends the new lie — no refit
     assert sk._services[f"bo-{objective}"].skopt_optimizer.last_fit == "append"
+    assert sk.last_ingest == "scan"                     # over gRPC the trials come through the wire scan, not the message walk
     ch.close()
     server.stop(0)
 
