@@ -7,14 +7,21 @@ from kubeflow_b200.gp import GPEngine
 from kubeflow_b200.cmaes import CmaEs
 from oracle import gp_oracle as O
 
-for N, M, D, mode in ((70, 300, 3, "f64"), (130, 515, 5, "tc"), (300, 700, 33, "tc")):
+for N, M, D, mode in ((70, 300, 3, "f64"), (135, 515, 5, "tc"), (300, 700, 33, "tc")):
     X, y, Xc = O.synthetic(N, M, D)
     th = O.theta_of_record(D)
     e = GPEngine(0, kernel="matern52", acq="ei", var_mode=mode, **th)
     e.tell(X, y)
     b = e.ask(Xc.astype(np.float32))
     b2, t = e.suggest_host(X, y, Xc)
-    print(N, M, D, mode, b.index, b2.index)
+    e.tell(X[:N - 3], y[:N - 3])                 # bordered-Cholesky appends, a rebase, the FP64 refinement of the tc pick, LML gradient
+    for i in range(N - 3, N):
+        e.append(X[i], y[i])
+    b3 = e.ask(Xc)
+    e.rebase(N - 5, y[:N - 5] * 0.5)
+    b4 = e.ask(Xc)
+    g = e.lml_grad()[1]
+    print(N, M, D, mode, b.index, b2.index, b3.index, b4.index, e.last_contenders(), float(g[0]))
     e.close()
 es = CmaEs(np.zeros(9), 1.0, popsize=20, seed=1)
 print(es.run_synthetic("sphere", 3))
