@@ -7,6 +7,9 @@ small ``experiment`` sub-message with protobuf, and lets the skopt service pull 
 (trial, parameter).  Everything else (``request.trials`` for the services that walk the messages, error paths) falls back to
 a full protobuf parse on first touch, so behaviour is the reference's; the scan only decides how fast the common case is.
 
+Trials are recognised by the 64-bit FNV-1a hash of their name: two different names colliding (probability ~n²/2⁶⁵) would make
+the later one look already told.
+
 Mirrors kubeflow/katib pkg/suggestion/v1beta1/internal/trial.py ``Trial.convert`` (filter: succeeded trials carrying the
 objective metric) and skopt/base_service.py ``getSuggestions`` (assignment lookup by parameter name, ``float``/``int``).
 """
