@@ -26,7 +26,7 @@ class Optimizer:
     def __init__(self, dimensions, base_estimator="GP", n_initial_points=10, acq_func="EI", acq_optimizer="sampling",
                  random_state=None, *, n_points=65536, kernel="matern52", length_scale=None, amplitude=1.0, noise=1e-3, xi=0.01,
                  kappa=1.96, var_mode="auto", theta_grid=1, theta_search=0, theta_fit=None, theta_fit_maxiter=25, ard=False, device=0, engine=None,
-                 candidate_backend="torch", incremental=True):
+                 candidate_backend="torch", incremental=True, shard=False):
         if str(base_estimator).upper() != "GP":
             raise ValueError("base_estimator must be GP (RF/ET/GBRT are not part of the GPU path)")
         self.space = dimensions if isinstance(dimensions, Space) else Space(dimensions)
@@ -50,11 +50,24 @@ class Optimizer:
             raise ValueError("candidate_backend must be 'torch' (sampled on the device) or 'numpy'")
         self.candidate_backend = candidate_backend
         self._tgen = None
+        self._crng = None
+        self.last_local_best = None
         self._seed = random_state
         self.Xi, self.yi = [], []
         self._Xt = np.empty((0, self.space.transformed_n_dims))   # transformed rows, one per told point
         self._engine = engine
         self.incremental = bool(incremental)   # False: refit on every ask, as skopt does
+        # Sharded sweep: every rank of the default process group holds the same optimizer (same tells, same
+        # seed) and sweeps its own n_points/world candidates; one all-gather picks the winner, its owner broadcasts the row.
+        # Opt-in (the SPMD server sets it): every rank must then make the same calls in the same order.
+        self.shard = bool(shard) and self._world()[1] > 1
+        if self.shard and random_state is None:
+            import torch.distributed as dist
+            box = [int(np.random.default_rng().integers(0, 2 ** 31))]
+            dist.broadcast_object_list(box, src=0)          # ranks must draw the same initial points
+            random_state = box[0]
+            self._seed = random_state
+            self.rng = np.random.default_rng(random_state)
         self._fit_state = None        # (θ key, rows in the engine, digest of those rows): lets a request that only adds trials append
         self.last_fit = None          # "fit" | "append" | "reuse": what the last ask did to the engine (diagnostics, tests)
         self.last_best = None
@@ -116,9 +129,19 @@ class Optimizer:
         self.last_fit = done
         self._fit_state = (key, np.array(Xt, dtype=np.float64, copy=True), np.array(ya, dtype=np.float64, copy=True))
 
-    def _sweep(self, eng, cand):
+    @staticmethod
+    def _world():
         try:
-            return eng.ask(cand)
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_rank(), dist.get_world_size()
+        except Exception:
+            pass
+        return 0, 1
+
+    def _sweep(self, eng, cand, global_offset=0):
+        try:
+            return eng.ask(cand, global_offset=global_offset)
         except Exception:
             self._fit_state = None      # e.g. an appended row made K singular: the next ask must refit from the history
             raise
@@ -177,19 +200,42 @@ class Optimizer:
             eng.length_scale, eng.noise = np.exp(res.x[:-1]), float(np.exp(res.x[-1]))
             self.last_theta = dict(length_scale=eng.length_scale.copy(), noise=eng.noise, lml=-float(res.fun), nfev=int(res.nfev))
         self._tell_engine(eng, Xt, ya)
+        rank, world = self._world() if self.shard else (0, 1)
+        from .dist import global_argmax, shard_rows
+        lo, hi = shard_rows(self.n_points, rank, world)
         if self.candidate_backend == "torch":
             import torch
             dev = torch.device("cuda", self.device)
             if self._tgen is None:
                 self._tgen = torch.Generator(device=dev)
-                self._tgen.manual_seed(int(self._seed) if self._seed is not None else int(self.rng.integers(0, 2 ** 31)))
-            cand = self.space.rvs_transformed_torch(self.n_points, self._tgen, dev)
-            best = self._sweep(eng, cand)
-            row = cand[best.index:best.index + 1].to(torch.float64).cpu().numpy()
+                base = int(self._seed) if self._seed is not None else int(self.rng.integers(0, 2 ** 31))
+                self._tgen.manual_seed(base + 1000003 * rank)
+            cand = self.space.rvs_transformed_torch(hi - lo, self._tgen, dev)
         else:
-            cand = self.space.rvs_transformed(self.n_points, self.rng, np.float32)
-            best = self._sweep(eng, cand)
-            row = cand[best.index:best.index + 1].astype(np.float64)
+            if self._crng is None:
+                self._crng = self.rng if world == 1 else np.random.default_rng([int(self._seed), rank])
+            cand = self.space.rvs_transformed(hi - lo, self._crng, np.float32)
+        best = self._sweep(eng, cand, lo)
+        self.last_local_best = best
+        li = best.index - lo
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            cdev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            best = global_argmax(best, device=cdev)
+            owner = next(r for r in range(world) if shard_rows(self.n_points, r, world)[0] <= best.index < shard_rows(self.n_points, r, world)[1])
+            rowt = torch.zeros(self.space.transformed_n_dims, dtype=torch.float64, device=cdev)
+            if rank == owner:
+                li = best.index - lo
+                src = cand[li] if isinstance(cand, torch.Tensor) else torch.from_numpy(np.asarray(cand[li]))
+                rowt.copy_(src.to(torch.float64))
+            dist.broadcast(rowt, src=owner)
+            row = rowt.cpu().numpy()[None, :]
+        elif self.candidate_backend == "torch":
+            import torch
+            row = cand[li:li + 1].to(torch.float64).cpu().numpy()
+        else:
+            row = cand[li:li + 1].astype(np.float64)
         self.last_best = best
         return self.space.inverse_transform(row)[0]
 

@@ -68,8 +68,33 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--port", type=int, default=DEFAULT_PORT)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--spmd", action="store_true",
+                    help="one process per GPU under torchrun: rank 0 serves gRPC, every request runs on all ranks with the candidate "
+                         "grid sharded (suggestion/spmd.py)")
     args = ap.parse_args()
     logging.basicConfig(level=logging.INFO)
+    if args.spmd:
+        import os
+        import torch
+        import torch.distributed as dist
+        from .spmd import SpmdServicer
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        inner = DispatchService([SkoptService({"device": local, "shard": True}), RandomService(), SobolService(),
+                                 CmaesService(), HyperbandService()])
+        spmd = SpmdServicer(inner)
+        if dist.get_rank() == 0:
+            server, port = serve(spmd, args.port)
+            logging.info("api.v1.beta1.Suggestion listening on :%d, %d ranks", port, dist.get_world_size())
+            try:
+                server.wait_for_termination()
+            finally:
+                spmd.stop()
+        else:
+            spmd.worker_loop()
+        dist.destroy_process_group()
+        return
     server, port = serve(DispatchService([SkoptService({"device": args.device}), RandomService(), SobolService(), CmaesService(), HyperbandService()]), args.port)
     logging.info("api.v1.beta1.Suggestion listening on :%d", port)
     server.wait_for_termination()
