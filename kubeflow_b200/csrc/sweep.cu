@@ -555,10 +555,42 @@ refine_best_kernel(const double* __restrict__ mun, const double* __restrict__ va
   }
 }
 
-// Σ_i (W k*)_i² for a handful of contender rows: CTA (bx, by) takes W rows [64·bx, 64·bx+64) and contenders [8·by, 8·by+8);
-// a warp owns one W row at a time, lanes stride the columns, butterfly reduction — the summation order depends on neither
+// K* row of a contender in FP64, one thread per (contender, trial): scaled differences summed in d order, exact kernel
+__global__ void __launch_bounds__(256)
+refine_cross_kernel(const double* __restrict__ Xg, int D, const double* __restrict__ inv_ls, int n_ls, const double* __restrict__ XsT, int ld,
+                    int N, int kind, double amp, double* __restrict__ Ks) {
+  __shared__ double xs[512];
+  const int c = blockIdx.y;
+  for (int d = threadIdx.x; d < D; d += 256) xs[d] = Xg[(size_t)c * D + d] * inv_ls[n_ls == 1 ? 0 : d];
+  __syncthreads();
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= N) return;
+  double d2 = 0.0;
+  for (int d = 0; d < D; d++) {
+    const double df = xs[d] - XsT[(size_t)d * ld + j];
+    d2 = fma(df, df, d2);
+  }
+  Ks[(size_t)c * ld + j] = amp * kbo_kernel_exact(d2, kind);
+}
+// normalised mean K*·alpha of one contender per CTA, fixed-order reduction
+__global__ void __launch_bounds__(256)
+refine_mu_kernel(const double* __restrict__ Ks, int ld, int N, const double* __restrict__ alpha, double* __restrict__ mun) {
+  __shared__ double red[256];
+  const double* k = Ks + (size_t)blockIdx.x * ld;
+  double a = 0.0;
+  for (int j = threadIdx.x; j < N; j += 256) a = fma(k[j], alpha[j], a);
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mun[blockIdx.x] = red[0];
+}
+// Σ_i (W k*)_i² for a handful of contender rows: CTA (bx, by) takes W rows [8·bx, 8·bx+8) and contenders [C·by, C·by+C);
+// a warp owns one W row, lanes stride the columns, butterfly reduction — the summation order depends on neither
 // the contender's position nor their number, so a candidate's refined value is bit-reproducible however the grid is sharded.
-#define KBO_RV_C 8
+template <int KBO_RV_C>
 __global__ void __launch_bounds__(256)
 refine_var_kernel(const double* __restrict__ W, int ld, int N, const double* __restrict__ Ks, int n, double* __restrict__ part, int nblk) {
   __shared__ double ssq[8][KBO_RV_C];
@@ -570,14 +602,13 @@ refine_var_kernel(const double* __restrict__ W, int ld, int N, const double* __r
   double sq[KBO_RV_C];
 #pragma unroll
   for (int c = 0; c < KBO_RV_C; c++) sq[c] = 0.0;
-  for (int r = 0; r < 8; r++) {
-    const int i = blockIdx.x * 64 + warp * 8 + r;
-    if (i >= N) break;
+  const int i = blockIdx.x * 8 + warp;   // one W row per warp: N/8 CTAs keep enough loads in flight to stream the triangle
+  if (i < N) {
     const double* w = W + (size_t)i * ld;
     double acc[KBO_RV_C];
 #pragma unroll
     for (int c = 0; c < KBO_RV_C; c++) acc[c] = 0.0;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = lane; j <= i; j += 32) {
       const double wv = w[j];
 #pragma unroll
@@ -588,7 +619,7 @@ refine_var_kernel(const double* __restrict__ W, int ld, int N, const double* __r
       double v = acc[c];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      sq[c] = fma(v, v, sq[c]);
+      sq[c] = v * v;
     }
   }
   if (lane == 0)
@@ -700,7 +731,7 @@ static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_
   if (n < 1 || n > KBO_REFINE_CAP) return KBO_OK;   // more near-ties than the cap: keep the tensor-core pick (n is reported)
   sort_contenders_kernel<<<1, 1024, 0, s>>>(list, count);
   KBO_LAUNCH_CHECK(h);
-  const int njt = (N + 63) / 64;
+  const int njt = (N + 7) / 8;   // row blocks of refine_var_kernel (8 rows of W per CTA)
   KBO_TRY(kbo_reserve(h, h->refine_x, sizeof(double) * (size_t)n * D));
   KBO_TRY(kbo_reserve(h, h->Ks64, sizeof(double) * (size_t)n * ld));
   KBO_TRY(kbo_reserve(h, h->part, sizeof(double) * ((size_t)n * njt + 2 * (size_t)n)));
@@ -712,8 +743,15 @@ static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_
   else
     gather_rows_kernel<float><<<n, 64, 0, s>>>((const float*)Xc, D, list, n, Xg);
   KBO_LAUNCH_CHECK(h);
-  KBO_TRY((launch_cross<double, double, 0>(h, Xg, n, n, (double*)h->Ks64.p, ld, nullptr, nullptr, mun64, s)));
-  refine_var_kernel<<<dim3(njt, (n + KBO_RV_C - 1) / KBO_RV_C), 256, 0, s>>>((const double*)h->W.p, ld, N, (const double*)h->Ks64.p, n, (double*)h->part.p, njt);
+  refine_cross_kernel<<<dim3((N + 255) / 256, n), 256, 0, s>>>(Xg, D, (const double*)h->d_inv_ls.p, (int)h->inv_ls.size(), (const double*)h->XsT.p, ld, N,
+                                                               h->prm.kernel, h->prm.amplitude, (double*)h->Ks64.p);
+  KBO_LAUNCH_CHECK(h);
+  refine_mu_kernel<<<n, 256, 0, s>>>((const double*)h->Ks64.p, ld, N, (const double*)h->alpha.p, mun64);
+  KBO_LAUNCH_CHECK(h);
+  if (n <= 2)   // the usual case: one contender — no point carrying eight accumulators through the triangle of W
+    refine_var_kernel<1><<<dim3(njt, n), 256, 0, s>>>((const double*)h->W.p, ld, N, (const double*)h->Ks64.p, n, (double*)h->part.p, njt);
+  else
+    refine_var_kernel<8><<<dim3(njt, (n + 7) / 8), 256, 0, s>>>((const double*)h->W.p, ld, N, (const double*)h->Ks64.p, n, (double*)h->part.p, njt);
   KBO_LAUNCH_CHECK(h);
   var_from_parts_kernel<<<(n + 255) / 256, 256, 0, s>>>((const double*)h->part.p, n, njt, h->prm.amplitude, varn64);
   KBO_LAUNCH_CHECK(h);
