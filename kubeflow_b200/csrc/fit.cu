@@ -350,6 +350,7 @@ __global__ void trmv_lower_kernel(const double* __restrict__ W, int N, int ldw, 
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= N) return;
   double s = 0.0;
+#pragma unroll 8   // eight loads in flight per lane; the accumulation order is unchanged
   for (int k = lane; k <= row; k += 32) s = fma(W[(size_t)row * ldw + k], x[k], s);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

@@ -729,8 +729,10 @@ static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_
   KBO_CUDA(h, cudaStreamSynchronize(s));
   h->last_contenders = n;
   if (n < 1 || n > KBO_REFINE_CAP) return KBO_OK;   // more near-ties than the cap: keep the tensor-core pick (n is reported)
-  sort_contenders_kernel<<<1, 1024, 0, s>>>(list, count);
-  KBO_LAUNCH_CHECK(h);
+  if (n > 1) {   // a single contender needs no ordering
+    sort_contenders_kernel<<<1, 1024, 0, s>>>(list, count);
+    KBO_LAUNCH_CHECK(h);
+  }
   const int njt = (N + 7) / 8;   // row blocks of refine_var_kernel (8 rows of W per CTA)
   KBO_TRY(kbo_reserve(h, h->refine_x, sizeof(double) * (size_t)n * D));
   KBO_TRY(kbo_reserve(h, h->Ks64, sizeof(double) * (size_t)n * ld));
