@@ -359,24 +359,31 @@ def main():
         var_launch_ms = float(np.mean(var_ms)) / max(chunks, 1)
         flops_launch = rows_per_launch * float(N) * float(N)           # Σ_j Σ_{k<=j} 2 flops = N² per candidate row
         achieved_tf = flops_launch / (var_launch_ms * 1e-3) / 1e12 if args.var_mode == "tc" else flops_launch / (var_launch_ms * 1e-3) / 1e12
+        rank_err = eng.last_rank_error() if args.var_mode == "tc" else 0.0
+        fast_rank = args.var_mode == "tc" and rank_err > 0.0
+        mma_products = 1.0 if fast_rank else 3.0
         line = {
             "metric": "suggestions/sec at (N=8192, M=1M, D=32)", "value": world * 1e3 / ms_step, "unit": "suggestions/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 fit+mean / fp16x3-split tcgen05 variance (fp32 accumulate)" if args.var_mode == "tc" else "f64",
+            "dtype": ("f64 fit+mean / fp16 tcgen05 ranking pass over sigma² (1 product, fp32 accumulate) + FP64 decision among the survivors"
+                      if fast_rank else "f64 fit+mean / fp16x3-split tcgen05 variance (fp32 accumulate)") if args.var_mode == "tc" else "f64",
             "data": "synthetic",
             "config": {"workload": f"cfg3: GP({KERNEL}) N={N} D={D}, {ACQ.upper()} sweep over M={M} candidates per GPU (grid {world * M}), fixed theta "
                                    f"(amp 1, ls 0.3*sqrt(D), noise 1e-3), one suggestion per step",
                        "kernel": KERNEL, "acq": ACQ, "per_gpu_candidates": M, "grid_candidates": world * M, "var_mode": args.var_mode,
                        "l2": "inputs larger than L2 (Xc 128 MiB, W planes 256 MiB, K* scratch ~2 GiB per chunk)", "argmax_index": best.index,
-                       "fp64_refined_contenders": eng.last_contenders() if args.var_mode == "tc" else None},
+                       "fp64_refined_contenders": eng.last_contenders() if args.var_mode == "tc" else None,
+                       "ranking_pass": ("1 fp16 product per term, error bound calibrated per sweep: max |d sigma²| on the calibration rows = %.3g" % rank_err) if fast_rank else None},
             "e2e": {"value": world * 1e3 / ms_step_e2e, "unit": "suggestions/s", "ms_per_step": ms_step_e2e,
                     "h2d_bytes_per_step": int(X.nbytes + y.nbytes + Xc.nbytes), "d2h_bytes_per_step": 32},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tc_variance_pair_kernel" if os.environ.get("KBO_TC_PAIR", "1") != "0" else "tc_variance_kernel", "achieved": achieved_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s",
                          "frac": achieved_tf / pk["tf_sus"], "peak_source": f"bf16_tflops_sustained, {pk['src']}",
-                         "issued_mma_tflops": 3.0 * achieved_tf * (1.0 + 256.0 / N), "traffic": tc_traffic(rows_per_launch),
+                         "issued_mma_tflops": mma_products * achieved_tf * (1.0 + 256.0 / N), "mma_products_per_term": mma_products,
+                         "traffic": tc_traffic(rows_per_launch) if not fast_rank else None,
+                         "traffic_note": None if not fast_rank else "the ncu --set full capture on file (profiles/tcvar_traffic.json: 31.8 GB per launch) is of the three-product kernel; the ranking pass loads the hi planes only, i.e. half of that",
                          "launch_ms": var_launch_ms, "launches_per_step": chunks, "flops_per_launch": flops_launch},
             "acquisition_hbm": {"kernel": "acq_kernel<float>", "bytes_per_candidate": 12, "candidates": M, "achieved": acq_gbs, "peak": pk["hbm"],
                                 "unit": "GB/s", "frac": acq_gbs / pk["hbm"], "peak_source": f"hbm_gbs, {pk['src']}", "launch_ms": acq_ms,

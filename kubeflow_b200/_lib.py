@@ -49,7 +49,7 @@ class KboNotPositiveDefinite(KboError):
 
 
 # every symbol include/kbo.h declares (tests/test_abi.py checks the .so exports exactly these)
-EXPORTS = ["kbo_version", "kbo_create", "kbo_destroy", "kbo_last_error", "kbo_set_scratch_limit", "kbo_set_tc_pair", "kbo_set_tc_refine", "kbo_last_contenders", "kbo_fit", "kbo_fit_append", "kbo_fit_room", "kbo_fit_rebase",
+EXPORTS = ["kbo_version", "kbo_create", "kbo_destroy", "kbo_last_error", "kbo_set_scratch_limit", "kbo_set_tc_pair", "kbo_set_tc_refine", "kbo_last_contenders", "kbo_set_tc_fast", "kbo_last_rank_error", "kbo_fit", "kbo_fit_append", "kbo_fit_room", "kbo_fit_rebase",
            "kbo_fit_info", "kbo_lml_grad", "kbo_fit_state", "kbo_sweep", "kbo_best_to_host", "kbo_suggest_host", "kbo_last_timings",
            "kbo_gram", "kbo_potrf", "kbo_trtri", "kbo_acq_argmax",
            "kbo_req_open", "kbo_req_close", "kbo_req_header", "kbo_req_trials", "kbo_hash64",
@@ -95,6 +95,9 @@ def load() -> C.CDLL:
     lib.kbo_hash64.restype = C.c_uint64
     lib.kbo_fit_rebase.argtypes = [vp, C.c_int32, vp, C.c_int, vp]
     lib.kbo_last_contenders.argtypes = [vp]
+    lib.kbo_set_tc_fast.argtypes = [vp, C.c_int]
+    lib.kbo_last_rank_error.argtypes = [vp]
+    lib.kbo_last_rank_error.restype = C.c_double
     lib.kbo_fit.argtypes = [vp, vp, vp, i32, i32, C.POINTER(KboParams), C.c_int, vp]
     lib.kbo_fit_info.argtypes = [vp, pd, pd, pd, pd, C.POINTER(i32), vp]
     lib.kbo_fit_state.argtypes = [vp, vp, vp, vp, vp]

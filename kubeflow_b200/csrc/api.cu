@@ -38,7 +38,7 @@ void kbo_destroy(kbo_handle* h) {
   cudaSetDevice(h->device);
   DevBuf* bufs[] = {&h->d_inv_ls, &h->Xs, &h->nx, &h->yn, &h->K, &h->W, &h->Linv, &h->T, &h->alpha, &h->z, &h->Wh, &h->Wl,
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
-                    &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow};
+                    &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : h->ev)
@@ -65,6 +65,14 @@ int kbo_set_tc_refine(kbo_handle* h, int enabled) {
   h->tc_refine = enabled != 0;
   return KBO_OK;
 }
+
+int kbo_set_tc_fast(kbo_handle* h, int enabled) {
+  if (!h) return KBO_ERR_INVALID;
+  h->tc_fast = enabled != 0;
+  return KBO_OK;
+}
+
+double kbo_last_rank_error(kbo_handle* h) { return h ? (double)h->last_rank_err : -1.0; }
 
 int kbo_last_contenders(kbo_handle* h) { return h ? h->last_contenders : KBO_ERR_INVALID; }
 

@@ -47,7 +47,10 @@ struct kbo_handle {
   DevBuf best;          // one kbo_best for suggest_host
   DevBuf refine, refine_x;  // contender list / gathered rows of the FP64 refinement (tensor-core mode)
   int last_contenders = 0;
+  float last_rank_err = 0.f;   // largest |σ²(1 product) − σ²(3 products)| over the calibration rows of the last fast sweep
   bool tc_refine = true;
+  bool tc_fast = true;      // array-free tensor-core sweeps rank with ONE fp16 product and let the FP64 refinement decide
+  DevBuf var_cal;           // three-product variance of the calibration rows
   kbo_timings tim{};
   cudaEvent_t ev[8] = {};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_var, ev_cross, ev_acq;
@@ -120,4 +123,4 @@ int kbo_i_acq_argmax_f32(kbo_handle* h, const float* mu_n, const float* var_n, i
 // ---- tc_var.cu ---------------------------------------------------------------------------------
 // var_n[m] = amp − Σ_j (Σ_k K*[m,k] W[j,k])²  for the rows of one chunk, on tcgen05 tensor cores.
 int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl,
-                      int Npad, double w_scale_inv, double amp, float* var_n_out, int k_span, cudaStream_t s);
+                      int Npad, double w_scale_inv, double amp, float* var_n_out, int k_span, cudaStream_t s, int nprod = 3);

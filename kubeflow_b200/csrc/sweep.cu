@@ -713,8 +713,10 @@ static cudaEvent_t* ev_pair(kbo_handle* h, std::vector<std::pair<cudaEvent_t, cu
 #define KBO_TIME_END()                                 \
   if (_ev) cudaEventRecord((&_ev[0])[1], s);
 
+// FP64 evaluation of the n contenders in list (sorted here) and the first-index argmax over them -> best_dev
+static int refine_evaluate(kbo_handle* h, const void* Xc, int xc_dtype, int n, int* list, int* count, int64_t goff, kbo_best* best_dev, cudaStream_t s);
+
 static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, kbo_best* best_dev, cudaStream_t s) {
-  const int N = h->N, D = h->D, ld = h->ld;
   const double* scal = (const double*)h->scal.p;
   KBO_TRY(kbo_reserve(h, h->refine, sizeof(int) * (KBO_REFINE_CAP + 16)));
   int* list = (int*)h->refine.p;
@@ -729,6 +731,12 @@ static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_
   KBO_CUDA(h, cudaStreamSynchronize(s));
   h->last_contenders = n;
   if (n < 1 || n > KBO_REFINE_CAP) return KBO_OK;   // more near-ties than the cap: keep the tensor-core pick (n is reported)
+  return refine_evaluate(h, Xc, xc_dtype, n, list, count, goff, best_dev, s);
+}
+
+static int refine_evaluate(kbo_handle* h, const void* Xc, int xc_dtype, int n, int* list, int* count, int64_t goff, kbo_best* best_dev, cudaStream_t s) {
+  const int N = h->N, D = h->D, ld = h->ld;
+  const double* scal = (const double*)h->scal.p;
   if (n > 1) {   // a single contender needs no ordering
     sort_contenders_kernel<<<1, 1024, 0, s>>>(list, count);
     KBO_LAUNCH_CHECK(h);
@@ -762,8 +770,112 @@ static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_
   return KBO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ranking pass with ONE fp16 product (kbo_set_tc_fast, default on for array-free tensor-core sweeps).  With the suggestion
+// decided in FP64 by the refinement, the sweep only has to RANK: keep every candidate that could still be the maximum given
+// the error of a cheaper variance.  The pass computes Σv² with the hi planes alone (a third of the MMAs, half the bytes);
+// its error bound E on σ² is calibrated per sweep against the three-product kernel on the first wave of rows (8× the largest
+// difference seen + 1e-6).  Candidate i survives iff  max(acq(μ_i, σ²_i ± E)) ≥ max_j min(acq(μ_j, σ²_j ± E)) − slack  — EI
+// and LCB grow with σ, PI is monotone either way, so the two ends bound the value over the interval.  Survivors (typically a
+// handful: EI is sharply peaked) go through the FP64 refinement; more than 4096 of them and the sweep is redone with the
+// three-product kernel.
+__device__ __forceinline__ float acq_any_f32(int acq, float mu, float var, float ym, float ys, float yo, float x, float kp) {
+  return acq == KBO_ACQ_EI    ? acq_value_f32<KBO_ACQ_EI>(mu, var, ym, ys, yo, x, kp)
+         : acq == KBO_ACQ_LCB ? acq_value_f32<KBO_ACQ_LCB>(mu, var, ym, ys, yo, x, kp)
+                              : acq_value_f32<KBO_ACQ_PI>(mu, var, ym, ys, yo, x, kp);
+}
+__device__ __forceinline__ unsigned ordered_bits(float v) {   // monotone float -> uint
+  const unsigned b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// fs[0] = E (bound on |σ²_1 − σ²_3|), fs[1] (as uint) = ordered bits of the best lower bound, reset here
+__global__ void __launch_bounds__(1024) calib_kernel(const float* __restrict__ v1, const float* __restrict__ v3, int n, float* __restrict__ fs) {
+  __shared__ float red[1024];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(v1[i] - v3[i]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    fs[0] = 8.f * red[0] + 1e-6f;
+    fs[2] = red[0];
+    ((unsigned*)fs)[1] = 0u;   // below every ordered value
+  }
+}
+__global__ void __launch_bounds__(256)
+bound_max_kernel(const float* __restrict__ mun, const float* __restrict__ varn, int64_t M, int acq, const double* __restrict__ scal, double xi,
+                 double kappa, float* __restrict__ fs) {
+  const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
+  const float E = fs[0];
+  float best = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256) {
+    const float lo = acq_any_f32(acq, mun[i], fmaxf(varn[i] - E, 0.f), ym, ys, yo, x, kp);
+    const float hi = acq_any_f32(acq, mun[i], varn[i] + E, ym, ys, yo, x, kp);
+    const float lb = fminf(lo, hi);
+    if (lb > best) best = lb;   // NaN never enters
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best > -INFINITY) atomicMax((unsigned*)fs + 1, ordered_bits(best));
+}
+__global__ void __launch_bounds__(256)
+survivor_kernel(const float* __restrict__ mun, const float* __restrict__ varn, int64_t M, int acq, const double* __restrict__ scal, double xi,
+                double kappa, const float* __restrict__ fs, int* __restrict__ list, int* __restrict__ count) {
+  const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
+  const float E = fs[0];
+  const float lb = from_ordered_bits(((const unsigned*)fs)[1]);
+  const float thr = lb - 1e-5f * fmaxf(1.f, fabsf(lb));   // fp32 evaluation and fp32 storage of μ
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256) {
+    const float lo = acq_any_f32(acq, mun[i], fmaxf(varn[i] - E, 0.f), ym, ys, yo, x, kp);
+    const float hi = acq_any_f32(acq, mun[i], varn[i] + E, ym, ys, yo, x, kp);
+    if (fmaxf(lo, hi) >= thr) {
+      const int slot = atomicAdd(count, 1);
+      if (slot < KBO_REFINE_CAP) list[slot] = (int)i;
+    }
+  }
+}
+
+// returns KBO_OK with *overflow = 1 when the survivors do not fit (the caller redoes the sweep with three products)
+static int fast_pick(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, int cal_n, kbo_best* best_dev, int* overflow,
+                     cudaStream_t s) {
+  const double* scal = (const double*)h->scal.p;
+  KBO_TRY(kbo_reserve(h, h->refine, sizeof(int) * (KBO_REFINE_CAP + 16)));
+  int* list = (int*)h->refine.p;
+  int* count = list + KBO_REFINE_CAP;
+  float* fs = (float*)(count + 4);
+  KBO_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int), s));
+  calib_kernel<<<1, 1024, 0, s>>>((const float*)h->varn.p, (const float*)h->var_cal.p, cal_n, fs);
+  KBO_LAUNCH_CHECK(h);
+  bound_max_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs);
+  KBO_LAUNCH_CHECK(h);
+  survivor_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs,
+                                                 list, count);
+  KBO_LAUNCH_CHECK(h);
+  struct { int n; int pad[3]; float fs[4]; } host;
+  KBO_CUDA(h, cudaMemcpyAsync(&host, count, sizeof host, cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaStreamSynchronize(s));
+  h->last_contenders = host.n;
+  h->last_rank_err = host.fs[2];
+  *overflow = (host.n < 1 || host.n > KBO_REFINE_CAP) ? 1 : 0;
+  if (*overflow) return KBO_OK;
+  return refine_evaluate(h, Xc, xc_dtype, host.n, list, count, goff, best_dev, s);
+}
+
+static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out, double* acq_out,
+                      kbo_best* best_dev, cudaStream_t s, bool force_three);
+
 int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out, double* acq_out,
                 kbo_best* best_dev, cudaStream_t s) {
+  return sweep_impl(h, Xc, xc_dtype, M, goff, mu_out, std_out, acq_out, best_dev, s, false);
+}
+
+static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out, double* acq_out,
+                      kbo_best* best_dev, cudaStream_t s, bool force_three) {
   if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_sweep: call kbo_fit first");
   if (M < 1) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: M must be >= 1 (got %lld)", (long long)M);
   if (xc_dtype != KBO_F64 && xc_dtype != KBO_F32) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: xc_dtype must be KBO_F64 or KBO_F32");
@@ -773,6 +885,9 @@ int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t 
                   (h->prm.var_mode == KBO_VAR_AUTO && h->have_planes && (double)M * h->N * h->N > 2e11);
   const size_t esz = xc_dtype == KBO_F64 ? 8 : 4;
   const double* scal = (const double*)h->scal.p;
+  // array-free tensor-core sweeps rank with one fp16 product and let the FP64 refinement decide (fast_pick above)
+  const bool fast = tc && !force_three && h->tc_fast && h->tc_refine && h->tc_pair && !mu_out && !std_out && !acq_out && M < 0x7fffffff;
+  int cal_n = 0;
   int64_t chunk;
   if (tc) {
     // wave-aligned chunks: the variance kernel runs one 128-row CTA per SM, the K* kernel two — a chunk that is a multiple
@@ -814,7 +929,15 @@ int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t 
       {
         KBO_TIME_BEGIN(ev_var, ev_var_used);
         KBO_TRY(kbo_i_tc_variance(h, (const __half*)h->Ksh.p, (const __half*)h->Ksl.p, rows_pad, (const __half*)h->Wh.p, (const __half*)h->Wl.p,
-                                  Npad, 0.0, h->prm.amplitude, (float*)h->varn.p + c0, h->prm.tc_k_span, s));
+                                  Npad, 0.0, h->prm.amplitude, (float*)h->varn.p + c0, fast ? 1024 : h->prm.tc_k_span, s, fast ? 1 : 3));
+        if (fast && c0 == 0) {   // calibration rows: the same first wave again with all three products
+          int64_t cal_rows = (int64_t)h->sm_count * 128;
+          if (cal_rows > rows_pad) cal_rows = rows_pad;
+          cal_n = (int)(cal_rows < rows ? cal_rows : rows);
+          KBO_TRY(kbo_reserve(h, h->var_cal, sizeof(float) * (size_t)cal_rows));
+          KBO_TRY(kbo_i_tc_variance(h, (const __half*)h->Ksh.p, (const __half*)h->Ksl.p, cal_rows, (const __half*)h->Wh.p, (const __half*)h->Wl.p,
+                                    Npad, 0.0, h->prm.amplitude, (float*)h->var_cal.p, h->prm.tc_k_span, s, 3));
+        }
         KBO_TIME_END();
       }
     } else {
@@ -843,6 +966,13 @@ int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t 
   // acquisition over the whole grid; y statistics are read from the fit's device scalars (no host sync)
   {
     KBO_TIME_BEGIN(ev_acq, ev_acq_used);
+    if (fast) {
+      int overflow = 0;
+      KBO_TRY(fast_pick(h, Xc, xc_dtype, M, goff, cal_n, best_dev, &overflow, s));
+      KBO_TIME_END();
+      if (overflow) return sweep_impl(h, Xc, xc_dtype, M, goff, mu_out, std_out, acq_out, best_dev, s, true);
+      return KBO_OK;
+    }
     if (tc) {
       KBO_TRY(launch_acq<float>(h, (const float*)h->mun.p, (const float*)h->varn.p, M, goff, h->prm.acq, 0.0, 1.0, 0.0, scal, h->prm.xi,
                                 h->prm.kappa, mu_out, std_out, acq_out, nullptr, best_dev, s));

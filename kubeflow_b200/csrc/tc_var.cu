@@ -310,7 +310,8 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_variance_pair_kernel(const __grid_constant__ CUtensorMap tmAh64, const __grid_constant__ CUtensorMap tmAl64,
                         const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int n_jtiles,
-                        int span_chunks, double* __restrict__ part /* [2][rows] raw Σv² (scaled units) */, int64_t rows) {
+                        int span_chunks, double* __restrict__ part /* [2][rows] raw Σv² (scaled units) */, int64_t rows,
+                        int nprod /* 3: Al·Bh + Ah·Bl + Ah·Bh; 1: Ah·Bh only (ranking pass, lo planes never loaded) */) {
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* ring = (unsigned char*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   TcSmem* S = (TcSmem*)(ring + TC_STAGES * TC_STAGE_BYTES);
@@ -357,15 +358,16 @@ tc_variance_pair_kernel(const __grid_constant__ CUtensorMap tmAh64, const __grid
           const uint32_t st = c % TC_STAGES, use = c / TC_STAGES;
           mbar_wait(smem_u32(&S->empty[st]), (use & 1) ^ 1, 11);
           const uint32_t bar = smem_u32(&S->full[st]);
-          mbar_expect_tx(bar, 2 * TC_A_BYTES + (ch < my_nch ? 2 * TC_B_BYTES : 0));
+          const uint32_t planes = nprod == 3 ? 2u : 1u;
+          mbar_expect_tx(bar, planes * TC_A_BYTES + (ch < my_nch ? planes * TC_B_BYTES : 0));
           const uint32_t base = smem_u32(ring + st * TC_STAGE_BYTES);
           const int k0 = ch * TC_BK;
           const uint32_t half_off = rank * (TC_A_BYTES / 2);  // rows 64·rank … of the 128-row A tile
           tma_load_2d_mc(base + half_off, &tmAh64, bar, k0, m0 + 64 * (int)rank, (uint16_t)3);
-          tma_load_2d_mc(base + TC_A_BYTES + half_off, &tmAl64, bar, k0, m0 + 64 * (int)rank, (uint16_t)3);
+          if (nprod == 3) tma_load_2d_mc(base + TC_A_BYTES + half_off, &tmAl64, bar, k0, m0 + 64 * (int)rank, (uint16_t)3);
           if (ch < my_nch) {
             tma_load_2d(base + 2 * TC_A_BYTES, &tmBh, bar, k0, my_tile * TC_BN);
-            tma_load_2d(base + 2 * TC_A_BYTES + TC_B_BYTES, &tmBl, bar, k0, my_tile * TC_BN);
+            if (nprod == 3) tma_load_2d(base + 2 * TC_A_BYTES + TC_B_BYTES, &tmBl, bar, k0, my_tile * TC_BN);
           }
         }
       }
@@ -403,9 +405,13 @@ tc_variance_pair_kernel(const __grid_constant__ CUtensorMap tmAh64, const __grid
                 const uint64_t al = umma_desc_sw64(base + TC_A_BYTES + koff);
                 const uint64_t bh = umma_desc_sw64(base + 2 * TC_A_BYTES + koff);
                 const uint64_t bl = umma_desc_sw64(base + 2 * TC_A_BYTES + TC_B_BYTES + koff);
-                umma_f16(d_tmem, al, bh, idesc, (ch > ch0 || k > 0) ? 1u : 0u);
-                umma_f16(d_tmem, ah, bl, idesc, 1u);
-                umma_f16(d_tmem, ah, bh, idesc, 1u);
+                if (nprod == 3) {
+                  umma_f16(d_tmem, al, bh, idesc, (ch > ch0 || k > 0) ? 1u : 0u);
+                  umma_f16(d_tmem, ah, bl, idesc, 1u);
+                  umma_f16(d_tmem, ah, bh, idesc, 1u);
+                } else {
+                  umma_f16(d_tmem, ah, bh, idesc, (ch > ch0 || k > 0) ? 1u : 0u);
+                }
               }
             }
             umma_commit_mc(smem_u32(&S->empty[st]), (uint16_t)3);  // release the stage in BOTH CTAs
@@ -509,7 +515,8 @@ int encode_map(kbo_handle* h, CUtensorMap* out, const void* base, uint64_t inner
 }
 
 int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl, int Npad,
-              const double* w_scale_dev, double amp, float* var_out, double* sumsq_out, int k_span, cudaStream_t s) {
+              const double* w_scale_dev, double amp, float* var_out, double* sumsq_out, int k_span, cudaStream_t s, int nprod = 3) {
+  if (nprod != 3 && !h->tc_pair) KBO_FAIL(h, KBO_ERR_STATE, "tc_variance: the one-product ranking pass needs the cluster kernel (kbo_set_tc_pair)");
   if (rows % TC_BM != 0 || Npad % TC_BN != 0) KBO_FAIL(h, KBO_ERR_INVALID, "tc_variance: rows %% 128 and Npad %% 256 must be 0");
   // TMEM accumulation rounds toward zero (one-sided error ≈ 5e-9·k_span relative on Σv², profiles/README.md): 128 puts the
   // truncation at the level of the fp16×3 split error (≈ 5e-7) and costs 8 % of tensor time against never draining.
@@ -533,7 +540,7 @@ int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows,
     KBO_TRY(encode_map(h, &tmAl64, Ksl, (uint64_t)Npad, (uint64_t)rows, 64));
     KBO_TRY(kbo_reserve(h, h->part, sizeof(double) * 2 * (size_t)rows));
     tc_variance_pair_kernel<<<(unsigned)(2 * (rows / TC_BM)), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh64, tmAl64, tmBh, tmBl, Npad / TC_BN, span_chunks,
-                                                                                             (double*)h->part.p, rows);
+                                                                                             (double*)h->part.p, rows, nprod);
     KBO_LAUNCH_CHECK(h);
     tc_pair_finish_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>((const double*)h->part.p, rows, w_scale_dev, amp, var_out, sumsq_out);
     KBO_LAUNCH_CHECK(h);
@@ -548,8 +555,8 @@ int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows,
 }  // namespace
 
 int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl, int Npad,
-                      double /*unused*/, double amp, float* var_n_out, int k_span, cudaStream_t s) {
-  return tc_launch(h, Ksh, Ksl, rows, Wh, Wl, Npad, (const double*)h->scal.p + 6, amp, var_n_out, nullptr, k_span, s);
+                      double /*unused*/, double amp, float* var_n_out, int k_span, cudaStream_t s, int nprod) {
+  return tc_launch(h, Ksh, Ksl, rows, Wh, Wl, Npad, (const double*)h->scal.p + 6, amp, var_n_out, nullptr, k_span, s, nprod);
 }
 
 // Raw entry for the kernel-level parity test: caller supplies fp16 planes and the scale pair on the device.

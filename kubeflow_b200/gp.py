@@ -28,7 +28,7 @@ class GPEngine:
     def __init__(self, device: int = 0, *, kernel: str = "matern52", length_scale=1.0, amplitude: float = 1.0,
                  noise: float = 1e-10, acq: str = "ei", xi: float = 0.01, kappa: float = 1.96,
                  normalize_y: bool = True, var_mode: str = "auto", tc_k_span: int = 0, scratch_limit: int | None = None,
-                 tc_pair: bool | None = None, tc_refine: bool | None = None):
+                 tc_pair: bool | None = None, tc_refine: bool | None = None, tc_fast: bool | None = None):
         if kernel not in L.KERNELS:
             raise ValueError(f"kernel must be one of {sorted(L.KERNELS)}, got {kernel!r}")
         if acq not in L.ACQS:
@@ -54,6 +54,8 @@ class GPEngine:
             L.check(self.lib, self._h, self.lib.kbo_set_tc_pair(self._h, int(bool(tc_pair))))
         if tc_refine is not None:
             L.check(self.lib, self._h, self.lib.kbo_set_tc_refine(self._h, int(bool(tc_refine))))
+        if tc_fast is not None:
+            L.check(self.lib, self._h, self.lib.kbo_set_tc_fast(self._h, int(bool(tc_fast))))
         self._best_dev = torch.empty(4, dtype=torch.float64, device=f"cuda:{self.device}")
 
     # -- plumbing ----------------------------------------------------------------------------------
@@ -148,6 +150,10 @@ class GPEngine:
     def last_contenders(self) -> int:
         """How many candidates the last tensor-core sweep re-evaluated in FP64 (kbo_set_tc_refine)."""
         return int(self.lib.kbo_last_contenders(self._h))
+
+    def last_rank_error(self) -> float:
+        """Largest |σ²(1 product) − σ²(3 products)| on the calibration rows of the last one-product sweep (kbo_set_tc_fast)."""
+        return float(self.lib.kbo_last_rank_error(self._h))
 
     def lml_grad(self):
         """(lml, grad) of the last tell; grad w.r.t. (log amplitude, log noise, log ℓ_1..ℓ_P) as a NumPy array."""

@@ -552,3 +552,42 @@ def test_optimizer_constant_liar_appends_instead_of_refitting():
     assert fits == ["append", "fit"]
     np.testing.assert_allclose(outs[0], outs[1], rtol=0, atol=0)
     np.testing.assert_allclose(later[0], later[1], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("N,M,D,kind,acq", [(1024, 50000, 8, "rbf", "ei"), (2048, 30000, 32, "matern52", "ei"), (1500, 20000, 6, "matern52", "lcb"),
+                                            (1200, 20000, 5, "rbf", "pi")])
+def test_one_product_ranking_pass_returns_the_same_suggestion(N, M, D, kind, acq):
+    """kbo_set_tc_fast: the array-free tensor-core sweep ranks with one fp16 product and lets the FP64 refinement decide among
+    the candidates that could still be the maximum.  The returned suggestion must be the three-product sweep's, bit for bit
+    (both end in the same FP64 evaluation), and the FP64 engine's to rounding; the ranking error it calibrates is reported."""
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    kw = dict(kind=kind, acq=acq, **th)
+    fast = _engine(kw, "tc"); fast.tell(X, y)
+    slow = _engine(kw, "tc", tc_fast=False); slow.tell(X, y)
+    e64 = _engine(kw, "f64"); e64.tell(X, y)
+    bf, bs, b6 = fast.ask(Xc), slow.ask(Xc), e64.ask(Xc)
+    assert (bf.index, bf.value, bf.mu, bf.std) == (bs.index, bs.value, bs.mu, bs.std)
+    assert bf.index == b6.index and abs(bf.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value))
+    assert 1 <= fast.last_contenders() <= 4096
+    assert 1e-7 < fast.last_rank_error() < 2e-2          # fp16 hi planes only: |d sigma²| ~ 1e-4 … 1e-3
+    assert slow.last_rank_error() == 0.0
+    # sharded over 3 ranks: each shard calibrates and prunes on its own rows, the exchange picks the same point
+    parts = [fast.ask(Xc[s:s + 7000], global_offset=s) for s in range(0, M, 7000)]
+    win = max(parts, key=lambda b: (b.value, -b.index))
+    assert (win.index, win.value) == (bf.index, bf.value)
+    for e in (fast, slow, e64):
+        e.close()
+
+
+def test_one_product_ranking_pass_falls_back_when_too_many_survive():
+    """6000 identical candidates all survive the pruning (> 4096): the sweep is redone with three products and the pick is
+    the lowest index, as the reference's argmin over identical values."""
+    X, y, Xc = O.synthetic(300, 10, 4)
+    th = O.theta_of_record(4)
+    eng = _engine(dict(kind="matern52", acq="ei", **th), "tc"); eng.tell(X, y)
+    b = eng.ask(np.repeat(Xc[:1], 6000, axis=0))
+    assert b.index == 0 and eng.last_contenders() > 4096
+    ref = O.suggest(X, y, Xc[:1], kind="matern52", acq="ei", **th)
+    assert abs(b.value - ref["value"]) <= TOL_TC
+    eng.close()
