@@ -119,7 +119,8 @@ class Optimizer:
                 if p == n == len(yh) and np.array_equal(ya, yh):
                     done = "reuse"
                 else:
-                    eng.rebase(p, ya[:p])
+                    if p != len(yh) or not np.array_equal(ya[:p], yh[:p]):   # rows dropped or targets changed
+                        eng.rebase(p, ya[:p])
                     for i in range(p, n):
                         eng.append(Xt[i], ya[i])
                     done = "append" if n > p else "rebase"
