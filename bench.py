@@ -384,7 +384,9 @@ def main():
                          "issued_mma_tflops": mma_products * achieved_tf * (1.0 + 256.0 / N), "mma_products_per_term": mma_products,
                          "traffic": tc_traffic(rows_per_launch) if not fast_rank else None,
                          "traffic_note": None if not fast_rank else "the ncu --set full capture on file (profiles/tcvar_traffic.json: 31.8 GB per launch) is of the three-product kernel; the ranking pass loads the hi planes only, i.e. half of that",
-                         "launch_ms": var_launch_ms, "launches_per_step": chunks, "flops_per_launch": flops_launch},
+                         "launch_ms": var_launch_ms, "launches_per_step": chunks, "flops_per_launch": flops_launch,
+                         "launch_note": ("variance phase time / chunks; the phase also holds the calibration launch (first wave of rows, three products), "
+                                         "so the per-launch time is overstated by ~5 %") if fast_rank else None},
             "acquisition_hbm": {"kernel": "acq_kernel<float>", "bytes_per_candidate": 12, "candidates": M, "achieved": acq_gbs, "peak": pk["hbm"],
                                 "unit": "GB/s", "frac": acq_gbs / pk["hbm"], "peak_source": f"hbm_gbs, {pk['src']}", "launch_ms": acq_ms,
                                 "at_16M_candidates": {"achieved": acq_gbs16, "frac": acq_gbs16 / pk["hbm"], "launch_ms": acq_ms16},
