@@ -651,6 +651,7 @@ int kbo_i_fit_append(kbo_handle* h, const double* x_dev, double y, cudaStream_t 
     KBO_LAUNCH_CHECK(h);
   }
   h->N = row + 1;
+  h->Npad = round_up(h->N, 256);   // a rebase may have shrunk it below the new N; the planes are rebuilt at this extent by fit_finish
   prep_y_kernel<<<1, 1024, 0, s>>>((const double*)h->yraw.p, h->N, h->prm.normalize_y, (double*)h->yn.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
   KBO_TRY(fit_finish(h, s));

@@ -881,6 +881,7 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
   if (xc_dtype != KBO_F64 && xc_dtype != KBO_F32) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: xc_dtype must be KBO_F64 or KBO_F32");
   if (h->D > 256) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_sweep: D <= 256 supported (got %d)", h->D);
   const int N = h->N, D = h->D, ld = h->ld, Npad = h->Npad;
+  if (N > Npad || N > ld) KBO_FAIL(h, KBO_ERR_STATE, "kbo_sweep: inconsistent fit state (N=%d, Npad=%d, ld=%d)", N, Npad, ld);
   const bool tc = h->prm.var_mode == KBO_VAR_TC_F16X3 ||
                   (h->prm.var_mode == KBO_VAR_AUTO && h->have_planes && (double)M * h->N * h->N > 2e11);
   const size_t esz = xc_dtype == KBO_F64 ? 8 : 4;

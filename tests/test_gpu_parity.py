@@ -591,3 +591,28 @@ def test_one_product_ranking_pass_falls_back_when_too_many_survive():
     ref = O.suggest(X, y, Xc[:1], kind="matern52", acq="ei", **th)
     assert abs(b.value - ref["value"]) <= TOL_TC
     eng.close()
+
+
+def test_rebase_then_append_across_a_256_boundary_in_tc_mode():
+    """fit 300 -> rebase 250 (the fp16 planes shrink to 256) -> append past 256: the planes and the K* scratch must grow back
+    with the history (a stale 256-wide extent dropped rows/columns of W and wrote past the K* scratch).  Compared against a
+    refit of the same 262-trial history, per-candidate arrays and the suggestion."""
+    D = 6
+    X, y, Xc = O.synthetic(262, 4000, D)
+    th = O.theta_of_record(D)
+    kw = dict(kind="matern52", acq="ei", **th)
+    eng = _engine(kw, "tc"); eng.tell(np.concatenate([X[:250], X[:50] * 0.5 + 0.25]), np.concatenate([y[:250], y[:50]]))
+    eng.rebase(250, y[:250])
+    for i in range(250, 262):
+        eng.append(X[i], y[i])
+    assert eng.N == 262
+    ref = _engine(kw, "tc"); ref.tell(X, y)
+    be, me, se, ae = eng.ask(Xc, return_arrays=True)
+    br, mr, sr, ar = ref.ask(Xc, return_arrays=True)
+    np.testing.assert_allclose(ae.cpu().numpy(), ar.cpu().numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(se.cpu().numpy(), sr.cpu().numpy(), rtol=0, atol=2e-5)
+    assert be.index == br.index and abs(be.value - br.value) <= 1e-9
+    b2, r2 = eng.ask(Xc), ref.ask(Xc)          # the array-free path (ranking pass + FP64 decision)
+    assert b2.index == r2.index and abs(b2.value - r2.value) <= 1e-9
+    _check_argmax(b2, O.suggest(X, y, Xc, kind="matern52", acq="ei", **th)["acq"], TOL_F64)
+    eng.close(); ref.close()
