@@ -93,6 +93,7 @@ typedef struct kbo_timings {
   float acq_kernel_ms;   /* acquisition + argmax kernels                      */
   int32_t launches;      /* kernels launched by the call                      */
   int32_t chunks;
+  float calib_ms;        /* ranking pass: the stratified calibration rows (FP64 K* + three-product contraction) */
 } kbo_timings;
 
 int kbo_version(void);
@@ -120,6 +121,18 @@ int kbo_last_contenders(kbo_handle* h);
  * largest |sigma²(1 product) - sigma²(3 products)| seen on the calibration rows of the last such sweep. */
 int kbo_set_tc_fast(kbo_handle* h, int enabled);
 double kbo_last_rank_error(kbo_handle* h);
+/* The ranking pass builds its K* plane on the tensor cores (c·x as tcgen05 MMAs of fp16 hi/lo splits, kernel values in fp32,
+ * only the hi plane written, the mean accumulated on the fly) and contracts it with cta_group::2 MMAs; 0 selects the FP64 K*
+ * kernel + single-CTA-MMA cluster kernel of round 1 for that pass.  Default 1 (needs D <= 128; wider spaces use the FP64
+ * kernel).  Either way the calibration rows are STRATIFIED over the grid (row i*M/n) and go through the FP64 K* kernel and
+ * the three-product contraction; kbo_last_rank_mu_error is the largest |mean(ranking) - mean(FP64)| seen on them, in
+ * normalised-y units (0 with the FP64 K* kernel).  The environment variable KBO_RANK_TC sets the initial value. */
+int kbo_set_rank_tc(kbo_handle* h, int enabled);
+double kbo_last_rank_mu_error(kbo_handle* h);
+/* How the last tensor-core sweep decided its suggestion: 0 = FP64 evaluation of every candidate that could still be the
+ * maximum; 1 = more such candidates than the cap (4096), FP64 decision among the best 4096 by fp32 value; 2 = not refined
+ * (exact fp32 ties beyond the cap, or refinement switched off): the suggestion carries the mode's own accuracy. */
+int kbo_last_unrefined(kbo_handle* h);
 
 /* ---- tell: GaussianProcessRegressor.fit at fixed θ ($SK/_gpr.py:275-280, 349-368) ---------------
  * X: N×D fp64, y: N fp64, device pointers (x_on_host = 0) or host pointers (x_on_host = 1).

@@ -28,7 +28,7 @@ class KboBest(C.Structure):
 class KboTimings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("fit_ms", C.c_float), ("sweep_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("total_ms", C.c_float), ("var_kernel_ms", C.c_float), ("cross_kernel_ms", C.c_float),
-                ("acq_kernel_ms", C.c_float), ("launches", C.c_int32), ("chunks", C.c_int32)]
+                ("acq_kernel_ms", C.c_float), ("launches", C.c_int32), ("chunks", C.c_int32), ("calib_ms", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -49,7 +49,7 @@ class KboNotPositiveDefinite(KboError):
 
 
 # every symbol include/kbo.h declares (tests/test_abi.py checks the .so exports exactly these)
-EXPORTS = ["kbo_version", "kbo_create", "kbo_destroy", "kbo_last_error", "kbo_set_scratch_limit", "kbo_set_tc_pair", "kbo_set_tc_refine", "kbo_last_contenders", "kbo_set_tc_fast", "kbo_last_rank_error", "kbo_fit", "kbo_fit_append", "kbo_fit_room", "kbo_fit_rebase",
+EXPORTS = ["kbo_version", "kbo_create", "kbo_destroy", "kbo_last_error", "kbo_set_scratch_limit", "kbo_set_tc_pair", "kbo_set_tc_refine", "kbo_last_contenders", "kbo_set_tc_fast", "kbo_last_rank_error", "kbo_set_rank_tc", "kbo_last_rank_mu_error", "kbo_last_unrefined", "kbo_fit", "kbo_fit_append", "kbo_fit_room", "kbo_fit_rebase",
            "kbo_fit_info", "kbo_lml_grad", "kbo_fit_state", "kbo_sweep", "kbo_best_to_host", "kbo_suggest_host", "kbo_last_timings",
            "kbo_gram", "kbo_potrf", "kbo_trtri", "kbo_acq_argmax",
            "kbo_req_open", "kbo_req_close", "kbo_req_header", "kbo_req_trials", "kbo_hash64",
@@ -98,6 +98,11 @@ def load() -> C.CDLL:
     lib.kbo_set_tc_fast.argtypes = [vp, C.c_int]
     lib.kbo_last_rank_error.argtypes = [vp]
     lib.kbo_last_rank_error.restype = C.c_double
+    lib.kbo_set_rank_tc.argtypes = [vp, C.c_int]
+    lib.kbo_last_rank_mu_error.argtypes = [vp]
+    lib.kbo_last_rank_mu_error.restype = C.c_double
+    lib.kbo_last_unrefined.argtypes = [vp]
+    lib.kbo_debug_rank_pass.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, vp]
     lib.kbo_fit.argtypes = [vp, vp, vp, i32, i32, C.POINTER(KboParams), C.c_int, vp]
     lib.kbo_fit_info.argtypes = [vp, pd, pd, pd, pd, C.POINTER(i32), vp]
     lib.kbo_fit_state.argtypes = [vp, vp, vp, vp, vp]
@@ -119,7 +124,7 @@ def load() -> C.CDLL:
     lib.kbo_cma_state.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
     lib.kbo_cma_run_synthetic.argtypes = [vp, vp, i32, i32, pd, C.POINTER(C.c_float), pd]
     lib.kbo_tc_variance_raw.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp, dbl, vp, vp, i32, vp]
-    for name in EXPORTS + ["kbo_tc_variance_raw"]:
+    for name in EXPORTS + ["kbo_tc_variance_raw", "kbo_debug_rank_pass"]:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("kbo_version",):
             fn.restype = C.c_int

@@ -24,6 +24,7 @@ int kbo_create(kbo_handle** out, int device) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("KBO_TC_PAIR")) h->tc_pair = atoi(e) != 0;
+  if (const char* e = getenv("KBO_RANK_TC")) h->rank_tc = atoi(e) != 0;
   if (prop.major != 10) {
     // sm_100a cubin only: refuse politely instead of failing at the first launch
     h->err = "libkbo is built for sm_100a (B200) only";
@@ -38,12 +39,14 @@ void kbo_destroy(kbo_handle* h) {
   cudaSetDevice(h->device);
   DevBuf* bufs[] = {&h->d_inv_ls, &h->Xs, &h->nx, &h->yn, &h->K, &h->W, &h->Linv, &h->T, &h->alpha, &h->z, &h->Wh, &h->Wl,
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
-                    &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal};
+                    &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal,
+                    &h->ks_center, &h->ks_Xh, &h->ks_Xl, &h->ks_nxal, &h->ks_Ch, &h->ks_Cl, &h->ks_nc, &h->rk_part, &h->cal_idx, &h->cal_x, &h->cal_mu,
+                    &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
-  for (auto* v : {&h->ev_var, &h->ev_cross, &h->ev_acq})
+  for (auto* v : {&h->ev_var, &h->ev_cross, &h->ev_acq, &h->ev_cal})
     for (auto& p : *v) {
       cudaEventDestroy(p.first);
       cudaEventDestroy(p.second);
@@ -73,6 +76,16 @@ int kbo_set_tc_fast(kbo_handle* h, int enabled) {
 }
 
 double kbo_last_rank_error(kbo_handle* h) { return h ? (double)h->last_rank_err : -1.0; }
+
+double kbo_last_rank_mu_error(kbo_handle* h) { return h ? (double)h->last_rank_mu_err : -1.0; }
+
+int kbo_last_unrefined(kbo_handle* h) { return h ? h->last_unrefined : KBO_ERR_INVALID; }
+
+int kbo_set_rank_tc(kbo_handle* h, int enabled) {
+  if (!h) return KBO_ERR_INVALID;
+  h->rank_tc = enabled != 0;
+  return KBO_OK;
+}
 
 int kbo_last_contenders(kbo_handle* h) { return h ? h->last_contenders : KBO_ERR_INVALID; }
 
@@ -208,7 +221,7 @@ int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N,
   KBO_TRY(kbo_reserve(h, h->best, sizeof(kbo_best)));
   h->launches = 0;
   h->time_kernels = true;
-  h->ev_var_used = h->ev_cross_used = h->ev_acq_used = 0;
+  h->ev_var_used = h->ev_cross_used = h->ev_acq_used = h->ev_cal_used = 0;
   cudaEventRecord(h->ev[0], s);
   // H2D of everything up front (X, y, Xc), then tell + ask, then the 32-byte result back
   int r = kbo_fit(h, X, y, N, D, p, 1, s);
@@ -240,6 +253,7 @@ int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N,
   t.var_kernel_ms = sum_pairs(h->ev_var, h->ev_var_used);
   t.cross_kernel_ms = sum_pairs(h->ev_cross, h->ev_cross_used);
   t.acq_kernel_ms = sum_pairs(h->ev_acq, h->ev_acq_used);
+  t.calib_ms = sum_pairs(h->ev_cal, h->ev_cal_used);
   t.launches = h->launches;
   t.chunks = h->tim.chunks;
   h->tim = t;
@@ -280,6 +294,35 @@ int kbo_acq_argmax(kbo_handle* h, const float* mu_n, const float* var_n, int64_t
   if (acq < KBO_ACQ_EI || acq > KBO_ACQ_PI) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_acq_argmax: unknown acquisition %d", acq);
   return kbo_i_acq_argmax_f32(h, mu_n, var_n, M, global_offset, acq, y_mean, y_std, y_opt, xi, kappa, 1.0, acq_out, best_dev,
                               (cudaStream_t)stream);
+}
+
+// Test hook (not in kbo.h): the ranking pass alone over M candidates (device pointer), normalised mean / variance copied to
+// caller-owned DEVICE float arrays.  mode 0 = FP64 K* kernel + one-product cluster kernel, 1 = tensor-core K* + cta_group::2
+// ranking kernel.  plane_out (optional, M × Npad fp16, M <= one chunk) receives the K* hi plane the contraction consumed.
+int kbo_debug_rank_pass(kbo_handle* h, const void* Xc, int32_t xc_dtype, int64_t M, int32_t mode, float* mun_out, float* varn_out, void* plane_out,
+                        void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!h->fitted || !h->have_planes) KBO_FAIL(h, KBO_ERR_STATE, "kbo_debug_rank_pass: needs a fit with tensor-core planes");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Npad = h->Npad;
+  const int64_t rows_pad = round_up64(M, 256);
+  KBO_TRY(kbo_reserve(h, h->Ksh, sizeof(__half) * (size_t)rows_pad * Npad));
+  KBO_TRY(kbo_reserve(h, h->Ksl, sizeof(__half) * (size_t)rows_pad * Npad));
+  KBO_TRY(kbo_reserve(h, h->mun, sizeof(float) * (size_t)(rows_pad + 256)));
+  KBO_TRY(kbo_reserve(h, h->varn, sizeof(float) * (size_t)(rows_pad + 256)));
+  if (mode == 1) {
+    if (!h->ks_ready) KBO_FAIL(h, KBO_ERR_STATE, "kbo_debug_rank_pass: tensor-core K* operands not available (D > 128?)");
+    KBO_TRY(kbo_i_tc_kstar(h, Xc, xc_dtype, M, (__half*)h->Ksh.p, (float*)h->mun.p, s));
+    KBO_TRY(kbo_i_tc_rank(h, (const __half*)h->Ksh.p, rows_pad, (const __half*)h->Wh.p, Npad, h->prm.amplitude, (float*)h->varn.p, s));
+  } else {
+    KBO_TRY(kbo_i_debug_cross_planes(h, Xc, xc_dtype, M, s));
+    KBO_TRY(kbo_i_tc_variance(h, (const __half*)h->Ksh.p, (const __half*)h->Ksl.p, round_up64(M, 128), (const __half*)h->Wh.p, (const __half*)h->Wl.p,
+                              Npad, 0.0, h->prm.amplitude, (float*)h->varn.p, 1024, s, 1));
+  }
+  KBO_CUDA(h, cudaMemcpyAsync(mun_out, h->mun.p, sizeof(float) * (size_t)M, cudaMemcpyDeviceToDevice, s));
+  KBO_CUDA(h, cudaMemcpyAsync(varn_out, h->varn.p, sizeof(float) * (size_t)M, cudaMemcpyDeviceToDevice, s));
+  if (plane_out) KBO_CUDA(h, cudaMemcpyAsync(plane_out, h->Ksh.p, sizeof(__half) * (size_t)M * Npad, cudaMemcpyDeviceToDevice, s));
+  return KBO_OK;
 }
 
 }  // extern "C"

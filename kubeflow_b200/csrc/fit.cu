@@ -450,7 +450,7 @@ int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double
 }
 
 // alpha = Wᵀ(W yn), LML, and (when the tensor-core sweep may be used) the fp16 hi/lo planes of W — shared by fit and append
-static int fit_finish(kbo_handle* h, cudaStream_t s) {
+static int fit_finish(kbo_handle* h, cudaStream_t s, bool new_center) {
   const int N = h->N, ld = h->ld;
   const kbo_params* p = &h->prm;
   trmv_lower_kernel<<<(N + 7) / 8, 256, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->yn.p, (double*)h->z.p);
@@ -478,6 +478,10 @@ static int fit_finish(kbo_handle* h, cudaStream_t s) {
     dim3 g((Npad + 255) / 256, Npad);
     split_w_kernel<<<g, 256, 0, s>>>((const double*)h->W.p, N, ld, Npad, amax, (__half*)h->Wh.p, (__half*)h->Wl.p, (double*)h->scal.p + 6);
     KBO_LAUNCH_CHECK(h);
+    // trial-side operands of the tensor-core K* kernel (alpha changes with every fit / append / rebase)
+    KBO_TRY(kbo_i_tc_trials_prep(h, new_center, s));
+  } else {
+    h->ks_ready = false;
   }
   return KBO_OK;
 }
@@ -493,6 +497,7 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
     if (!(p->length_scale[d] > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit: length_scale[%d] must be > 0", d);
   h->fitted = false;
   h->have_planes = false;
+  h->ks_ready = false;
   h->N = N;
   h->D = D;
   h->ld = round_up(N, 64);
@@ -535,7 +540,7 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   if (trace) cudaEventRecord(te[2], s);
   KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
   if (trace) cudaEventRecord(te[3], s);
-  KBO_TRY(fit_finish(h, s));
+  KBO_TRY(fit_finish(h, s, true));
   if (trace) {
     cudaEventRecord(te[4], s);
     cudaEventSynchronize(te[4]);
@@ -654,7 +659,7 @@ int kbo_i_fit_append(kbo_handle* h, const double* x_dev, double y, cudaStream_t 
   h->Npad = round_up(h->N, 256);   // a rebase may have shrunk it below the new N; the planes are rebuilt at this extent by fit_finish
   prep_y_kernel<<<1, 1024, 0, s>>>((const double*)h->yraw.p, h->N, h->prm.normalize_y, (double*)h->yn.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
-  KBO_TRY(fit_finish(h, s));
+  KBO_TRY(fit_finish(h, s, false));
   return KBO_OK;
 }
 
@@ -674,6 +679,6 @@ int kbo_i_fit_rebase(kbo_handle* h, int n_keep, const double* y_dev, cudaStream_
   KBO_LAUNCH_CHECK(h);
   prep_y_kernel<<<1, 1024, 0, s>>>((const double*)h->yraw.p, h->N, h->prm.normalize_y, (double*)h->yn.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
-  KBO_TRY(fit_finish(h, s));
+  KBO_TRY(fit_finish(h, s, false));
   return KBO_OK;
 }

@@ -1,5 +1,6 @@
 // Internal declarations shared by the libkbo translation units (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -53,12 +54,30 @@ struct kbo_handle {
   DevBuf var_cal;           // three-product variance of the calibration rows
   kbo_timings tim{};
   cudaEvent_t ev[8] = {};
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_var, ev_cross, ev_acq;
-  size_t ev_var_used = 0, ev_cross_used = 0, ev_acq_used = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_var, ev_cross, ev_acq, ev_cal;
+  size_t ev_var_used = 0, ev_cross_used = 0, ev_acq_used = 0, ev_cal_used = 0;
   int launches = 0;
   bool time_kernels = false;
   bool attr_fit = false, attr_tc = false;
   int tc_pair = 1;  // variance kernel variant (kbo_set_tc_pair)  // cudaFuncSetAttribute done for this handle's device
+  // ---- tensor-core K* generation (tc_kstar.cu) and cta_group::2 ranking kernel (tc_rank.cu) ---------------------------
+  bool rank_tc = true;        // kbo_set_rank_tc: the ranking pass builds K̃* on the tensor cores and contracts with cta_group::2 MMAs
+  bool ks_ready = false;      // trial-side operands below match the current fit
+  DevBuf ks_center;           // D doubles: centre subtracted from the scaled coordinates (any fixed vector is valid)
+  DevBuf ks_Xh, ks_Xl;        // trials, fp16 hi/lo planes, round_up(N,256) × round_up(D,32)
+  DevBuf ks_nxal;             // (|x̂_n|², alpha_n) float pairs
+  DevBuf ks_Ch, ks_Cl, ks_nc; // candidate planes / squared norms of the current chunk
+  DevBuf rk_part;             // [tile pairs][rows] partial Σ v² of the ranking kernel
+  struct RkSched {
+    int key[3] = {-1, -1, -1};  // (row groups, j-tiles, clusters)
+    DevBuf dev;
+    std::vector<int> host;
+  } rk_sched[4];
+  int rk_sched_next = 0;
+  bool attr_rank = false;
+  DevBuf cal_idx, cal_x, cal_mu;   // stratified calibration rows of the ranking pass: indices, gathered rows, FP64-path mean
+  float last_rank_mu_err = 0.f;    // largest |μ̃ − μ| (normalised units) on the calibration rows of the last ranking sweep
+  int last_unrefined = 0;          // 1: the last tensor-core sweep could not decide in FP64 (more near-ties than the cap)
 };
 
 enum ScalIdx { S_YMEAN = 0, S_YSTD = 1, S_YOPT = 2, S_LML = 3, S_LOGDET = 4, S_QUAD = 5, S_COUNT = 8 };
@@ -117,9 +136,16 @@ int kbo_i_fit(kbo_handle* h, const double* X_dev, const double* y_dev, int N, in
 // ---- sweep.cu ----------------------------------------------------------------------------------
 int kbo_i_sweep(kbo_handle* h, const void* Xc_dev, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out,
                 double* acq_out, kbo_best* best_dev, cudaStream_t s);
+int kbo_i_debug_cross_planes(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, cudaStream_t s);   // FP64 K* → Ksh/Ksl, mun (test hook)
 int kbo_i_acq_argmax_f32(kbo_handle* h, const float* mu_n, const float* var_n, int64_t M, int64_t goff, int acq, double y_mean,
                          double y_std, double y_opt, double xi, double kappa, double amp, float* acq_out, kbo_best* best_dev,
                          cudaStream_t s);
+int kbo_i_encode_map_f16(kbo_handle* h, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                         uint32_t box_outer);
+// ---- tc_kstar.cu / tc_rank.cu ------------------------------------------------------------------
+int kbo_i_tc_trials_prep(kbo_handle* h, bool new_center, cudaStream_t s);
+int kbo_i_tc_kstar(kbo_handle* h, const void* Xc, int xc_dtype, int64_t rows, __half* Ksh, float* mun, cudaStream_t s);
+int kbo_i_tc_rank(kbo_handle* h, const __half* Ksh, int64_t rows, const __half* Wh, int Npad, double amp, float* var_n_out, cudaStream_t s);
 // ---- tc_var.cu ---------------------------------------------------------------------------------
 // var_n[m] = amp − Σ_j (Σ_k K*[m,k] W[j,k])²  for the rows of one chunk, on tcgen05 tensor cores.
 int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl,

@@ -721,16 +721,31 @@ static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_
   KBO_TRY(kbo_reserve(h, h->refine, sizeof(int) * (KBO_REFINE_CAP + 16)));
   int* list = (int*)h->refine.p;
   int* count = list + KBO_REFINE_CAP;
-  KBO_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int), s));
-  const double delta = 2e-4;   // ≥ 10× the tensor-core mode's acquisition error bound
-  contender_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa,
-                                                  best_dev, goff, delta, list, count);
-  KBO_LAUNCH_CHECK(h);
-  int n = 0;
-  KBO_CUDA(h, cudaMemcpyAsync(&n, count, sizeof(int), cudaMemcpyDeviceToHost, s));
-  KBO_CUDA(h, cudaStreamSynchronize(s));
-  h->last_contenders = n;
-  if (n < 1 || n > KBO_REFINE_CAP) return KBO_OK;   // more near-ties than the cap: keep the tensor-core pick (n is reported)
+  // contenders: within delta of the fp32 maximum.  2e-4 is ≥ 10× the tensor-core mode's acquisition error bound; when more
+  // than the cap lie inside it (a flat landscape, or a late-stage experiment whose best EI is itself below 2e-4) the window is
+  // narrowed until the cap holds and the FP64 decision is taken among the best by fp32 value (last_unrefined = 1); only
+  // exact fp32 ties beyond the cap — e.g. thousands of identical candidates — keep the tensor-core pick (last_unrefined = 2),
+  // which is then the lowest index among them, as the reference's argmin is.
+  double delta = 2e-4;
+  int n = 0, first_n = 0;
+  h->last_unrefined = 0;
+  for (int round = 0; round < 24; round++) {
+    KBO_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int), s));
+    contender_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa,
+                                                    best_dev, goff, delta, list, count);
+    KBO_LAUNCH_CHECK(h);
+    KBO_CUDA(h, cudaMemcpyAsync(&n, count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KBO_CUDA(h, cudaStreamSynchronize(s));
+    if (round == 0) first_n = n;
+    if (n <= KBO_REFINE_CAP) break;
+    h->last_unrefined = 1;
+    delta = round < 22 ? delta * 0.25 : 0.0;   // the last attempt: exact ties of the maximum only
+  }
+  h->last_contenders = first_n;
+  if (n < 1 || n > KBO_REFINE_CAP) {
+    h->last_unrefined = 2;
+    return KBO_OK;
+  }
   return refine_evaluate(h, Xc, xc_dtype, n, list, count, goff, best_dev, s);
 }
 
@@ -790,33 +805,61 @@ __device__ __forceinline__ unsigned ordered_bits(float v) {   // monotone float 
 }
 __device__ __forceinline__ float from_ordered_bits(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
-// fs[0] = E (bound on |σ²_1 − σ²_3|), fs[1] (as uint) = ordered bits of the best lower bound, reset here
-__global__ void __launch_bounds__(1024) calib_kernel(const float* __restrict__ v1, const float* __restrict__ v3, int n, float* __restrict__ fs) {
-  __shared__ float red[1024];
-  float m = 0.f;
-  for (int i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(v1[i] - v3[i]));
+// Calibration of the ranking pass on STRATIFIED rows: row i·M/n of the grid, i < n (n = one wave of the variance kernel, or all
+// rows of a small grid), so a sorted / clustered / blocked candidate order is sampled across its whole extent.  Those rows went
+// through the FP64 K* kernel and the three-product contraction (var3, mu3); v1 / mu1 are the ranking pass's values of the whole grid.
+// fs[0] = E (bound on |σ̃² − σ²|), fs[1] (as uint) = ordered bits of the best lower bound (reset here), fs[2] = raw max |dσ²|,
+// fs[3] = Eμ (bound on |μ̃ − μ|, normalised units), fs[4] = raw max |dμ|.
+__global__ void cal_index_kernel(int* __restrict__ list, int n, int64_t M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) list[i] = (int)(((int64_t)i * M) / n);
+}
+__global__ void __launch_bounds__(1024) calib_kernel(const float* __restrict__ v1, const float* __restrict__ v3, const float* __restrict__ mu1,
+                                                     const float* __restrict__ mu3, const int* __restrict__ list, int n, float* __restrict__ fs) {
+  __shared__ float red[1024], redm[1024];
+  float m = 0.f, mm = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const int g = list[i];
+    m = fmaxf(m, fabsf(v1[g] - v3[i]));
+    mm = fmaxf(mm, fabsf(mu1[g] - mu3[i]));
+  }
   red[threadIdx.x] = m;
+  redm[threadIdx.x] = mm;
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    if (threadIdx.x < o) {
+      red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+      redm[threadIdx.x] = fmaxf(redm[threadIdx.x], redm[threadIdx.x + o]);
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     fs[0] = 8.f * red[0] + 1e-6f;
     fs[2] = red[0];
+    fs[3] = 8.f * redm[0] + 1e-7f;
+    fs[4] = redm[0];
     ((unsigned*)fs)[1] = 0u;   // below every ordered value
   }
+}
+// Bounds of the acquisition value over the box (μ ± Eμ) × (σ² ± E): all three kinds fall with μ; EI and LCB grow with σ, PI is
+// monotone in σ either way — so the corners bound the value.
+__device__ __forceinline__ void acq_bounds_f32(int acq, float mu, float var, float E, float Em, float ym, float ys, float yo, float x, float kp,
+                                               float* lb, float* ub) {
+  const float vlo = fmaxf(var - E, 0.f), vhi = var + E;
+  const float u0 = acq_any_f32(acq, mu - Em, vlo, ym, ys, yo, x, kp), u1 = acq_any_f32(acq, mu - Em, vhi, ym, ys, yo, x, kp);
+  const float l0 = acq_any_f32(acq, mu + Em, vlo, ym, ys, yo, x, kp), l1 = acq_any_f32(acq, mu + Em, vhi, ym, ys, yo, x, kp);
+  *ub = fmaxf(u0, u1);
+  *lb = fminf(l0, l1);
 }
 __global__ void __launch_bounds__(256)
 bound_max_kernel(const float* __restrict__ mun, const float* __restrict__ varn, int64_t M, int acq, const double* __restrict__ scal, double xi,
                  double kappa, float* __restrict__ fs) {
   const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
-  const float E = fs[0];
+  const float E = fs[0], Em = fs[3];
   float best = -INFINITY;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256) {
-    const float lo = acq_any_f32(acq, mun[i], fmaxf(varn[i] - E, 0.f), ym, ys, yo, x, kp);
-    const float hi = acq_any_f32(acq, mun[i], varn[i] + E, ym, ys, yo, x, kp);
-    const float lb = fminf(lo, hi);
+    float lb, ub;
+    acq_bounds_f32(acq, mun[i], varn[i], E, Em, ym, ys, yo, x, kp, &lb, &ub);
     if (lb > best) best = lb;   // NaN never enters
   }
 #pragma unroll
@@ -827,13 +870,13 @@ __global__ void __launch_bounds__(256)
 survivor_kernel(const float* __restrict__ mun, const float* __restrict__ varn, int64_t M, int acq, const double* __restrict__ scal, double xi,
                 double kappa, const float* __restrict__ fs, int* __restrict__ list, int* __restrict__ count) {
   const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
-  const float E = fs[0];
-  const float lb = from_ordered_bits(((const unsigned*)fs)[1]);
-  const float thr = lb - 1e-5f * fmaxf(1.f, fabsf(lb));   // fp32 evaluation and fp32 storage of μ
+  const float E = fs[0], Em = fs[3];
+  const float lbmax = from_ordered_bits(((const unsigned*)fs)[1]);
+  const float thr = lbmax - 1e-5f * fmaxf(1.f, fabsf(lbmax));   // fp32 evaluation and fp32 storage of μ
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256) {
-    const float lo = acq_any_f32(acq, mun[i], fmaxf(varn[i] - E, 0.f), ym, ys, yo, x, kp);
-    const float hi = acq_any_f32(acq, mun[i], varn[i] + E, ym, ys, yo, x, kp);
-    if (fmaxf(lo, hi) >= thr) {
+    float lb, ub;
+    acq_bounds_f32(acq, mun[i], varn[i], E, Em, ym, ys, yo, x, kp, &lb, &ub);
+    if (ub >= thr) {
       const int slot = atomicAdd(count, 1);
       if (slot < KBO_REFINE_CAP) list[slot] = (int)i;
     }
@@ -849,25 +892,61 @@ static int fast_pick(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int
   int* count = list + KBO_REFINE_CAP;
   float* fs = (float*)(count + 4);
   KBO_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int), s));
-  calib_kernel<<<1, 1024, 0, s>>>((const float*)h->varn.p, (const float*)h->var_cal.p, cal_n, fs);
+  calib_kernel<<<1, 1024, 0, s>>>((const float*)h->varn.p, (const float*)h->var_cal.p, (const float*)h->mun.p, (const float*)h->cal_mu.p,
+                                  (const int*)h->cal_idx.p, cal_n, fs);
   KBO_LAUNCH_CHECK(h);
   bound_max_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs);
   KBO_LAUNCH_CHECK(h);
   survivor_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs,
                                                  list, count);
   KBO_LAUNCH_CHECK(h);
-  struct { int n; int pad[3]; float fs[4]; } host;
+  struct { int n; int pad[3]; float fs[8]; } host;
   KBO_CUDA(h, cudaMemcpyAsync(&host, count, sizeof host, cudaMemcpyDeviceToHost, s));
   KBO_CUDA(h, cudaStreamSynchronize(s));
   h->last_contenders = host.n;
   h->last_rank_err = host.fs[2];
+  h->last_rank_mu_err = host.fs[4];
   *overflow = (host.n < 1 || host.n > KBO_REFINE_CAP) ? 1 : 0;
   if (*overflow) return KBO_OK;
+  h->last_unrefined = 0;
   return refine_evaluate(h, Xc, xc_dtype, host.n, list, count, goff, best_dev, s);
+}
+
+// The stratified calibration rows of a ranking sweep through the FP64 K* kernel and the three-product contraction:
+// cal_idx (row indices), cal_mu (normalised mean), var_cal (normalised variance).  Uses the K* scratch planes, so it runs
+// before the first chunk.
+static int calibration_rows(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int* cal_n_out, cudaStream_t s) {
+  int64_t want = (int64_t)h->sm_count * 128;
+  const int cal_n = (int)(M < want ? M : want);
+  const int64_t cal_pad = round_up64(cal_n, 128);
+  KBO_TRY(kbo_reserve(h, h->cal_idx, sizeof(int) * (size_t)cal_pad));
+  KBO_TRY(kbo_reserve(h, h->cal_x, sizeof(double) * (size_t)cal_pad * h->D));
+  KBO_TRY(kbo_reserve(h, h->cal_mu, sizeof(float) * (size_t)cal_pad));
+  KBO_TRY(kbo_reserve(h, h->var_cal, sizeof(float) * (size_t)cal_pad));
+  cal_index_kernel<<<(cal_n + 255) / 256, 256, 0, s>>>((int*)h->cal_idx.p, cal_n, M);
+  KBO_LAUNCH_CHECK(h);
+  if (xc_dtype == KBO_F64)
+    gather_rows_kernel<double><<<cal_n, 64, 0, s>>>((const double*)Xc, h->D, (const int*)h->cal_idx.p, cal_n, (double*)h->cal_x.p);
+  else
+    gather_rows_kernel<float><<<cal_n, 64, 0, s>>>((const float*)Xc, h->D, (const int*)h->cal_idx.p, cal_n, (double*)h->cal_x.p);
+  KBO_LAUNCH_CHECK(h);
+  KBO_TRY((launch_cross<double, float, 1>(h, (const double*)h->cal_x.p, cal_n, cal_pad, nullptr, 0, (__half*)h->Ksh.p, (__half*)h->Ksl.p,
+                                          (float*)h->cal_mu.p, s)));
+  KBO_TRY(kbo_i_tc_variance(h, (const __half*)h->Ksh.p, (const __half*)h->Ksl.p, cal_pad, (const __half*)h->Wh.p, (const __half*)h->Wl.p, h->Npad,
+                            0.0, h->prm.amplitude, (float*)h->var_cal.p, h->prm.tc_k_span, s, 3));
+  *cal_n_out = cal_n;
+  return KBO_OK;
 }
 
 static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out, double* acq_out,
                       kbo_best* best_dev, cudaStream_t s, bool force_three);
+
+int kbo_i_debug_cross_planes(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, cudaStream_t s) {
+  const int64_t rows_pad = round_up64(M, 128);
+  if (xc_dtype == KBO_F64)
+    return launch_cross<double, float, 1>(h, (const double*)Xc, M, rows_pad, nullptr, 0, (__half*)h->Ksh.p, (__half*)h->Ksl.p, (float*)h->mun.p, s);
+  return launch_cross<float, float, 1>(h, (const float*)Xc, M, rows_pad, nullptr, 0, (__half*)h->Ksh.p, (__half*)h->Ksl.p, (float*)h->mun.p, s);
+}
 
 int kbo_i_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out, double* acq_out,
                 kbo_best* best_dev, cudaStream_t s) {
@@ -888,20 +967,34 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
   const double* scal = (const double*)h->scal.p;
   // array-free tensor-core sweeps rank with one fp16 product and let the FP64 refinement decide (fast_pick above)
   const bool fast = tc && !force_three && h->tc_fast && h->tc_refine && h->tc_pair && !mu_out && !std_out && !acq_out && M < 0x7fffffff;
+  // ... and, by default, build that pass's K̃* on the tensor cores and contract it with cta_group::2 MMAs (tc_kstar.cu, tc_rank.cu)
+  const bool rank_tc = fast && h->rank_tc && h->ks_ready;
   int cal_n = 0;
   int64_t chunk;
   if (tc) {
-    // wave-aligned chunks: the variance kernel runs one 128-row CTA per SM, the K* kernel two — a chunk that is a multiple
-    // of sm_count·128 rows leaves no partial wave (512 CTAs on 148 SMs idled 13 % of the tensor time; profiles/README.md)
     const int64_t wave = (int64_t)h->sm_count * 128;
-    chunk = (int64_t)(h->scratch_limit / ((size_t)Npad * 4));
-    chunk = chunk >= wave ? chunk / wave * wave : chunk / 128 * 128;
-    if (chunk < 128) chunk = 128;
-    if (chunk > round_up64(M, 128)) chunk = round_up64(M, 128);
-    KBO_TRY(kbo_reserve(h, h->Ksh, sizeof(__half) * (size_t)chunk * Npad));
-    KBO_TRY(kbo_reserve(h, h->Ksl, sizeof(__half) * (size_t)chunk * Npad));
-    KBO_TRY(kbo_reserve(h, h->mun, sizeof(float) * (size_t)round_up64(M, 128)));
-    KBO_TRY(kbo_reserve(h, h->varn, sizeof(float) * (size_t)round_up64(M, 128)));
+    const int64_t cal_pad = fast ? round_up64(M < wave ? M : wave, 128) : 0;
+    if (rank_tc) {
+      // one fp16 plane per chunk; the ranking kernel deals (256-row group, tile pair) items, so any multiple of 256 rows will do
+      chunk = (int64_t)(h->scratch_limit / ((size_t)Npad * 2)) / 256 * 256;
+      if (chunk < 256) chunk = 256;
+      if (chunk > round_up64(M, 256)) chunk = round_up64(M, 256);
+      const int64_t rows_sh = chunk > cal_pad ? chunk : cal_pad;
+      KBO_TRY(kbo_reserve(h, h->Ksh, sizeof(__half) * (size_t)rows_sh * Npad));
+      KBO_TRY(kbo_reserve(h, h->Ksl, sizeof(__half) * (size_t)cal_pad * Npad));   // the lo plane exists for the calibration rows only
+    } else {
+      // wave-aligned chunks: the variance kernel runs one 128-row CTA per SM, the K* kernel two — a chunk that is a multiple
+      // of sm_count·128 rows leaves no partial wave (512 CTAs on 148 SMs idled 13 % of the tensor time; profiles/README.md)
+      chunk = (int64_t)(h->scratch_limit / ((size_t)Npad * 4));
+      chunk = chunk >= wave ? chunk / wave * wave : chunk / 128 * 128;
+      if (chunk < 128) chunk = 128;
+      if (chunk > round_up64(M, 128)) chunk = round_up64(M, 128);
+      const int64_t rows_sh = chunk > cal_pad ? chunk : cal_pad;
+      KBO_TRY(kbo_reserve(h, h->Ksh, sizeof(__half) * (size_t)rows_sh * Npad));
+      KBO_TRY(kbo_reserve(h, h->Ksl, sizeof(__half) * (size_t)rows_sh * Npad));
+    }
+    KBO_TRY(kbo_reserve(h, h->mun, sizeof(float) * (size_t)(round_up64(M, 256) + 256)));
+    KBO_TRY(kbo_reserve(h, h->varn, sizeof(float) * (size_t)(round_up64(M, 256) + 256)));
   } else {
     chunk = (int64_t)(h->scratch_limit / ((size_t)ld * 8)) / 64 * 64;
     if (chunk < 64) chunk = 64;
@@ -912,11 +1005,28 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
     KBO_TRY(kbo_reserve(h, h->varn, sizeof(double) * (size_t)M));
   }
   h->tim.chunks = 0;
+  if (fast) {   // the calibration rows borrow the K* scratch, so they go first
+    KBO_TIME_BEGIN(ev_cal, ev_cal_used);
+    KBO_TRY(calibration_rows(h, Xc, xc_dtype, M, &cal_n, s));
+    KBO_TIME_END();
+  }
   for (int64_t c0 = 0; c0 < M; c0 += chunk) {
     const int64_t rows = (M - c0 < chunk) ? (M - c0) : chunk;
     const unsigned char* xc = (const unsigned char*)Xc + (size_t)c0 * D * esz;
     h->tim.chunks++;
-    if (tc) {
+    if (rank_tc) {
+      {
+        KBO_TIME_BEGIN(ev_cross, ev_cross_used);
+        KBO_TRY(kbo_i_tc_kstar(h, xc, xc_dtype, rows, (__half*)h->Ksh.p, (float*)h->mun.p + c0, s));
+        KBO_TIME_END();
+      }
+      {
+        KBO_TIME_BEGIN(ev_var, ev_var_used);
+        KBO_TRY(kbo_i_tc_rank(h, (const __half*)h->Ksh.p, round_up64(rows, 256), (const __half*)h->Wh.p, Npad, h->prm.amplitude,
+                              (float*)h->varn.p + c0, s));
+        KBO_TIME_END();
+      }
+    } else if (tc) {
       const int64_t rows_pad = round_up64(rows, 128);
       float* mun = (float*)h->mun.p + c0;
       {
@@ -931,14 +1041,6 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
         KBO_TIME_BEGIN(ev_var, ev_var_used);
         KBO_TRY(kbo_i_tc_variance(h, (const __half*)h->Ksh.p, (const __half*)h->Ksl.p, rows_pad, (const __half*)h->Wh.p, (const __half*)h->Wl.p,
                                   Npad, 0.0, h->prm.amplitude, (float*)h->varn.p + c0, fast ? 1024 : h->prm.tc_k_span, s, fast ? 1 : 3));
-        if (fast && c0 == 0) {   // calibration rows: the same first wave again with all three products
-          int64_t cal_rows = (int64_t)h->sm_count * 128;
-          if (cal_rows > rows_pad) cal_rows = rows_pad;
-          cal_n = (int)(cal_rows < rows ? cal_rows : rows);
-          KBO_TRY(kbo_reserve(h, h->var_cal, sizeof(float) * (size_t)cal_rows));
-          KBO_TRY(kbo_i_tc_variance(h, (const __half*)h->Ksh.p, (const __half*)h->Ksl.p, cal_rows, (const __half*)h->Wh.p, (const __half*)h->Wl.p,
-                                    Npad, 0.0, h->prm.amplitude, (float*)h->var_cal.p, h->prm.tc_k_span, s, 3));
-        }
         KBO_TIME_END();
       }
     } else {
@@ -977,10 +1079,13 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
     if (tc) {
       KBO_TRY(launch_acq<float>(h, (const float*)h->mun.p, (const float*)h->varn.p, M, goff, h->prm.acq, 0.0, 1.0, 0.0, scal, h->prm.xi,
                                 h->prm.kappa, mu_out, std_out, acq_out, nullptr, best_dev, s));
+      h->last_unrefined = 2;
       if (h->tc_refine && M < 0x7fffffff) KBO_TRY(refine_suggestion(h, Xc, xc_dtype, M, goff, best_dev, s));
-    } else
+    } else {
+      h->last_unrefined = 0;
       KBO_TRY(launch_acq<double>(h, (const double*)h->mun.p, (const double*)h->varn.p, M, goff, h->prm.acq, 0.0, 1.0, 0.0, scal, h->prm.xi,
                                  h->prm.kappa, mu_out, std_out, acq_out, nullptr, best_dev, s));
+    }
     KBO_TIME_END();
   }
   return KBO_OK;

@@ -28,7 +28,8 @@ class GPEngine:
     def __init__(self, device: int = 0, *, kernel: str = "matern52", length_scale=1.0, amplitude: float = 1.0,
                  noise: float = 1e-10, acq: str = "ei", xi: float = 0.01, kappa: float = 1.96,
                  normalize_y: bool = True, var_mode: str = "auto", tc_k_span: int = 0, scratch_limit: int | None = None,
-                 tc_pair: bool | None = None, tc_refine: bool | None = None, tc_fast: bool | None = None):
+                 tc_pair: bool | None = None, tc_refine: bool | None = None, tc_fast: bool | None = None,
+                 rank_tc: bool | None = None):
         if kernel not in L.KERNELS:
             raise ValueError(f"kernel must be one of {sorted(L.KERNELS)}, got {kernel!r}")
         if acq not in L.ACQS:
@@ -56,6 +57,8 @@ class GPEngine:
             L.check(self.lib, self._h, self.lib.kbo_set_tc_refine(self._h, int(bool(tc_refine))))
         if tc_fast is not None:
             L.check(self.lib, self._h, self.lib.kbo_set_tc_fast(self._h, int(bool(tc_fast))))
+        if rank_tc is not None:
+            L.check(self.lib, self._h, self.lib.kbo_set_rank_tc(self._h, int(bool(rank_tc))))
         self._best_dev = torch.empty(4, dtype=torch.float64, device=f"cuda:{self.device}")
 
     # -- plumbing ----------------------------------------------------------------------------------
@@ -154,6 +157,35 @@ class GPEngine:
     def last_rank_error(self) -> float:
         """Largest |σ²(1 product) − σ²(3 products)| on the calibration rows of the last one-product sweep (kbo_set_tc_fast)."""
         return float(self.lib.kbo_last_rank_error(self._h))
+
+    def last_rank_mu_error(self) -> float:
+        """Largest |mean(ranking pass) − mean(FP64 K* kernel)| on the calibration rows of the last ranking sweep (normalised y)."""
+        return float(self.lib.kbo_last_rank_mu_error(self._h))
+
+    def last_unrefined(self) -> int:
+        """0: the last tensor-core suggestion was decided in FP64 among every candidate that could be the maximum;
+        1: among the best 4096 by fp32 value (window overflow); 2: not refined (exact ties beyond the cap / refinement off)."""
+        return int(self.lib.kbo_last_unrefined(self._h))
+
+    def rank_pass(self, Xc, mode: int, want_plane: bool = False):
+        """Test hook: the ranking pass alone (mode 0: FP64 K* + one-product cluster kernel, 1: tensor-core K* + cta_group::2
+        kernel) -> normalised mean, normalised variance (float32 CUDA tensors) and optionally the fp16 K* hi plane."""
+        dev = f"cuda:{self.device}"
+        if not isinstance(Xc, torch.Tensor):
+            Xc = torch.as_tensor(np.ascontiguousarray(Xc), device=dev)
+        Xc = Xc.contiguous()
+        dt = L.KBO_F64 if Xc.dtype == torch.float64 else L.KBO_F32
+        M = Xc.shape[0]
+        npad = (self.N + 255) // 256 * 256
+        mu = torch.empty(M, dtype=torch.float32, device=dev)
+        var = torch.empty(M, dtype=torch.float32, device=dev)
+        plane = torch.empty((M, npad), dtype=torch.float16, device=dev) if want_plane else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.kbo_debug_rank_pass(self._h, Xc.data_ptr(), dt, int(M), int(mode), mu.data_ptr(), var.data_ptr(),
+                                              plane.data_ptr() if want_plane else None, self._stream())
+            L.check(self.lib, self._h, rc)
+            torch.cuda.current_stream(self.device).synchronize()
+        return mu, var, plane
 
     def lml_grad(self):
         """(lml, grad) of the last tell; grad w.r.t. (log amplitude, log noise, log ℓ_1..ℓ_P) as a NumPy array."""

@@ -26,10 +26,10 @@ def test_library_exports_every_header_symbol():
 
 
 def test_struct_layouts_match_header():
-    # sizes the C side uses (kbo_params: 4*i32 + 4*f64 + ptr + 2*i32 = 64; kbo_best 32; kbo_timings 40)
+    # sizes the C side uses (kbo_params: 4*i32 + 4*f64 + ptr + 2*i32 = 64; kbo_best 32; kbo_timings 44)
     assert ctypes.sizeof(_lib.KboParams) == 64
     assert ctypes.sizeof(_lib.KboBest) == 32
-    assert ctypes.sizeof(_lib.KboTimings) == 40
+    assert ctypes.sizeof(_lib.KboTimings) == 44
 
 
 def test_create_fails_loudly_without_gpu():

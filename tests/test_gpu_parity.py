@@ -616,3 +616,154 @@ def test_rebase_then_append_across_a_256_boundary_in_tc_mode():
     assert b2.index == r2.index and abs(b2.value - r2.value) <= 1e-9
     _check_argmax(b2, O.suggest(X, y, Xc, kind="matern52", acq="ei", **th)["acq"], TOL_F64)
     eng.close(); ref.close()
+
+
+# ---- round 2: tensor-core K* generation + cta_group::2 ranking kernel --------------------------------------------------------
+@pytest.mark.parametrize("N,M,D,kind", [(1000, 700, 7, "matern52"), (2048, 1500, 32, "matern52"), (777, 300, 5, "rbf"), (1300, 513, 100, "matern52"),
+                                        (300, 256, 40, "rbf")])
+def test_tensor_core_kstar_plane_and_mean_against_fp64_kernel(N, M, D, kind):
+    """tc_kstar.cu: K̃* from tcgen05 dot products + fp32 kernel evaluation vs the FP64 K* kernel of the same fit.  The fp16 hi
+    planes may differ by one fp16 ulp where the fp32 value falls on the other side of a rounding boundary, nowhere by more;
+    padding columns are zero; the on-the-fly mean agrees to the fp32 evaluation error times |alpha|."""
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    eng = _engine(dict(kind=kind, acq="ei", **th), "tc"); eng.tell(X, y)
+    xc = torch.tensor(Xc.astype(np.float32), device="cuda")
+    mu0, v0, p0 = eng.rank_pass(xc, 0, want_plane=True)
+    mu1, v1, p1 = eng.rank_pass(xc, 1, want_plane=True)
+    p0, p1 = p0.float().cpu().numpy(), p1.float().cpu().numpy()
+    assert np.all(p1[:, N:] == 0) and np.all(p0[:, N:] == 0)
+    Kref = O.kernel_matrix(Xc.astype(np.float32).astype(np.float64), X, th["length_scale"], kind, th["amplitude"])
+    ulp = np.maximum(np.abs(Kref), 2.0 ** -14) * 2.0 ** -10       # one fp16 ulp at the value's magnitude (normal range)
+    d = np.abs(p1[:, :N] - p0[:, :N])
+    assert np.all(d <= 1.01 * ulp), f"max plane difference {np.max(d / ulp):.2f} ulp"
+    frac = float(np.mean(d > 0))
+    assert frac < 0.02, f"{frac:.4f} of the entries round differently"
+    assert np.all(np.abs(p1[:, :N] - Kref) <= 0.51 * ulp + 2e-6)
+    fit = O.gp_fit(X, y, kind=kind, **{k: th[k] for k in ("length_scale", "amplitude", "noise")})
+    a1 = float(np.abs(fit["alpha"]).sum())
+    dm = np.abs(mu1.cpu().numpy() - mu0.cpu().numpy()).max()
+    print(f"\nN={N} M={M} D={D} {kind}: plane entries differing {frac:.2e}, max|d mu_n|={dm:.3e} (|alpha|_1={a1:.3e}), "
+          f"max|d var_n|={np.abs(v1.cpu().numpy() - v0.cpu().numpy()).max():.3e}")
+    assert dm <= 2e-6 * a1 + 1e-6
+    # both ranking passes against the oracle's normalised posterior: the hi-plane-only contraction is a RANKING value
+    mu_ref, std_ref = O.gp_predict(fit, Xc.astype(np.float32).astype(np.float64))
+    var_ref = (std_ref / fit["y_std"]) ** 2
+    for v in (v0, v1):
+        assert np.abs(v.cpu().numpy() - var_ref).max() < 5e-2
+    assert np.abs(v1.cpu().numpy() - v0.cpu().numpy()).max() < 1e-2
+    np.testing.assert_allclose(mu1.cpu().numpy(), (mu_ref - fit["y_mean"]) / fit["y_std"], rtol=0, atol=2e-6 * a1 + 1e-5)
+    eng.close()
+
+
+@pytest.mark.parametrize("N,M,D,kind,acq", [(1024, 50000, 8, "rbf", "ei"), (2048, 30000, 32, "matern52", "ei"), (1500, 20000, 6, "matern52", "lcb"),
+                                            (1200, 20000, 5, "rbf", "pi"), (1100, 9000, 70, "matern52", "ei")])
+def test_tensor_core_ranking_pass_returns_the_fp64_suggestion(N, M, D, kind, acq):
+    """The product path (tensor-core K*, cta_group::2 ranking kernel, stratified calibration with a mean bound, FP64 decision)
+    returns the same suggestion as the round-1 ranking pass (FP64 K*), the three-product sweep and the FP64 engine."""
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    kw = dict(kind=kind, acq=acq, **th)
+    new = _engine(kw, "tc"); new.tell(X, y)
+    old = _engine(kw, "tc", rank_tc=False); old.tell(X, y)
+    slow = _engine(kw, "tc", tc_fast=False); slow.tell(X, y)
+    e64 = _engine(kw, "f64"); e64.tell(X, y)
+    bn, bo, bs, b6 = new.ask(Xc), old.ask(Xc), slow.ask(Xc), e64.ask(Xc)
+    assert (bn.index, bn.value, bn.mu, bn.std) == (bo.index, bo.value, bo.mu, bo.std) == (bs.index, bs.value, bs.mu, bs.std)
+    assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value))
+    assert new.last_unrefined() == 0 and 1 <= new.last_contenders() <= 4096
+    assert 0 < new.last_rank_mu_error() < 1e-2 and old.last_rank_mu_error() == 0.0
+    print(f"\nN={N} M={M} D={D} {kind}/{acq}: survivors new {new.last_contenders()} old {old.last_contenders()}, "
+          f"rank err var {new.last_rank_error():.2e} / {old.last_rank_error():.2e}, mu {new.last_rank_mu_error():.2e}")
+    parts = [new.ask(Xc[s:s + 7000], global_offset=s) for s in range(0, M, 7000)]
+    win = max(parts, key=lambda b: (b.value, -b.index))
+    assert (win.index, win.value) == (bn.index, bn.value)
+    for e in (new, old, slow, e64):
+        e.close()
+
+
+def _adversarial_grids(X, y, Xc):
+    """Candidate orders that a first-wave calibration would not represent: sorted by distance to the incumbent, half of the
+    rows duplicated (each duplicate right after its original), and a block-structured grid (discrete parameters)."""
+    inc = X[int(np.argmin(y))]
+    order = np.argsort(((Xc - inc) ** 2).sum(1))
+    yield "sorted-near-first", Xc[order]
+    yield "sorted-far-first", Xc[order[::-1]]
+    half = Xc[: len(Xc) // 2]
+    yield "half-duplicated", np.repeat(half, 2, axis=0)
+    disc = Xc.copy()
+    disc[:, : Xc.shape[1] // 2] = np.round(disc[:, : Xc.shape[1] // 2] * 3) / 3
+    yield "discrete-blocks", disc[np.lexsort(disc[:, : Xc.shape[1] // 2].T[::-1])]
+
+
+def test_ranking_pass_on_non_exchangeable_candidate_orders():
+    """Stratified calibration: on sorted, duplicated and block-structured grids the ranking pass (both variants) returns
+    bit for bit what the three-product sweep and the FP64 engine return."""
+    N, M, D = 2048, 60000, 16
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    kw = dict(kind="matern52", acq="ei", **th)
+    new = _engine(kw, "tc"); new.tell(X, y)
+    old = _engine(kw, "tc", rank_tc=False); old.tell(X, y)
+    slow = _engine(kw, "tc", tc_fast=False); slow.tell(X, y)
+    e64 = _engine(kw, "f64"); e64.tell(X, y)
+    for name, G in _adversarial_grids(X, y, Xc):
+        bn, bo, bs, b6 = new.ask(G), old.ask(G), slow.ask(G), e64.ask(G)
+        assert (bn.index, bn.value) == (bo.index, bo.value) == (bs.index, bs.value), name
+        assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value)), name
+        print(f"\n{name}: index {bn.index} survivors {new.last_contenders()} rank err {new.last_rank_error():.2e} mu {new.last_rank_mu_error():.2e}")
+    for e in (new, old, slow, e64):
+        e.close()
+
+
+def test_ranking_pass_on_a_flat_landscape_falls_back_and_still_decides_in_fp64():
+    """A near-flat EI landscape (tiny candidate cube far from the data: every candidate within the ranking error of the best):
+    more than 4096 survive, the sweep is redone with three products, whose own window overflows too and is narrowed — the
+    suggestion is still the FP64 engine's and the caller can see how it was decided."""
+    N, M, D = 1024, 30000, 6
+    X, y, _ = O.synthetic(N, 10, D)
+    th = O.theta_of_record(D)
+    r = np.random.default_rng(5)
+    G = 0.5 + 1e-4 * (r.random((M, D)) - 0.5)
+    kw = dict(kind="matern52", acq="ei", **th)
+    new = _engine(kw, "tc"); new.tell(X, y)
+    e64 = _engine(kw, "f64"); e64.tell(X, y)
+    bn, b6 = new.ask(G), e64.ask(G)
+    assert new.last_contenders() > 4096 and new.last_unrefined() in (1, 2)
+    ref = O.suggest(X, y, G, kind="matern52", acq="ei", **th)
+    assert abs(bn.value - ref["value"]) <= TOL_TC
+    assert bn.index == b6.index or abs(ref["acq"][bn.index] - ref["value"]) <= TOL_TC
+    new.close(); e64.close()
+
+
+def test_cfg3_full_size_path_of_record():
+    """BASELINE.json config 3 at full size through the path the bench times (array-free tensor-core sweep): N=8192, D=32,
+    M=1,048,576, Matérn-5/2, EI.  The suggestion must be the FP64 engine's (same index, value to rounding) and the oracle's
+    value on the winner row and on a 4096-row sample must agree to 1e-5 with the winner dominating the sample."""
+    N, M, D = 8192, 1_048_576, 32
+    X, y, _ = O.synthetic(N, 1, D)
+    Xc = np.random.default_rng(4321).random((M, D)).astype(np.float32)
+    th = O.theta_of_record(D)
+    kw = dict(kind="matern52", acq="ei", **th)
+    xc = torch.tensor(Xc, device="cuda")
+    new = _engine(kw, "tc"); new.tell(X, y)
+    bn = new.ask(xc)
+    surv, rerr, merr = new.last_contenders(), new.last_rank_error(), new.last_rank_mu_error()
+    assert new.last_unrefined() == 0
+    old = _engine(kw, "tc", rank_tc=False); old.tell(X, y)
+    bo = old.ask(xc)
+    old.close()
+    e64 = _engine(kw, "f64"); e64.tell(X, y)
+    b6 = e64.ask(xc)
+    e64.close()
+    assert (bn.index, bn.value) == (bo.index, bo.value)
+    assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-10 * max(1.0, abs(b6.value))
+    sample = np.concatenate([[bn.index], np.random.default_rng(9).choice(M, 4096, replace=False)])
+    fit = O.gp_fit(X, y, kind="matern52", **{k: th[k] for k in ("length_scale", "amplitude", "noise")})
+    mu, std = O.gp_predict(fit, Xc[sample].astype(np.float64))
+    a = O.acquisition(mu, std, float(y.min()), "ei", th["xi"], th["kappa"])
+    print(f"\ncfg3 full size: index {bn.index} value {bn.value:.10f} oracle {a[0]:.10f} |d|={abs(bn.value - a[0]):.2e} survivors {surv} "
+          f"rank err var {rerr:.2e} mu {merr:.2e} next best of sample {np.max(a[1:]):.4f}")
+    assert abs(bn.value - a[0]) <= TOL_TC
+    assert a[0] >= np.max(a[1:])
+    new.close()
