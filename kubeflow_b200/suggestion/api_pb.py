@@ -159,3 +159,6 @@ UNKNOWN_TYPE, DOUBLE, INT, DISCRETE, CATEGORICAL = range(5)
 UNKNOWN, MINIMIZE, MAXIMIZE = range(3)
 SUCCEEDED = TRIAL_CONDITIONS.index("SUCCEEDED")
 EARLYSTOPPED = TRIAL_CONDITIONS.index("EARLYSTOPPED")
+FAILED = TRIAL_CONDITIONS.index("FAILED")
+KILLED = TRIAL_CONDITIONS.index("KILLED")
+METRICSUNAVAILABLE = TRIAL_CONDITIONS.index("METRICSUNAVAILABLE")

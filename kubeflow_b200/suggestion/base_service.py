@@ -39,9 +39,9 @@ class BaseSkoptService:
 
     def getSuggestions(self, trials, current_request_number):
         """trials: internal.Trial list (all completed trials, resent every call); returns a list of Assignment lists."""
-        skopt_suggested, loss_for_skopt = [], []
+        skopt_suggested, loss_for_skopt, new_names = [], [], []
         for trial in trials:
-            if trial.name in self.told_trials:
+            if trial.name in self.told_trials or trial.name in new_names:
                 continue
             row = []
             by_name = {a.name: a.value for a in trial.assignments}
@@ -55,9 +55,10 @@ class BaseSkoptService:
                 loss = -1.0 * loss
             skopt_suggested.append(row)
             loss_for_skopt.append(loss)
-            self.told_trials.add(trial.name)
+            new_names.append(trial.name)
         if skopt_suggested:
             self.skopt_optimizer.tell(skopt_suggested, loss_for_skopt)
+            self.told_trials.update(new_names)   # only once tell() succeeded: a bad later trial must not mark earlier ones as told
         points = self.skopt_optimizer.ask(n_points=current_request_number)
         return [self.convert(self.search_space, p) for p in points]
 

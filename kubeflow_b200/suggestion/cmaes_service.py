@@ -3,9 +3,13 @@
 Search happens in the normalised cube [0,1]^D (reals and integers; categorical/discrete parameters are rejected, as
 goptuna's CMA sampler does), mean0 = 0.5, sigma0 = 1/6 unless ``sigma`` is set; samples are clipped to the cube.
 A generation's λ points are handed out across GetSuggestions calls; when all λ results are back the population is told
-and the next generation is sampled.  If the controller asks for more points than the generation has left, the extra
-points are independent draws from the current distribution (they do not enter the update), which is what goptuna's
-relative/independent sampling split amounts to.
+and the next generation is sampled.  Samples are tracked BY INDEX: two samples that round or clip to the same assignment
+strings (integer parameters, cube boundary) are two pending entries under one key, matched first-in first-out; a sample
+whose trial ended without an objective (FAILED / KILLED / METRICSUNAVAILABLE) goes back to the head of the queue and is
+handed out again — goptuna likewise keeps sampling the running generation until popsize trials are COMPLETE — so neither
+duplicates nor failures can stall the generation.  If the controller asks for more points than the generation has left,
+the extra points are independent draws from the current distribution (they do not enter the update), which is what
+goptuna's relative/independent sampling split amounts to.
 """
 from __future__ import annotations
 
@@ -13,6 +17,7 @@ import threading
 
 import numpy as np
 
+from . import api_pb as api
 from .internal import (CATEGORICAL, DISCRETE, DOUBLE, INTEGER, MAX_GOAL, AlgorithmSettingsError, Assignment,
                        HyperParameterSearchSpace, Trial, parse_settings)
 from .service import _Base, _reply_from
@@ -51,9 +56,10 @@ class _Experiment:
         self.es = CmaEs(np.full(D, 0.5), settings.get("sigma", 1.0 / 6.0), popsize=settings.get("popsize"),
                         seed=settings.get("random_state", 0), device=int(settings.get("device", 0)))
         self.queue = []          # [(sample index, assignments)] of the current generation not handed out yet
-        self.pending = {}        # key -> sample index
+        self.assign = {}         # sample index -> assignments of the current generation
+        self.pending = {}        # key -> [sample indices handed out, no result yet] (first in, first out)
         self.fitness = {}        # sample index -> value
-        self.seen = set()
+        self.seen = set()        # trial names already accounted for (finished with or without an objective)
         self.extra_rng = np.random.default_rng(settings.get("random_state", 0) + 7919)
 
 
@@ -94,7 +100,8 @@ class CmaesService(_Base):
     def _new_generation(self, st, ss):
         X = st.es.ask().cpu().numpy()
         st.queue = [(i, self._to_assignments(ss, X[i])) for i in range(X.shape[0])]
-        st.pending = {self._key(a): i for i, a in st.queue}
+        st.assign = {i: a for i, a in st.queue}
+        st.pending = {}
         st.fitness = {}
 
     def get_suggestions(self, request):
@@ -112,16 +119,29 @@ class CmaesService(_Base):
                 if t.name in st.seen:
                     continue
                 st.seen.add(t.name)
-                i = st.pending.get(self._key(t.assignments))
-                if i is not None and i not in st.fitness:
-                    st.fitness[i] = sign * float(t.target_metric.value)
+                waiting = st.pending.get(self._key(t.assignments))
+                if waiting:
+                    st.fitness[waiting.pop(0)] = sign * float(t.target_metric.value)
+            # trials that ended without an objective: their sample is handed out again
+            for t in request.trials:
+                # (a SUCCEEDED / EARLYSTOPPED trial still unseen here carried no objective metric: same treatment)
+                if t.name in st.seen or t.status.condition not in (api.FAILED, api.KILLED, api.METRICSUNAVAILABLE, api.SUCCEEDED,
+                                                                   api.EARLYSTOPPED):
+                    continue
+                st.seen.add(t.name)
+                waiting = st.pending.get(self._key(Assignment.convert(t.spec.parameter_assignments.assignments)))
+                if waiting:
+                    i = waiting.pop(0)
+                    st.queue.insert(0, (i, st.assign[i]))
             if len(st.fitness) == st.es.popsize:
                 st.es.tell(np.array([st.fitness[i] for i in range(st.es.popsize)]))
                 self._new_generation(st, ss)
             lists = []
             for _ in range(max(int(request.current_request_number), 0)):
                 if st.queue:
-                    lists.append(st.queue.pop(0)[1])
+                    i, a = st.queue.pop(0)
+                    st.pending.setdefault(self._key(a), []).append(i)
+                    lists.append(a)
                 else:   # generation exhausted but not finished: independent draw from the current distribution
                     s = st.es.state()
                     z = st.extra_rng.standard_normal(st.es.D)

@@ -146,13 +146,24 @@ class SkoptService(_Base):
         settings = validate_skopt_settings(parse_settings(exp))
         from .ingest import LazyRequest
         lazy = request if isinstance(request, LazyRequest) and request.scanned else None
+        # an experiment recreated under the same name, or whose search space / objective / settings changed, must not meet the
+        # old optimizer (old dimensions, old history, old settings): the cache entry is valid for one fingerprint only
+        fingerprint = (search_space.goal, exp.spec.objective.objective_metric_name,
+                       tuple((p.name, p.type, p.min, p.max, tuple(p.list), p.step) for p in search_space.params),
+                       tuple(sorted((k, repr(v)) for k, v in settings.items())))
         with self._lock:
             svc = self._services.get(exp.name)
+            if svc is not None and svc.fingerprint != fingerprint:
+                eng = getattr(self._services.pop(exp.name).skopt_optimizer, "_engine", None)
+                if eng is not None:
+                    eng.close()
+                svc = None
             if svc is None:
                 kw = dict(self.engine_defaults)
                 kw.update(settings)
                 from .base_service import BaseSkoptService
                 svc = BaseSkoptService(search_space=search_space, **kw)
+                svc.fingerprint = fingerprint
                 self._services[exp.name] = svc
                 while len(self._services) > self.max_experiments:       # evict the least recently used experiment's engine
                     old_name = next(iter(self._services))

@@ -198,7 +198,8 @@ def test_tc_variance_kernel_raw(rows, Npad, k_span, pair):
 @pytest.mark.parametrize("var_mode,tol", [("f64", 2e-7), ("tc", TOL_TC)])
 def test_multi_chunk_sweep_matches_oracle(var_mode, tol):
     """Force the candidate grid through several scratch chunks with a ragged tail (64 MiB scratch: 16 384-row chunks in tc
-    mode at Npad = 1024, 8 192-row chunks in f64 mode) and compare every candidate with the oracle."""
+    mode at Npad = 1024 — 32 768 for the ranking pass, which keeps one plane —, 8 192-row chunks in f64 mode) and compare every
+    candidate with the oracle."""
     N, M, D = 1000, 40_003, 6
     X, y, Xc = O.synthetic(N, M, D)
     th = O.theta_of_record(D)
@@ -211,7 +212,7 @@ def test_multi_chunk_sweep_matches_oracle(var_mode, tol):
     assert err <= tol
     _check_argmax(best, ref["acq"], tol)
     b_host, t = eng.suggest_host(X, y, Xc)
-    assert t["chunks"] >= 3 and b_host.index == eng.ask(Xc).index
+    assert t["chunks"] >= 2 and b_host.index == eng.ask(Xc).index
     eng.close()
 
 

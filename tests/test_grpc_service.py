@@ -165,3 +165,102 @@ def test_sobol_is_low_discrepancy_and_resumes():
                                                                     current_request_number=64))
     Q = np.asarray([[float(a.value) for a in pa.assignments] for pa in one.parameter_assignments])
     np.testing.assert_allclose(P, Q, rtol=0, atol=1e-12)            # 16 + 16 + 32 == one call of 64
+
+
+# ---- service state hygiene (round-1 advisor findings) ----------------------------------------------------------------------------
+def test_skopt_service_rebuilds_the_optimizer_when_the_experiment_changes():
+    """The per-experiment cache is keyed by name AND a fingerprint of (space, objective, settings): an experiment recreated
+    under the same name with another space or other settings must not inherit the old optimizer's dimensions or history."""
+    svc = SkoptService()
+    exp = make_experiment("bayesianoptimization", {"n_initial_points": 50, "random_state": 1})
+    req = api.GetSuggestionsRequest(experiment=exp, current_request_number=1)
+    add_trial(req, "t0", {"x0": 0.05, "x1": 0.0, "x2": 15.0, "x3": 1.0}, 0.3)
+    svc.get_suggestions(req)
+    first = svc._services["exp-1"]
+    assert first.told_trials == {"t0"}
+    svc.get_suggestions(req)
+    assert svc._services["exp-1"] is first                       # unchanged experiment: same optimizer
+    exp2 = make_experiment("bayesianoptimization", {"n_initial_points": 50, "random_state": 1})
+    exp2.spec.parameter_specs.parameters[1].feasible_space.max = "3.0"      # same name, wider space
+    req2 = api.GetSuggestionsRequest(experiment=exp2, current_request_number=1)
+    rep = svc.get_suggestions(req2)
+    second = svc._services["exp-1"]
+    assert second is not first and second.told_trials == set()
+    assert float(second.search_space.params[1].max) == 3.0 and len(rep.parameter_assignments) == 1
+    exp3 = make_experiment("bayesianoptimization", {"n_initial_points": 50, "random_state": 2})   # other settings
+    svc.get_suggestions(api.GetSuggestionsRequest(experiment=exp3, current_request_number=1))
+    assert svc._services["exp-1"] is not second
+
+
+def test_trials_are_marked_told_only_after_tell_succeeded():
+    """A bad later trial (missing assignment) fails the request; the good earlier trial must not be left marked as told
+    without having been told — it would be skipped on every later request."""
+    svc = SkoptService()
+    exp = make_experiment("bayesianoptimization", {"n_initial_points": 50, "random_state": 1}, name="exp-told")
+    req = api.GetSuggestionsRequest(experiment=exp, current_request_number=1)
+    add_trial(req, "good", {"x0": 0.05, "x1": 0.0, "x2": 15.0, "x3": 1.0}, 0.3)
+    add_trial(req, "bad", {"x0": 0.05, "x1": 0.0, "x2": 15.0}, 0.4)           # x3 missing
+    with pytest.raises(ValueError):
+        svc.get_suggestions(req)
+    b = svc._services["exp-told"]
+    assert b.told_trials == set() and len(b.skopt_optimizer.yi) == 0
+    a = req.trials[1].spec.parameter_assignments.assignments.add()
+    a.name, a.value = "x3", "2.0"
+    svc.get_suggestions(req)
+    assert b.told_trials == {"good", "bad"} and len(b.skopt_optimizer.yi) == 2
+
+
+class _FakeEs:
+    """Stand-in for the GPU CMA-ES sampler (kubeflow_b200.cmaes.CmaEs): records tells, hands out fixed populations."""
+    def __init__(self, mean0, sigma0, popsize=None, seed=0, device=0):
+        self.D, self.popsize, self.told, self.gen = len(mean0), int(popsize or 4), [], 0
+
+    def ask(self):
+        class _T:
+            def __init__(self, a): self.a = a
+            def cpu(self): return self
+            def numpy(self): return self.a
+        self.gen += 1
+        # integer parameter x0 in [0, 3]: samples 0 and 1 round to the same value; sample 3 is clipped at the boundary
+        base = np.array([[0.34, 0.2], [0.36, 0.2], [0.9, 0.7], [1.4, 0.7]])
+        return _T(np.clip(base + 0.001 * self.gen, 0, 2))
+
+    def tell(self, f):
+        self.told.append(np.asarray(f).copy())
+
+    def state(self):
+        return {"mean": np.full(self.D, 0.5), "sigma": 0.1, "B": np.eye(self.D), "d": np.ones(self.D)}
+
+
+def test_cmaes_generation_survives_duplicate_assignments_and_failed_trials(monkeypatch):
+    import kubeflow_b200.cmaes as cm
+    from kubeflow_b200.suggestion.cmaes_service import CmaesService
+    monkeypatch.setattr(cm, "CmaEs", _FakeEs, raising=False)
+    svc = CmaesService()
+    e = api.Experiment()
+    e.name = "cma-dup"
+    e.spec.objective.type = api.MINIMIZE
+    e.spec.objective.objective_metric_name = "loss"
+    e.spec.algorithm.algorithm_name = "cmaes"
+    s = e.spec.algorithm.algorithm_settings.add(); s.name, s.value = "popsize", "4"
+    p = e.spec.parameter_specs.parameters.add(); p.name, p.parameter_type = "x0", api.INT
+    p.feasible_space.min, p.feasible_space.max = "0", "3"
+    p = e.spec.parameter_specs.parameters.add(); p.name, p.parameter_type = "x1", api.DOUBLE
+    p.feasible_space.min, p.feasible_space.max = "0", "1"
+    req = api.GetSuggestionsRequest(experiment=e, current_request_number=4)
+    rep = svc.get_suggestions(req)
+    pts = [{a.name: a.value for a in pa.assignments} for pa in rep.parameter_assignments]
+    assert pts[0] == pts[1]                                      # two samples, one assignment string
+    es = svc._exps["cma-dup"].es
+    # results: the duplicates both succeed, sample 2 FAILS, sample 3 succeeds
+    add_trial(req, "t0", pts[0], 1.0); add_trial(req, "t1", pts[1], 2.0)
+    add_trial(req, "t2", pts[2], 0.0, condition=api.FAILED); add_trial(req, "t3", pts[3], 4.0)
+    req.current_request_number = 1
+    rep = svc.get_suggestions(req)
+    again = {a.name: a.value for a in rep.parameter_assignments[0].assignments}
+    assert again == pts[2] and es.told == []                     # the failed sample is handed out again, nothing told yet
+    add_trial(req, "t4", again, 3.0)
+    rep = svc.get_suggestions(req)
+    # samples 2 and 3 share one assignment string too (boundary clip): results are matched to them first-in first-out
+    assert len(es.told) == 1 and es.told[0].tolist() == [1.0, 2.0, 4.0, 3.0]   # every sample counted once, by index
+    assert es.gen == 2 and len(rep.parameter_assignments) == 1
