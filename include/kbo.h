@@ -175,6 +175,20 @@ int kbo_sweep(kbo_handle* h, const void* Xc, int32_t xc_dtype, int64_t M, int64_
 /* synchronises `stream`, copies *best_dev to host, and returns KBO_ERR_NOT_PD if the fit failed. */
 int kbo_best_to_host(kbo_handle* h, const kbo_best* best_dev, kbo_best* best_host, void* stream);
 
+/* ---- multi-GPU: the grid shards by rows, one exchange step ---------------------------------------------
+ * One process (or thread) per GPU, one handle each.  Rank r sweeps rows [lo_r, hi_r) of the grid with global_offset = lo_r;
+ * kbo_allreduce_argmax then replaces *best_dev on every rank by the global first-index argmax (maximum value, lowest global
+ * index among equals = np.argmin(-values) over the concatenated grid): ONE ncclAllGather of 32 bytes per rank on `stream`
+ * plus a one-thread reduce.  NCCL is bound at run time (dlopen libnccl.so.2): kbo_comm_unique_id on one rank gives the
+ * 128-byte ncclUniqueId the caller distributes by any means (the gRPC SPMD server broadcasts it); kbo_comm_init is
+ * collective over the n_ranks handles.  Without a communicator (or with one rank) kbo_allreduce_argmax is a no-op. */
+#define KBO_COMM_ID_BYTES 128
+int kbo_comm_unique_id(void* id_out /* KBO_COMM_ID_BYTES */);
+int kbo_comm_init(kbo_handle* h, int32_t n_ranks, int32_t rank, const void* id /* KBO_COMM_ID_BYTES */);
+int kbo_comm_destroy(kbo_handle* h);
+int kbo_comm_size(kbo_handle* h);
+int kbo_allreduce_argmax(kbo_handle* h, kbo_best* best_dev, void* stream);
+
 /* ---- one call, HOST buffers in, host result out (tell + ask); synchronises -----------------------
  * The end-to-end entry: H2D of X, y, Xc and D2H of the result are inside the call. */
 int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, const void* Xc,

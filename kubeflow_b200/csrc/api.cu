@@ -37,11 +37,12 @@ int kbo_create(kbo_handle** out, int device) {
 void kbo_destroy(kbo_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  kbo_comm_destroy(h);
   DevBuf* bufs[] = {&h->d_inv_ls, &h->Xs, &h->nx, &h->yn, &h->K, &h->W, &h->Linv, &h->T, &h->alpha, &h->z, &h->Wh, &h->Wl,
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
                     &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal,
                     &h->ks_center, &h->ks_Xh, &h->ks_Xl, &h->ks_nxal, &h->ks_Ch, &h->ks_Cl, &h->ks_nc, &h->rk_part, &h->cal_idx, &h->cal_x, &h->cal_mu,
-                    &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev};
+                    &h->comm_buf, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : h->ev)

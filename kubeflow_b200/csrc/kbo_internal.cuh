@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -78,6 +79,10 @@ struct kbo_handle {
   DevBuf cal_idx, cal_x, cal_mu;   // stratified calibration rows of the ranking pass: indices, gathered rows, FP64-path mean
   float last_rank_mu_err = 0.f;    // largest |μ̃ − μ| (normalised units) on the calibration rows of the last ranking sweep
   int last_unrefined = 0;          // 1: the last tensor-core sweep could not decide in FP64 (more near-ties than the cap)
+  // ---- multi-GPU exchange (comm.cu): NCCL communicator bound at run time ------------------------------------------------
+  void* comm = nullptr;            // ncclComm_t
+  int comm_ranks = 1, comm_rank = 0;
+  DevBuf comm_buf;                 // n_ranks kbo_best gathered
 };
 
 enum ScalIdx { S_YMEAN = 0, S_YSTD = 1, S_YOPT = 2, S_LML = 3, S_LOGDET = 4, S_QUAD = 5, S_COUNT = 8 };

@@ -206,9 +206,31 @@ class GPEngine:
         torch.cuda.current_stream(self.device).synchronize()
         return Lm, Wm, al
 
+    # -- multi-GPU exchange through the C ABI (kbo_comm_*, kbo_allreduce_argmax) --------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """The 128-byte NCCL unique id (call on one rank, hand the bytes to every rank's ``comm_init``)."""
+        buf = C.create_string_buffer(128)
+        rc = L.load().kbo_comm_unique_id(buf)
+        if rc != L.KBO_OK:
+            raise L.KboError(rc, "kbo_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        """Collective over the ranks' engines: afterwards ``ask(..., allreduce=True)`` returns the global argmax."""
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self._h, self.lib.kbo_comm_init(self._h, int(n_ranks), int(rank), C.c_char_p(unique_id)))
+        return self
+
+    def comm_size(self) -> int:
+        return int(self.lib.kbo_comm_size(self._h))
+
     # -- ask ---------------------------------------------------------------------------------------
-    def ask(self, Xc, global_offset: int = 0, return_arrays: bool = False):
-        """Sweep the candidate grid; returns Best (and mu/std/acq float64 CUDA tensors if asked)."""
+    def ask(self, Xc, global_offset: int = 0, return_arrays: bool = False, allreduce: bool = False):
+        """Sweep the candidate grid; returns Best (and mu/std/acq float64 CUDA tensors if asked).  ``allreduce``: combine the
+        ranks' results into the global first-index argmax inside libkbo (kbo_allreduce_argmax; needs ``comm_init``)."""
         dev = f"cuda:{self.device}"
         if isinstance(Xc, torch.Tensor):
             if not Xc.is_cuda or Xc.dtype not in (torch.float64, torch.float32):
@@ -239,6 +261,8 @@ class GPEngine:
             rc = self.lib.kbo_sweep(self._h, ptr, dt, int(M), int(global_offset), on_host, mp, sp, ap,
                                     self._best_dev.data_ptr(), self._stream())
             L.check(self.lib, self._h, rc)
+            if allreduce:
+                L.check(self.lib, self._h, self.lib.kbo_allreduce_argmax(self._h, self._best_dev.data_ptr(), self._stream()))
             b = L.KboBest()
             rc = self.lib.kbo_best_to_host(self._h, self._best_dev.data_ptr(), C.byref(b), self._stream())
             L.check(self.lib, self._h, rc)

@@ -203,6 +203,8 @@ class Optimizer:
         self._tell_engine(eng, Xt, ya)
         rank, world = self._world() if self.shard else (0, 1)
         from .dist import global_argmax, shard_rows
+        if world > 1 and self.n_points < world:     # identical on every rank, before any collective: all raise together
+            raise ValueError(f"n_points={self.n_points} must be >= the number of ranks ({world}) when the grid is sharded")
         lo, hi = shard_rows(self.n_points, rank, world)
         if self.candidate_backend == "torch":
             import torch
@@ -216,14 +218,20 @@ class Optimizer:
             if self._crng is None:
                 self._crng = self.rng if world == 1 else np.random.default_rng([int(self._seed), rank])
             cand = self.space.rvs_transformed(hi - lo, self._crng, np.float32)
-        best = self._sweep(eng, cand, lo)
+        failed = None
+        try:
+            best = self._sweep(eng, cand, lo)
+        except Exception as e:  # noqa: BLE001
+            if world == 1:
+                raise
+            best, failed = None, f"{type(e).__name__}: {e}"   # still join the exchange: every rank raises there, none hangs
         self.last_local_best = best
-        li = best.index - lo
+        li = best.index - lo if best is not None else 0
         if world > 1:
             import torch
             import torch.distributed as dist
             cdev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
-            best = global_argmax(best, device=cdev)
+            best = global_argmax(best, device=cdev, failed=failed)
             owner = next(r for r in range(world) if shard_rows(self.n_points, r, world)[0] <= best.index < shard_rows(self.n_points, r, world)[1])
             rowt = torch.zeros(self.space.transformed_n_dims, dtype=torch.float64, device=cdev)
             if rank == owner:

@@ -76,3 +76,36 @@ def test_shard_rows_partition():
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(R - 1))
         sizes = [b - a for a, b in blocks]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _worker_fail(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kubeflow_b200.dist import RankFailure, global_argmax
+    from kubeflow_b200.gp import Best
+    try:
+        if rank == 1:
+            global_argmax(None, failed="KboError: boom")      # this rank's sweep raised: it still joins the exchange
+        else:
+            global_argmax(Best(1.0, 3, 0.0, 1.0))
+        q.put((rank, "no error"))
+    except RankFailure as e:
+        q.put((rank, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_a_failed_rank_joins_the_exchange_and_every_rank_raises():
+    """Advisor finding: a rank-local failure before the all-gather left the other ranks blocked forever.  The failing rank
+    now contributes (−inf, flag) and all ranks raise RankFailure together."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_fail, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert "rank(s) [1]" in out[0] and "rank(s) [1]" in out[1] and "boom" in out[1]

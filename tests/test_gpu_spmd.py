@@ -83,3 +83,47 @@ def test_spmd_service_two_gpus():
     assert r0["last_fit"] == r1["last_fit"] == "append"
     for pts in r0["replies"]:
         assert len(pts) == 2 and all(-1 <= v["x1"] <= 1 and 10 <= v["x2"] <= 20 for v in pts)
+
+
+def _comm_worker(rank, world, uid, q):
+    """C-ABI exchange: each rank's engine sweeps its shard and kbo_allreduce_argmax (ncclAllGather + reduce) gives the global winner."""
+    from kubeflow_b200.dist import shard_rows
+    from kubeflow_b200.gp import GPEngine
+    from oracle import gp_oracle as O
+    torch.cuda.set_device(rank)
+    N, M, D = 1500, 40001, 7
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    if rank == 0:
+        uid_bytes = GPEngine.comm_unique_id()
+        uid.put(uid_bytes)
+    else:
+        uid_bytes = uid.get(timeout=120)
+    eng = GPEngine(rank, kernel="matern52", acq="ei", var_mode="tc", **th)
+    eng.comm_init(world, rank, uid_bytes)
+    assert eng.comm_size() == world
+    eng.tell(X, y)
+    lo, hi = shard_rows(M, rank, world)
+    local = eng.ask(Xc[lo:hi], global_offset=lo)
+    glob = eng.ask(Xc[lo:hi], global_offset=lo, allreduce=True)
+    full = eng.ask(Xc) if rank == 0 else None
+    q.put((rank, (local.index, local.value), (glob.index, glob.value, glob.mu, glob.std), (full.index, full.value) if full else None))
+    eng.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_c_abi_allreduce_argmax_two_gpus():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q, uid = ctx.Queue(), ctx.Queue()
+    ps = [ctx.Process(target=_comm_worker, args=(r, 2, uid, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted([q.get(timeout=600) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, l0, g0, full), (_, l1, g1, _) = out
+    assert g0 == g1                                                  # every rank holds the same global result
+    assert g0[:2] == max([l0, l1], key=lambda b: (b[1], -b[0]))       # the better shard winner, lowest index on ties
+    assert g0[:2] == full                                            # = the single-GPU sweep of the whole grid
