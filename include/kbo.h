@@ -190,7 +190,8 @@ int kbo_comm_size(kbo_handle* h);
 int kbo_allreduce_argmax(kbo_handle* h, kbo_best* best_dev, void* stream);
 
 /* ---- one call, HOST buffers in, host result out (tell + ask); synchronises -----------------------
- * The end-to-end entry: H2D of X, y, Xc and D2H of the result are inside the call. */
+ * The end-to-end entry: H2D of X, y, Xc and D2H of the result are inside the call.  With a communicator (kbo_comm_init) the
+ * call is collective: every rank passes its row block and global_offset, and best_host is the global argmax on every rank. */
 int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, const void* Xc,
                      int32_t xc_dtype, int64_t M, int64_t global_offset, const kbo_params* p,
                      kbo_best* best_host, kbo_timings* timings /* may be NULL */);

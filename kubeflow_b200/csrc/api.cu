@@ -240,6 +240,7 @@ int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N,
   }
   cudaEventRecord(h->ev[2], s);
   if (r == KBO_OK) r = kbo_i_sweep(h, h->stage_Xc.p, xc_dtype, M, global_offset, nullptr, nullptr, nullptr, (kbo_best*)h->best.p, s);
+  if (r == KBO_OK && h->comm) r = kbo_allreduce_argmax(h, (kbo_best*)h->best.p, s);   // sharded grid: the global first-index argmax
   cudaEventRecord(h->ev[3], s);
   if (r == KBO_OK) r = kbo_best_to_host(h, (const kbo_best*)h->best.p, best_host, s);
   cudaEventRecord(h->ev[4], s);
