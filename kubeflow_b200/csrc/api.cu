@@ -47,6 +47,9 @@ void kbo_destroy(kbo_handle* h) {
     if (b->p) cudaFree(b->p);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& e : h->ev_panel) cudaEventDestroy(e);
+  if (h->s_hi) cudaStreamDestroy(h->s_hi);
+  if (h->s_lo) cudaStreamDestroy(h->s_lo);
   for (auto* v : {&h->ev_var, &h->ev_cross, &h->ev_acq, &h->ev_cal})
     for (auto& p : *v) {
       cudaEventDestroy(p.first);

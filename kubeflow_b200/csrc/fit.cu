@@ -258,7 +258,10 @@ __global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ P,
   }
 }
 
-int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s) {
+// `panel_done` (optional) is called after each 256-column outer panel is final — all rows of L in those columns, before the
+// trailing update of the rest is enqueued — with the number of finished columns; the fit uses it to interleave L⁻¹.
+template <typename Hook>
+static int potrf_impl(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s, Hook panel_done) {
   KBO_TRY(kbo_reserve(h, h->Linv, sizeof(double) * KBO_NB * KBO_NB));
   const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
   if (!h->attr_fit) {
@@ -294,6 +297,7 @@ int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStr
         }
       }
     }
+    KBO_TRY(panel_done(K0, W));
     const int rows_t = N - (K0 + W);
     if (rows_t > 0) {
       const double* Pp = A + (size_t)(K0 + W) * lda + K0;  // rows below the panel × the panel's W columns
@@ -303,6 +307,10 @@ int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStr
     }
   }
   return KBO_OK;
+}
+
+int kbo_i_potrf(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s) {
+  return potrf_impl(h, A, N, lda, info_dev, s, [](int, int) { return (int)KBO_OK; });
 }
 
 // W = L^-1 by recursive doubling: [[W11,0],[−W22·L21·W11, W22]] — log2(N/64) levels of two batched GEMMs.
@@ -342,6 +350,83 @@ int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int l
     }
   }
   return KBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// L = chol(K) and W = L⁻¹ TOGETHER.  The Cholesky of N = 8192 is a chain of 128 single-CTA diagonal blocks (67 µs each) with
+// small panel kernels in between: most of the GPU idles for a third of its 23 ms, and the recursive-doubling inverse (10 ms,
+// at the FP64 ceiling) could only start afterwards — three quarters of its flops sit in the top level, which needs the last
+// panel.  The inverse is therefore computed by ROW PANELS instead:   W_ii = L_ii⁻¹,   W_i,<i = −W_ii · (L_i,<i · W_<i,<i),
+// and row panel i needs nothing but the rows of L in panel i — final as soon as the Cholesky has factored that panel — and
+// the rows of W above it.  Same N³/3 flops, but panel i's share (growing with i) runs on a second stream while the Cholesky
+// works on the panels after it (whose trailing updates shrink with i): only the last row panel (~2 ms) is exposed.
+// The Cholesky chain runs on a high-priority stream so its small kernels are scheduled ahead of the inverse's GEMM blocks.
+static int fit_streams(kbo_handle* h, int n_panels) {
+  if (!h->s_hi) {
+    int lo = 0, hi = 0;
+    KBO_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s_hi, cudaStreamNonBlocking, hi));
+    KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s_lo, cudaStreamNonBlocking, lo));
+  }
+  while ((int)h->ev_panel.size() < n_panels + 3) {
+    cudaEvent_t e;
+    KBO_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev_panel.push_back(e);
+  }
+  return KBO_OK;
+}
+
+static int factor_and_invert(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s) {
+  const int OW = 256, n_panels = (N + OW - 1) / OW;
+  KBO_TRY(fit_streams(h, n_panels));
+  KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
+  const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
+  KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  double* T = (double*)h->T.p;
+  cudaEvent_t e_start = h->ev_panel[n_panels], e_hi = h->ev_panel[n_panels + 1], e_lo = h->ev_panel[n_panels + 2];
+  cudaStream_t shi = h->s_hi, slo = h->s_lo;
+  KBO_CUDA(h, cudaEventRecord(e_start, s));            // the Gram matrix is complete; earlier readers of W / T on s are done
+  KBO_CUDA(h, cudaStreamWaitEvent(shi, e_start, 0));
+  KBO_CUDA(h, cudaStreamWaitEvent(slo, e_start, 0));
+  KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, slo));
+  int rc = potrf_impl(h, A, N, lda, info_dev, shi, [&](int K0, int Wd) -> int {
+    cudaEvent_t ev = h->ev_panel[K0 / OW];
+    KBO_CUDA(h, cudaEventRecord(ev, shi));
+    KBO_CUDA(h, cudaStreamWaitEvent(slo, ev, 0));
+    const double* L = A;
+    // W_PP = L_PP⁻¹: the 64-blocks' inverses, then recursive doubling inside the 256-wide panel
+    double* Wpp = W + (size_t)K0 * ldw + K0;
+    const double* Lpp = L + (size_t)K0 * lda + K0;
+    diag_inv_kernel<<<(Wd + KBO_NB - 1) / KBO_NB, 1024, smem, slo>>>(Lpp, Wd, lda, Wpp, ldw);
+    KBO_LAUNCH_CHECK(h);
+    for (int b = KBO_NB; b < Wd; b *= 2)
+      for (int r0 = 0; r0 + b < Wd; r0 += 2 * b) {
+        const int rows2 = min(b, Wd - (r0 + b));
+        double* T21 = T + (size_t)(K0 + r0 + b) * ldw + K0 + r0;
+        dgemm64_launch<false, EPI_STORE>(slo, rows2, b, b, Lpp + (size_t)(r0 + b) * lda + r0, lda, Wpp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
+                                         KM_FROM_N, 0, TS_NONE);
+        KBO_LAUNCH_CHECK(h);
+        dgemm64_launch<false, EPI_STORE>(slo, rows2, b, rows2, Wpp + (size_t)(r0 + b) * ldw + r0 + b, ldw, T21, ldw, Wpp + (size_t)(r0 + b) * ldw + r0,
+                                         ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+        KBO_LAUNCH_CHECK(h);
+      }
+    if (K0 > 0) {
+      double* Trow = T + (size_t)K0 * ldw;
+      // T_P,<P = L_P,<P · W_<P,<P   (W lower triangular: k >= n)
+      dgemm64_launch<false, EPI_STORE>(slo, Wd, K0, K0, L + (size_t)K0 * lda, lda, W, ldw, Trow, ldw, 1.0, 0.0, KM_FROM_N, 0, TS_NONE);
+      KBO_LAUNCH_CHECK(h);
+      // W_P,<P = −W_PP · T_P,<P     (W_PP lower triangular: k <= m)
+      dgemm64_launch<false, EPI_STORE>(slo, Wd, K0, Wd, Wpp, ldw, Trow, ldw, W + (size_t)K0 * ldw, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+      KBO_LAUNCH_CHECK(h);
+    }
+    return KBO_OK;
+  });
+  // join both streams back into the caller's, also on the error path (the launches already enqueued must not outlive the call's ordering)
+  cudaEventRecord(e_hi, shi);
+  cudaEventRecord(e_lo, slo);
+  cudaStreamWaitEvent(s, e_hi, 0);
+  cudaStreamWaitEvent(s, e_lo, 0);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -536,9 +621,15 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   if (trace) cudaEventRecord(te[0], s);
   KBO_TRY(kbo_i_gram(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, s));
   if (trace) cudaEventRecord(te[1], s);
-  KBO_TRY(kbo_i_potrf(h, (double*)h->K.p, N, ld, (int*)h->info.p, s));
-  if (trace) cudaEventRecord(te[2], s);
-  KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
+  static const bool serial = getenv("KBO_FIT_SERIAL") != nullptr;   // A/B: Cholesky, then recursive-doubling inverse, on one stream
+  if (serial) {
+    KBO_TRY(kbo_i_potrf(h, (double*)h->K.p, N, ld, (int*)h->info.p, s));
+    if (trace) cudaEventRecord(te[2], s);
+    KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
+  } else {
+    KBO_TRY(factor_and_invert(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s));
+    if (trace) cudaEventRecord(te[2], s);
+  }
   if (trace) cudaEventRecord(te[3], s);
   KBO_TRY(fit_finish(h, s, true));
   if (trace) {
