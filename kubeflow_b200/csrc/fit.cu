@@ -359,8 +359,11 @@ int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int l
 // panel.  The inverse is therefore computed by ROW PANELS instead:   W_ii = L_ii⁻¹,   W_i,<i = −W_ii · (L_i,<i · W_<i,<i),
 // and row panel i needs nothing but the rows of L in panel i — final as soon as the Cholesky has factored that panel — and
 // the rows of W above it.  Same N³/3 flops, but panel i's share (growing with i) runs on a second stream while the Cholesky
-// works on the panels after it (whose trailing updates shrink with i): only the last row panel (~2 ms) is exposed.
+// works on the panels after it (whose trailing updates shrink with i): only the last row panel is exposed.
 // The Cholesky chain runs on a high-priority stream so its small kernels are scheduled ahead of the inverse's GEMM blocks.
+// Measured (KBO_FIT_TRACE timeline, profiles/README.md): 34.7 -> 33.7 ms at N = 8192 — the two share one FP64 pipe, the
+// Cholesky's own GEMMs run at ~13 of the ~18 TFLOP/s ceiling, and the chain slows to 28 ms under the contention, so the
+// overlap buys 3 %, not the 10 ms the idle SMs suggested.  KBO_FIT_SERIAL=1 selects the one-stream sequence for A/B runs.
 static int fit_streams(kbo_handle* h, int n_panels) {
   if (!h->s_hi) {
     int lo = 0, hi = 0;
@@ -385,24 +388,45 @@ static int factor_and_invert(kbo_handle* h, double* A, int N, int lda, double* W
   double* T = (double*)h->T.p;
   cudaEvent_t e_start = h->ev_panel[n_panels], e_hi = h->ev_panel[n_panels + 1], e_lo = h->ev_panel[n_panels + 2];
   cudaStream_t shi = h->s_hi, slo = h->s_lo;
+  static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
+  cudaEvent_t trace_ev[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> trace_rp;
+  if (trace) {
+    for (auto& e : trace_ev) cudaEventCreate(&e);
+    cudaEventRecord(trace_ev[0], s);
+  }
   KBO_CUDA(h, cudaEventRecord(e_start, s));            // the Gram matrix is complete; earlier readers of W / T on s are done
   KBO_CUDA(h, cudaStreamWaitEvent(shi, e_start, 0));
   KBO_CUDA(h, cudaStreamWaitEvent(slo, e_start, 0));
   KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, slo));
+  // Row panels of the inverse are 512 wide (two Cholesky panels): M = 512 gives the triangular GEMM below 4 × K0/64 tiles —
+  // several waves, longest K ranges first — where a 256-row panel had too few tiles to balance their unequal K ranges.
+  const int RW = 512;
+  int rp0 = 0;   // first column of the row panel being collected
   int rc = potrf_impl(h, A, N, lda, info_dev, shi, [&](int K0, int Wd) -> int {
+    const int done = K0 + Wd;
+    if (done - rp0 < RW && done < N) return KBO_OK;
+    const int P0 = rp0, Pw = done - rp0;
+    rp0 = done;
     cudaEvent_t ev = h->ev_panel[K0 / OW];
     KBO_CUDA(h, cudaEventRecord(ev, shi));
     KBO_CUDA(h, cudaStreamWaitEvent(slo, ev, 0));
+    if (trace) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, slo);
+      trace_rp.push_back(e);
+    }
     const double* L = A;
-    // W_PP = L_PP⁻¹: the 64-blocks' inverses, then recursive doubling inside the 256-wide panel
-    double* Wpp = W + (size_t)K0 * ldw + K0;
-    const double* Lpp = L + (size_t)K0 * lda + K0;
-    diag_inv_kernel<<<(Wd + KBO_NB - 1) / KBO_NB, 1024, smem, slo>>>(Lpp, Wd, lda, Wpp, ldw);
+    // W_PP = L_PP⁻¹: the 64-blocks' inverses, then recursive doubling inside the panel
+    double* Wpp = W + (size_t)P0 * ldw + P0;
+    const double* Lpp = L + (size_t)P0 * lda + P0;
+    diag_inv_kernel<<<(Pw + KBO_NB - 1) / KBO_NB, 1024, smem, slo>>>(Lpp, Pw, lda, Wpp, ldw);
     KBO_LAUNCH_CHECK(h);
-    for (int b = KBO_NB; b < Wd; b *= 2)
-      for (int r0 = 0; r0 + b < Wd; r0 += 2 * b) {
-        const int rows2 = min(b, Wd - (r0 + b));
-        double* T21 = T + (size_t)(K0 + r0 + b) * ldw + K0 + r0;
+    for (int b = KBO_NB; b < Pw; b *= 2)
+      for (int r0 = 0; r0 + b < Pw; r0 += 2 * b) {
+        const int rows2 = min(b, Pw - (r0 + b));
+        double* T21 = T + (size_t)(P0 + r0 + b) * ldw + P0 + r0;
         dgemm64_launch<false, EPI_STORE>(slo, rows2, b, b, Lpp + (size_t)(r0 + b) * lda + r0, lda, Wpp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
                                          KM_FROM_N, 0, TS_NONE);
         KBO_LAUNCH_CHECK(h);
@@ -410,14 +434,20 @@ static int factor_and_invert(kbo_handle* h, double* A, int N, int lda, double* W
                                          ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
         KBO_LAUNCH_CHECK(h);
       }
-    if (K0 > 0) {
-      double* Trow = T + (size_t)K0 * ldw;
+    if (P0 > 0) {
+      double* Trow = T + (size_t)P0 * ldw;
       // T_P,<P = L_P,<P · W_<P,<P   (W lower triangular: k >= n)
-      dgemm64_launch<false, EPI_STORE>(slo, Wd, K0, K0, L + (size_t)K0 * lda, lda, W, ldw, Trow, ldw, 1.0, 0.0, KM_FROM_N, 0, TS_NONE);
+      dgemm64_launch<false, EPI_STORE>(slo, Pw, P0, P0, L + (size_t)P0 * lda, lda, W, ldw, Trow, ldw, 1.0, 0.0, KM_FROM_N, 0, TS_NONE);
       KBO_LAUNCH_CHECK(h);
       // W_P,<P = −W_PP · T_P,<P     (W_PP lower triangular: k <= m)
-      dgemm64_launch<false, EPI_STORE>(slo, Wd, K0, Wd, Wpp, ldw, Trow, ldw, W + (size_t)K0 * ldw, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+      dgemm64_launch<false, EPI_STORE>(slo, Pw, P0, Pw, Wpp, ldw, Trow, ldw, W + (size_t)P0 * ldw, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
       KBO_LAUNCH_CHECK(h);
+    }
+    if (trace) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, slo);
+      trace_rp.push_back(e);
     }
     return KBO_OK;
   });
@@ -426,6 +456,25 @@ static int factor_and_invert(kbo_handle* h, double* A, int N, int lda, double* W
   cudaEventRecord(e_lo, slo);
   cudaStreamWaitEvent(s, e_hi, 0);
   cudaStreamWaitEvent(s, e_lo, 0);
+  if (trace_ev[0]) {   // KBO_FIT_TRACE: when each stream finished and when each row panel of the inverse began / ended
+    cudaEventRecord(trace_ev[1], shi);
+    cudaEventRecord(trace_ev[2], slo);
+    cudaStreamSynchronize(shi);
+    cudaStreamSynchronize(slo);
+    float a_ms = 0.f, b_ms = 0.f;
+    cudaEventElapsedTime(&a_ms, trace_ev[0], trace_ev[1]);
+    cudaEventElapsedTime(&b_ms, trace_ev[0], trace_ev[2]);
+    fprintf(stderr, "[kbo fit N=%d] cholesky stream done at %.3f ms, inverse stream done at %.3f ms; inverse row panels (begin-end ms):", N, a_ms, b_ms);
+    for (size_t i = 0; i + 1 < trace_rp.size(); i += 2) {
+      float x = 0.f, y = 0.f;
+      cudaEventElapsedTime(&x, trace_ev[0], trace_rp[i]);
+      cudaEventElapsedTime(&y, trace_ev[0], trace_rp[i + 1]);
+      fprintf(stderr, " %.2f-%.2f", x, y);
+    }
+    fprintf(stderr, "\n");
+    for (auto& e : trace_ev) cudaEventDestroy(e);
+    for (auto& e : trace_rp) cudaEventDestroy(e);
+  }
   return rc;
 }
 
