@@ -129,6 +129,16 @@ double kbo_last_rank_error(kbo_handle* h);
  * normalised-y units (0 with the FP64 K* kernel).  The environment variable KBO_RANK_TC sets the initial value. */
 int kbo_set_rank_tc(kbo_handle* h, int enabled);
 double kbo_last_rank_mu_error(kbo_handle* h);
+/* Pruning pass in front of the ranking pass (needs kbo_set_rank_tc).  sigma² = amp - sum_j v_j² with every term >= 0, so the sum
+ * over a PREFIX of the trial tiles bounds sigma² from above, and with it EI / LCB (they grow with sigma; PI is bounded by 1 where
+ * the improvement is positive) — at the prefix's share of the triangular contraction: the first eighth of the trials costs 1/64
+ * of the MMAs.  The calibration rows' (near-exact) values give a lower bound on the maximum for free.  Candidates whose upper
+ * bound stays below it are out; the rest (at most 16384, else the full ranking pass runs as before) get the full contraction,
+ * the interval test and the FP64 decision.  tile_pairs: 512-trial tile pairs in the prefix; -1 (default) = an eighth of them,
+ * 0 = no pruning pass.  kbo_last_prefix_survivors: how many candidates the last pruning pass kept (-1: it did not run).
+ * The environment variable KBO_RANK_PREFIX sets the initial value. */
+int kbo_set_rank_prefix(kbo_handle* h, int tile_pairs);
+int kbo_last_prefix_survivors(kbo_handle* h);
 /* How the last tensor-core sweep decided its suggestion: 0 = FP64 evaluation of every candidate that could still be the
  * maximum; 1 = more such candidates than the cap (4096), FP64 decision among the best 4096 by fp32 value; 2 = not refined
  * (exact fp32 ties beyond the cap, or refinement switched off): the suggestion carries the mode's own accuracy. */

@@ -25,6 +25,7 @@ int kbo_create(kbo_handle** out, int device) {
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("KBO_TC_PAIR")) h->tc_pair = atoi(e) != 0;
   if (const char* e = getenv("KBO_RANK_TC")) h->rank_tc = atoi(e) != 0;
+  if (const char* e = getenv("KBO_RANK_PREFIX")) h->rank_prefix = atoi(e);
   if (prop.major != 10) {
     // sm_100a cubin only: refuse politely instead of failing at the first launch
     h->err = "libkbo is built for sm_100a (B200) only";
@@ -42,7 +43,8 @@ void kbo_destroy(kbo_handle* h) {
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
                     &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal,
                     &h->ks_center, &h->ks_Xh, &h->ks_Xl, &h->ks_nxal, &h->ks_Ch, &h->ks_Cl, &h->ks_nc, &h->rk_part, &h->cal_idx, &h->cal_x, &h->cal_mu,
-                    &h->comm_buf, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev};
+                    &h->comm_buf, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
+                    &h->rk_sched[6].dev, &h->rk_sched[7].dev, &h->pr_list, &h->pr_x, &h->pr_mu, &h->pr_var, &h->cal_mu_rk, &h->cal_var_rk};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : h->ev)
@@ -84,6 +86,14 @@ double kbo_last_rank_error(kbo_handle* h) { return h ? (double)h->last_rank_err 
 double kbo_last_rank_mu_error(kbo_handle* h) { return h ? (double)h->last_rank_mu_err : -1.0; }
 
 int kbo_last_unrefined(kbo_handle* h) { return h ? h->last_unrefined : KBO_ERR_INVALID; }
+
+int kbo_set_rank_prefix(kbo_handle* h, int tile_pairs) {
+  if (!h) return KBO_ERR_INVALID;
+  h->rank_prefix = tile_pairs < 0 ? -1 : tile_pairs;
+  return KBO_OK;
+}
+
+int kbo_last_prefix_survivors(kbo_handle* h) { return h ? h->last_prefix_survivors : KBO_ERR_INVALID; }
 
 int kbo_set_rank_tc(kbo_handle* h, int enabled) {
   if (!h) return KBO_ERR_INVALID;

@@ -70,12 +70,16 @@ struct kbo_handle {
   DevBuf ks_Ch, ks_Cl, ks_nc; // candidate planes / squared norms of the current chunk
   DevBuf rk_part;             // [tile pairs][rows] partial Σ v² of the ranking kernel
   struct RkSched {
-    int key[3] = {-1, -1, -1};  // (row groups, j-tiles, clusters)
+    int key[5] = {-1, -1, -1, -1, -1};  // (row groups, j-tiles, clusters, first tile pair, end tile pair)
     DevBuf dev;
     std::vector<int> host;
-  } rk_sched[4];
+  } rk_sched[8];
   int rk_sched_next = 0;
   bool attr_rank = false;
+  int rank_prefix = -1;            // kbo_set_rank_prefix: tile pairs of the pruning pass (-1: an eighth of them, 0: no pruning pass)
+  int last_prefix_survivors = -1;  // candidates whose prefix upper bound reached the calibration rows' best value (-1: pass not run)
+  DevBuf pr_list, pr_x, pr_mu, pr_var;   // pruning pass: survivor indices, their gathered rows, their ranking-pass mean / variance
+  DevBuf cal_mu_rk, cal_var_rk;          // the ranking arithmetic on the calibration rows
   DevBuf cal_idx, cal_x, cal_mu;   // stratified calibration rows of the ranking pass: indices, gathered rows, FP64-path mean
   float last_rank_mu_err = 0.f;    // largest |μ̃ − μ| (normalised units) on the calibration rows of the last ranking sweep
   int last_unrefined = 0;          // 1: the last tensor-core sweep could not decide in FP64 (more near-ties than the cap)
@@ -152,8 +156,10 @@ int kbo_i_encode_map_f16(kbo_handle* h, CUtensorMap* out, const void* base, uint
                          uint32_t box_outer);
 // ---- tc_kstar.cu / tc_rank.cu ------------------------------------------------------------------
 int kbo_i_tc_trials_prep(kbo_handle* h, bool new_center, cudaStream_t s);
-int kbo_i_tc_kstar(kbo_handle* h, const void* Xc, int xc_dtype, int64_t rows, __half* Ksh, float* mun, cudaStream_t s);
-int kbo_i_tc_rank(kbo_handle* h, const __half* Ksh, int64_t rows, const __half* Wh, int Npad, double amp, float* var_n_out, cudaStream_t s);
+// store_cols: leading columns of the plane actually written (-1: all); the mean always runs over every trial
+int kbo_i_tc_kstar(kbo_handle* h, const void* Xc, int xc_dtype, int64_t rows, __half* Ksh, float* mun, cudaStream_t s, int store_cols = -1);
+int kbo_i_tc_rank(kbo_handle* h, const __half* Ksh, int64_t rows, const __half* Wh, int Npad, double amp, float* var_n_out, cudaStream_t s,
+                  int p_begin = 0, int p_end = -1);
 // ---- tc_var.cu ---------------------------------------------------------------------------------
 // var_n[m] = amp − Σ_j (Σ_k K*[m,k] W[j,k])²  for the rows of one chunk, on tcgen05 tensor cores.
 int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl,

@@ -883,6 +883,206 @@ survivor_kernel(const float* __restrict__ mun, const float* __restrict__ varn, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pruning pass (kbo_set_rank_prefix).  sigma² = amp − Σ_j v_j² with every v_j² >= 0, so the sum over a PREFIX of the trial
+// tiles gives an upper bound on sigma² — and EI / LCB grow with sigma, so acq(mu, sigma²_prefix) bounds the acquisition value
+// from above at the prefix's share of the triangular contraction (the first eighth of the trials: 1/64 of the MMAs).  A lower
+// bound on the maximum comes for free: the calibration rows carry (near-)exact values.  Every candidate whose upper bound stays
+// below it is out; the few that remain (tens to hundreds of a million on the workload of record — EI is decided by the mean
+// far more than by sigma) get the full contraction, the interval test of the ranking pass and the FP64 decision, exactly as
+// before.  A landscape too flat to prune this way falls back to the full ranking pass over the grid.
+//   fs[0] = E, fs[1] = ordered bits of the lower bound on the maximum, fs[2] = raw max |d sigma²|, fs[3] = Emu, fs[4] = raw max |d mu|
+__global__ void __launch_bounds__(1024)
+calib_lb_kernel(const float* __restrict__ v_rk, const float* __restrict__ v_ex, const float* __restrict__ mu_rk, const float* __restrict__ mu_ex, int n,
+                int acq, const double* __restrict__ scal, double xi, double kappa, float* __restrict__ fs) {
+  __shared__ float red[1024], redm[1024], redl[1024];
+  const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
+  float m = 0.f, mm = 0.f, lb = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    m = fmaxf(m, fabsf(v_rk[i] - v_ex[i]));
+    mm = fmaxf(mm, fabsf(mu_rk[i] - mu_ex[i]));
+    const float a = acq_any_f32(acq, mu_ex[i], v_ex[i], ym, ys, yo, x, kp);   // three-product value: |error| ~ 1e-6
+    if (a > lb) lb = a;
+  }
+  red[threadIdx.x] = m;
+  redm[threadIdx.x] = mm;
+  redl[threadIdx.x] = lb;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+      redm[threadIdx.x] = fmaxf(redm[threadIdx.x], redm[threadIdx.x + o]);
+      redl[threadIdx.x] = fmaxf(redl[threadIdx.x], redl[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    fs[0] = 8.f * red[0] + 1e-6f;
+    fs[2] = red[0];
+    fs[3] = 8.f * redm[0] + 1e-7f;
+    fs[4] = redm[0];
+    const float l = redl[0] - 2e-5f * fmaxf(1.f, fabsf(redl[0]));   // the calibration values' own error, generously
+    ((unsigned*)fs)[1] = l > -INFINITY ? ordered_bits(l) : 0u;
+  }
+}
+// supremum of the acquisition value over mu in [mu ± Em], sigma² in (0, var_ub]
+__device__ __forceinline__ float acq_prefix_ub_f32(int acq, float mu, float var_ub, float Em, float ym, float ys, float yo, float x, float kp) {
+  if (acq == KBO_ACQ_PI) {   // Φ(imp/σ): falls with σ where imp > 0 — its supremum there is 1
+    const float imp = yo - x - fmaf(ys, mu - Em, ym);
+    if (imp > 0.f) return 1.f;
+  }
+  return acq_any_f32(acq, mu - Em, var_ub, ym, ys, yo, x, kp);
+}
+__global__ void __launch_bounds__(256)
+prefix_survivor_kernel(const float* __restrict__ mun, const float* __restrict__ var_ub, int64_t M, int acq, const double* __restrict__ scal, double xi,
+                       double kappa, const float* __restrict__ fs, int* __restrict__ list, int* __restrict__ count, int cap) {
+  const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
+  const float E = fs[0], Em = fs[3];
+  const float lb = from_ordered_bits(((const unsigned*)fs)[1]);
+  const float thr = lb - 1e-5f * fmaxf(1.f, fabsf(lb));
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256) {
+    const float ub = acq_prefix_ub_f32(acq, mun[i], fmaxf(var_ub[i], 0.f) + E, Em, ym, ys, yo, x, kp);
+    if (!(ub < thr)) {   // NaN survives
+      const int slot = atomicAdd(count, 1);
+      if (slot < cap) list[slot] = (int)i;
+    }
+  }
+}
+// interval test among the n prefix survivors (contiguous ranking-pass values): best lower bound, then who can still reach it
+__global__ void __launch_bounds__(256)
+survivor_lb_kernel(const float* __restrict__ mun, const float* __restrict__ varn, int n, int acq, const double* __restrict__ scal, double xi, double kappa,
+                   float* __restrict__ fs) {
+  const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
+  const float E = fs[0], Em = fs[3];
+  float best = -INFINITY;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    float lb, ub;
+    acq_bounds_f32(acq, mun[i], varn[i], E, Em, ym, ys, yo, x, kp, &lb, &ub);
+    if (lb > best) best = lb;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best > -INFINITY) atomicMax((unsigned*)fs + 1, ordered_bits(best));
+}
+__global__ void __launch_bounds__(256)
+survivor_final_kernel(const float* __restrict__ mun, const float* __restrict__ varn, const int* __restrict__ src, int n, int acq,
+                      const double* __restrict__ scal, double xi, double kappa, const float* __restrict__ fs, int* __restrict__ list, int* __restrict__ count) {
+  const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
+  const float E = fs[0], Em = fs[3];
+  const float lbmax = from_ordered_bits(((const unsigned*)fs)[1]);
+  const float thr = lbmax - 1e-5f * fmaxf(1.f, fabsf(lbmax));
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    float lb, ub;
+    acq_bounds_f32(acq, mun[i], varn[i], E, Em, ym, ys, yo, x, kp, &lb, &ub);
+    if (!(ub < thr)) {
+      const int slot = atomicAdd(count, 1);
+      if (slot < KBO_REFINE_CAP) list[slot] = src[i];
+    }
+  }
+}
+
+#define KBO_PRUNE_CAP 16384
+// The pruning sweep.  *pruned = 1: best_dev holds the FP64-decided suggestion.  *pruned = 0: too many candidates survive the
+// prefix bound (or the interval test) — the caller runs the full ranking pass; the calibration buffers stay valid for it.
+static int prune_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, int cal_n, int64_t chunk, kbo_best* best_dev, int* pruned,
+                       cudaStream_t s) {
+  *pruned = 0;
+  const int D = h->D, Npad = h->Npad;
+  const size_t esz = xc_dtype == KBO_F64 ? 8 : 4;
+  const double* scal = (const double*)h->scal.p;
+  const int n_pairs = (Npad / 256 + 1) / 2;
+  int P1 = h->rank_prefix < 0 ? (n_pairs + 7) / 8 : h->rank_prefix;
+  if (P1 < 1) P1 = 1;
+  if (P1 >= n_pairs) return KBO_OK;   // nothing to save: the caller's full pass is the prefix
+  KBO_TRY(kbo_reserve(h, h->refine, sizeof(int) * (KBO_REFINE_CAP + 16)));
+  int* list = (int*)h->refine.p;
+  int* count = list + KBO_REFINE_CAP;
+  float* fs = (float*)(count + 4);
+  KBO_TRY(kbo_reserve(h, h->pr_list, sizeof(int) * (KBO_PRUNE_CAP + 16)));
+  int* plist = (int*)h->pr_list.p;
+  int* pcount = plist + KBO_PRUNE_CAP;
+  const int64_t cal_pad = round_up64(cal_n, 256);
+  KBO_TRY(kbo_reserve(h, h->cal_mu_rk, sizeof(float) * (size_t)(cal_pad + 256)));
+  KBO_TRY(kbo_reserve(h, h->cal_var_rk, sizeof(float) * (size_t)(cal_pad + 256)));
+  {
+    KBO_TIME_BEGIN(ev_cal, ev_cal_used);
+    // the ranking arithmetic on the calibration rows (all tile pairs): what E and Emu are measured from
+    KBO_TRY(kbo_i_tc_kstar(h, h->cal_x.p, KBO_F64, cal_n, (__half*)h->Ksh.p, (float*)h->cal_mu_rk.p, s));
+    KBO_TRY(kbo_i_tc_rank(h, (const __half*)h->Ksh.p, cal_pad, (const __half*)h->Wh.p, Npad, h->prm.amplitude, (float*)h->cal_var_rk.p, s));
+    calib_lb_kernel<<<1, 1024, 0, s>>>((const float*)h->cal_var_rk.p, (const float*)h->var_cal.p, (const float*)h->cal_mu_rk.p, (const float*)h->cal_mu.p, cal_n,
+                                       h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs);
+    KBO_LAUNCH_CHECK(h);
+    KBO_TIME_END();
+  }
+  // pass 1 over the grid: mean over all trials, variance bound from the first P1 tile pairs
+  const int prefix_cols = P1 * 512 < Npad ? P1 * 512 : Npad;
+  for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+    const int64_t rows = (M - c0 < chunk) ? (M - c0) : chunk;
+    const unsigned char* xc = (const unsigned char*)Xc + (size_t)c0 * D * esz;
+    h->tim.chunks++;
+    {
+      KBO_TIME_BEGIN(ev_cross, ev_cross_used);
+      KBO_TRY(kbo_i_tc_kstar(h, xc, xc_dtype, rows, (__half*)h->Ksh.p, (float*)h->mun.p + c0, s, prefix_cols));
+      KBO_TIME_END();
+    }
+    {
+      KBO_TIME_BEGIN(ev_var, ev_var_used);
+      KBO_TRY(kbo_i_tc_rank(h, (const __half*)h->Ksh.p, round_up64(rows, 256), (const __half*)h->Wh.p, Npad, h->prm.amplitude, (float*)h->varn.p + c0, s, 0,
+                            P1));
+      KBO_TIME_END();
+    }
+  }
+  KBO_TIME_BEGIN(ev_acq, ev_acq_used);
+  KBO_CUDA(h, cudaMemsetAsync(pcount, 0, sizeof(int), s));
+  prefix_survivor_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs, plist,
+                                                       pcount, KBO_PRUNE_CAP);
+  KBO_LAUNCH_CHECK(h);
+  struct { int n; int pad[3]; float fs[8]; } host;
+  int n1 = 0;
+  KBO_CUDA(h, cudaMemcpyAsync(&n1, pcount, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaMemcpyAsync(&host, count, sizeof host, cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaStreamSynchronize(s));
+  h->last_prefix_survivors = n1;
+  h->last_rank_err = host.fs[2];
+  h->last_rank_mu_err = host.fs[4];
+  if (n1 < 1 || n1 > KBO_PRUNE_CAP) {
+    KBO_TIME_END();
+    return KBO_OK;
+  }
+  // pass 2: the survivors' rows through the whole ranking pass, then the interval test and the FP64 decision
+  const int64_t n1_pad = round_up64(n1, 256);
+  KBO_TRY(kbo_reserve(h, h->pr_x, sizeof(double) * (size_t)n1_pad * D));
+  KBO_TRY(kbo_reserve(h, h->pr_mu, sizeof(float) * (size_t)(n1_pad + 256)));
+  KBO_TRY(kbo_reserve(h, h->pr_var, sizeof(float) * (size_t)(n1_pad + 256)));
+  if (xc_dtype == KBO_F64)
+    gather_rows_kernel<double><<<n1, 64, 0, s>>>((const double*)Xc, D, plist, n1, (double*)h->pr_x.p);
+  else
+    gather_rows_kernel<float><<<n1, 64, 0, s>>>((const float*)Xc, D, plist, n1, (double*)h->pr_x.p);
+  KBO_LAUNCH_CHECK(h);
+  KBO_TRY(kbo_i_tc_kstar(h, h->pr_x.p, KBO_F64, n1, (__half*)h->Ksh.p, (float*)h->pr_mu.p, s));
+  KBO_TRY(kbo_i_tc_rank(h, (const __half*)h->Ksh.p, n1_pad, (const __half*)h->Wh.p, Npad, h->prm.amplitude, (float*)h->pr_var.p, s));
+  KBO_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int), s));
+  const int g2 = (n1 + 255) / 256;
+  survivor_lb_kernel<<<g2, 256, 0, s>>>((const float*)h->pr_mu.p, (const float*)h->pr_var.p, n1, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs);
+  KBO_LAUNCH_CHECK(h);
+  survivor_final_kernel<<<g2, 256, 0, s>>>((const float*)h->pr_mu.p, (const float*)h->pr_var.p, plist, n1, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs, list,
+                                           count);
+  KBO_LAUNCH_CHECK(h);
+  int n2 = 0;
+  KBO_CUDA(h, cudaMemcpyAsync(&n2, count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaStreamSynchronize(s));
+  h->last_contenders = n2;
+  if (n2 < 1 || n2 > KBO_REFINE_CAP) {
+    KBO_TIME_END();
+    return KBO_OK;
+  }
+  h->last_unrefined = 0;
+  KBO_TRY(refine_evaluate(h, Xc, xc_dtype, n2, list, count, goff, best_dev, s));
+  KBO_TIME_END();
+  *pruned = 1;
+  return KBO_OK;
+}
+
 // returns KBO_OK with *overflow = 1 when the survivors do not fit (the caller redoes the sweep with three products)
 static int fast_pick(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, int cal_n, kbo_best* best_dev, int* overflow,
                      cudaStream_t s) {
@@ -979,7 +1179,9 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
       chunk = (int64_t)(h->scratch_limit / ((size_t)Npad * 2)) / 256 * 256;
       if (chunk < 256) chunk = 256;
       if (chunk > round_up64(M, 256)) chunk = round_up64(M, 256);
-      const int64_t rows_sh = chunk > cal_pad ? chunk : cal_pad;
+      int64_t rows_sh = chunk > round_up64(cal_pad, 256) ? chunk : round_up64(cal_pad, 256);
+      const int64_t prune_rows = round_up64(M < 16384 ? M : 16384, 256);          // the pruning pass re-runs up to 16384 survivors in one go
+      if (rows_sh < prune_rows) rows_sh = prune_rows;
       KBO_TRY(kbo_reserve(h, h->Ksh, sizeof(__half) * (size_t)rows_sh * Npad));
       KBO_TRY(kbo_reserve(h, h->Ksl, sizeof(__half) * (size_t)cal_pad * Npad));   // the lo plane exists for the calibration rows only
     } else {
@@ -1009,6 +1211,13 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
     KBO_TIME_BEGIN(ev_cal, ev_cal_used);
     KBO_TRY(calibration_rows(h, Xc, xc_dtype, M, &cal_n, s));
     KBO_TIME_END();
+  }
+  h->last_prefix_survivors = -1;
+  if (rank_tc && h->rank_prefix != 0) {
+    int pruned = 0;
+    KBO_TRY(prune_sweep(h, Xc, xc_dtype, M, goff, cal_n, chunk, best_dev, &pruned, s));
+    if (pruned) return KBO_OK;
+    h->tim.chunks = 0;   // not prunable: the full ranking pass below starts over
   }
   for (int64_t c0 = 0; c0 < M; c0 += chunk) {
     const int64_t rows = (M - c0 < chunk) ? (M - c0) : chunk;

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(KS_THREADS, 1)
 tc_kstar_kernel(const __grid_constant__ CUtensorMap tmCh, const __grid_constant__ CUtensorMap tmCl, const __grid_constant__ CUtensorMap tmXh,
                 const __grid_constant__ CUtensorMap tmXl, int ns, int ntiles, int N, const float* __restrict__ ncand,
                 const float4* __restrict__ nxal4 /* (|x̂_n|², alpha_n) pairs, two trials per float4 */, float log2amp,
-                __half* __restrict__ Ksh, int Npad, float* __restrict__ mun) {
+                __half* __restrict__ Ksh, int Npad, float* __restrict__ mun, int store_tiles /* trial tiles whose K* columns are written */) {
   extern __shared__ unsigned char ks_smem_raw[];
   unsigned char* base = (unsigned char*)(((uintptr_t)ks_smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* smA = base;                                            // [ns][hi 8 KB | lo 8 KB]
@@ -224,9 +224,10 @@ tc_kstar_kernel(const __grid_constant__ CUtensorMap tmCh, const __grid_constant_
           }
           mu_d += (double)macc;
         }
-        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_row + (size_t)t * KS_BN + q * 16), "r"(o[0]), "r"(o[1]),
-                     "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
-                     : "memory");
+        if (t < store_tiles)   // a pruning pass contracts a prefix of the trials only: the mean needs every column, the plane does not
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_row + (size_t)t * KS_BN + q * 16), "r"(o[0]), "r"(o[1]),
+                       "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                       : "memory");
       }
     }
     musum[cg * KS_BM + row] = mu_d;
@@ -320,7 +321,7 @@ int kbo_i_tc_trials_prep(kbo_handle* h, bool new_center, cudaStream_t s) {
 }
 
 // K̃* hi plane (rows_pad × Npad fp16, rows_pad = rows rounded up to 256) and μ̃ for `rows` candidates starting at Xc.
-int kbo_i_tc_kstar(kbo_handle* h, const void* Xc, int xc_dtype, int64_t rows, __half* Ksh, float* mun, cudaStream_t s) {
+int kbo_i_tc_kstar(kbo_handle* h, const void* Xc, int xc_dtype, int64_t rows, __half* Ksh, float* mun, cudaStream_t s, int store_cols) {
   if (!h->ks_ready) KBO_FAIL(h, KBO_ERR_STATE, "tc_kstar: trial operands not prepared");
   const int N = h->N, D = h->D, Dp = round_up(D, KS_BK), Np = round_up(N, KS_BN), ns = Dp / KS_BK;
   const int64_t rows_pad = round_up64(rows, 256);
@@ -346,14 +347,15 @@ int kbo_i_tc_kstar(kbo_handle* h, const void* Xc, int xc_dtype, int64_t rows, __
   const size_t smem = ks_smem_bytes(ns);
   const float log2amp = (float)log2(h->prm.amplitude);
   const int ntiles = h->Npad / KS_BN;   // tiles past Np read out-of-bounds trial rows (TMA zero fill) and are masked to 0
+  const int store_tiles = (store_cols < 0 || store_cols >= h->Npad) ? ntiles : (store_cols + KS_BN - 1) / KS_BN;
   if (h->prm.kernel == KBO_KERNEL_RBF) {
     KBO_CUDA(h, cudaFuncSetAttribute(tc_kstar_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_kstar_kernel<0><<<(unsigned)(rows_pad / KS_BM), KS_THREADS, smem, s>>>(tmCh, tmCl, tmXh, tmXl, ns, ntiles, N, (const float*)h->ks_nc.p,
-                                                                            (const float4*)h->ks_nxal.p, log2amp, Ksh, h->Npad, mun);
+                                                                            (const float4*)h->ks_nxal.p, log2amp, Ksh, h->Npad, mun, store_tiles);
   } else {
     KBO_CUDA(h, cudaFuncSetAttribute(tc_kstar_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_kstar_kernel<1><<<(unsigned)(rows_pad / KS_BM), KS_THREADS, smem, s>>>(tmCh, tmCl, tmXh, tmXl, ns, ntiles, N, (const float*)h->ks_nc.p,
-                                                                            (const float4*)h->ks_nxal.p, log2amp, Ksh, h->Npad, mun);
+                                                                            (const float4*)h->ks_nxal.p, log2amp, Ksh, h->Npad, mun, store_tiles);
   }
   KBO_LAUNCH_CHECK(h);
   return KBO_OK;

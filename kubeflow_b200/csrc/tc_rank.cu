@@ -209,12 +209,12 @@ tc_rank_kernel(const __grid_constant__ CUtensorMap tmA /* K̃* hi plane, box 32 
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-__global__ void rank_finish_kernel(const float* __restrict__ part, int n_pairs, int64_t rows, const double* __restrict__ w_scale, double amp,
+__global__ void rank_finish_kernel(const float* __restrict__ part, int p_begin, int p_end, int64_t rows, const double* __restrict__ w_scale, double amp,
                                    float* __restrict__ var_out) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= rows) return;
   double tot = 0.0;
-  for (int p = 0; p < n_pairs; p++) tot += (double)part[(size_t)p * rows + m];
+  for (int p = p_begin; p < p_end; p++) tot += (double)part[(size_t)p * rows + m];
   const double sc = w_scale[1];
   var_out[m] = (float)(amp - tot * sc * sc);
 }
@@ -222,20 +222,19 @@ __global__ void rank_finish_kernel(const float* __restrict__ part, int n_pairs, 
 // Item lists: items in row-group-major order (largest tile pair of a group first), each dealt to the least-loaded cluster.
 // Loads stay level (≤ 1 % spread on a full chunk), and because they do, the clusters consume the row groups in step: the
 // ~74 items in flight always belong to 4–5 neighbouring row groups, whose K* rows therefore stay in L2.
-int rk_schedule(kbo_handle* h, int n_rg, int n_jtiles, int clusters, const int** sched_dev, cudaStream_t s) {
+int rk_schedule(kbo_handle* h, int n_rg, int n_jtiles, int clusters, int p_begin, int p_end, const int** sched_dev, cudaStream_t s) {
   for (auto& e : h->rk_sched)
-    if (e.key[0] == n_rg && e.key[1] == n_jtiles && e.key[2] == clusters) {
+    if (e.key[0] == n_rg && e.key[1] == n_jtiles && e.key[2] == clusters && e.key[3] == p_begin && e.key[4] == p_end) {
       *sched_dev = (const int*)e.dev.p;
       return KBO_OK;
     }
   kbo_handle::RkSched& e = h->rk_sched[h->rk_sched_next];
-  h->rk_sched_next = (h->rk_sched_next + 1) % 4;
+  h->rk_sched_next = (h->rk_sched_next + 1) % 8;
   e.key[0] = -1;
-  const int n_pairs = (n_jtiles + 1) / 2;
   std::vector<std::vector<int>> lists(clusters);
   std::vector<long long> load(clusters, 0);
   for (int rg = 0; rg < n_rg; rg++)
-    for (int p = n_pairs - 1; p >= 0; p--) {
+    for (int p = p_end - 1; p >= p_begin; p--) {
       int best = 0;
       for (int c = 1; c < clusters; c++)
         if (load[c] < load[best]) best = c;
@@ -257,14 +256,19 @@ int rk_schedule(kbo_handle* h, int n_rg, int n_jtiles, int clusters, const int**
   e.key[0] = n_rg;
   e.key[1] = n_jtiles;
   e.key[2] = clusters;
+  e.key[3] = p_begin;
+  e.key[4] = p_end;
   *sched_dev = (const int*)e.dev.p;
   return KBO_OK;
 }
 
 }  // namespace
 
-// var_n_out[m] = amp − Σ_j (Σ_k K̃*h[m,k]·W[j,k])² for `rows` (multiple of 256) candidate rows of the hi plane Ksh (rows × Npad).
-int kbo_i_tc_rank(kbo_handle* h, const __half* Ksh, int64_t rows, const __half* Wh, int Npad, double amp, float* var_n_out, cudaStream_t s) {
+// var_n_out[m] = amp − Σ_j (Σ_k K̃*h[m,k]·W[j,k])² for `rows` (multiple of 256) candidate rows of the hi plane Ksh (rows × Npad),
+// j restricted to the tile pairs [p_begin, p_end) (p_end < 0: all).  A PREFIX of the pairs gives an upper bound on the variance
+// (every (W k*)_j² is non-negative) at the cost of the prefix's share of the triangle: the first eighth of the trials costs 1/64.
+int kbo_i_tc_rank(kbo_handle* h, const __half* Ksh, int64_t rows, const __half* Wh, int Npad, double amp, float* var_n_out, cudaStream_t s,
+                  int p_begin, int p_end) {
   if (rows % (2 * RK_BM) != 0 || Npad % RK_BN != 0) KBO_FAIL(h, KBO_ERR_INVALID, "tc_rank: rows %% 256 and Npad %% 256 must be 0");
   CUtensorMap tmA, tmW;
   KBO_TRY(kbo_i_encode_map_f16(h, &tmA, Ksh, (uint64_t)Npad, (uint64_t)rows, RK_BK, RK_BM));
@@ -275,15 +279,17 @@ int kbo_i_tc_rank(kbo_handle* h, const __half* Ksh, int64_t rows, const __half* 
   }
   const int n_jtiles = Npad / RK_BN, n_pairs = (n_jtiles + 1) / 2;
   const int64_t n_rg = rows / (2 * RK_BM);
+  if (p_end < 0 || p_end > n_pairs) p_end = n_pairs;
+  if (p_begin < 0 || p_begin >= p_end) KBO_FAIL(h, KBO_ERR_INVALID, "tc_rank: empty tile-pair range [%d, %d)", p_begin, p_end);
   if (n_pairs > 256 || n_rg >= (1 << 23)) KBO_FAIL(h, KBO_ERR_INVALID, "tc_rank: problem too large for the item encoding (Npad %d, rows %lld)", Npad, (long long)rows);
   KBO_TRY(kbo_reserve(h, h->rk_part, sizeof(float) * (size_t)n_pairs * rows));
   int clusters = h->sm_count / 2;
-  if ((int64_t)clusters > n_rg * n_pairs) clusters = (int)(n_rg * n_pairs);
+  if ((int64_t)clusters > n_rg * (p_end - p_begin)) clusters = (int)(n_rg * (p_end - p_begin));
   const int* sched = nullptr;
-  KBO_TRY(rk_schedule(h, (int)n_rg, n_jtiles, clusters, &sched, s));
+  KBO_TRY(rk_schedule(h, (int)n_rg, n_jtiles, clusters, p_begin, p_end, &sched, s));
   tc_rank_kernel<<<(unsigned)(2 * clusters), RK_THREADS, RK_SMEM_BYTES, s>>>(tmA, tmW, n_jtiles, sched, (float*)h->rk_part.p, rows);
   KBO_LAUNCH_CHECK(h);
-  rank_finish_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>((const float*)h->rk_part.p, n_pairs, rows, (const double*)h->scal.p + 6, amp, var_n_out);
+  rank_finish_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>((const float*)h->rk_part.p, p_begin, p_end, rows, (const double*)h->scal.p + 6, amp, var_n_out);
   KBO_LAUNCH_CHECK(h);
   return KBO_OK;
 }

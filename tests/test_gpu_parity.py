@@ -660,21 +660,26 @@ def test_tensor_core_kstar_plane_and_mean_against_fp64_kernel(N, M, D, kind):
 @pytest.mark.parametrize("N,M,D,kind,acq", [(1024, 50000, 8, "rbf", "ei"), (2048, 30000, 32, "matern52", "ei"), (1500, 20000, 6, "matern52", "lcb"),
                                             (1200, 20000, 5, "rbf", "pi"), (1100, 9000, 70, "matern52", "ei")])
 def test_tensor_core_ranking_pass_returns_the_fp64_suggestion(N, M, D, kind, acq):
-    """The product path (tensor-core K*, cta_group::2 ranking kernel, stratified calibration with a mean bound, FP64 decision)
-    returns the same suggestion as the round-1 ranking pass (FP64 K*), the three-product sweep and the FP64 engine."""
+    """The product path (prefix-bound pruning pass, tensor-core K*, cta_group::2 ranking kernel, stratified calibration with a
+    mean bound, FP64 decision) returns the same suggestion as the same path without the pruning pass, the round-1 ranking pass
+    (FP64 K*), the three-product sweep and the FP64 engine."""
     X, y, Xc = O.synthetic(N, M, D)
     th = O.theta_of_record(D)
     kw = dict(kind=kind, acq=acq, **th)
     new = _engine(kw, "tc"); new.tell(X, y)
+    full = _engine(kw, "tc", rank_prefix=0); full.tell(X, y)
     old = _engine(kw, "tc", rank_tc=False); old.tell(X, y)
     slow = _engine(kw, "tc", tc_fast=False); slow.tell(X, y)
     e64 = _engine(kw, "f64"); e64.tell(X, y)
-    bn, bo, bs, b6 = new.ask(Xc), old.ask(Xc), slow.ask(Xc), e64.ask(Xc)
+    bn, bf, bo, bs, b6 = new.ask(Xc), full.ask(Xc), old.ask(Xc), slow.ask(Xc), e64.ask(Xc)
+    assert (bn.index, bn.value, bn.mu, bn.std) == (bf.index, bf.value, bf.mu, bf.std)
+    assert full.last_prefix_survivors() == -1 and new.last_prefix_survivors() >= 1
+    full.close()
     assert (bn.index, bn.value, bn.mu, bn.std) == (bo.index, bo.value, bo.mu, bo.std) == (bs.index, bs.value, bs.mu, bs.std)
     assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value))
     assert new.last_unrefined() == 0 and 1 <= new.last_contenders() <= 4096
     assert 0 < new.last_rank_mu_error() < 1e-2 and old.last_rank_mu_error() == 0.0
-    print(f"\nN={N} M={M} D={D} {kind}/{acq}: survivors new {new.last_contenders()} old {old.last_contenders()}, "
+    print(f"\nN={N} M={M} D={D} {kind}/{acq}: prefix survivors {new.last_prefix_survivors()}, survivors new {new.last_contenders()} old {old.last_contenders()}, "
           f"rank err var {new.last_rank_error():.2e} / {old.last_rank_error():.2e}, mu {new.last_rank_mu_error():.2e}")
     parts = [new.ask(Xc[s:s + 7000], global_offset=s) for s in range(0, M, 7000)]
     win = max(parts, key=lambda b: (b.value, -b.index))
@@ -712,25 +717,27 @@ def test_ranking_pass_on_non_exchangeable_candidate_orders():
         bn, bo, bs, b6 = new.ask(G), old.ask(G), slow.ask(G), e64.ask(G)
         assert (bn.index, bn.value) == (bo.index, bo.value) == (bs.index, bs.value), name
         assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value)), name
-        print(f"\n{name}: index {bn.index} survivors {new.last_contenders()} rank err {new.last_rank_error():.2e} mu {new.last_rank_mu_error():.2e}")
+        print(f"\n{name}: index {bn.index} prefix survivors {new.last_prefix_survivors()} survivors {new.last_contenders()} rank err {new.last_rank_error():.2e} mu {new.last_rank_mu_error():.2e}")
     for e in (new, old, slow, e64):
         e.close()
 
 
 def test_ranking_pass_on_a_flat_landscape_falls_back_and_still_decides_in_fp64():
-    """A near-flat EI landscape (tiny candidate cube far from the data: every candidate within the ranking error of the best):
-    more than 4096 survive, the sweep is redone with three products, whose own window overflows too and is narrowed — the
-    suggestion is still the FP64 engine's and the caller can see how it was decided."""
+    """A near-flat EI landscape (a 1e-4 cube around the incumbent: EI positive and equal to ~1e-6 across the grid): the prefix
+    bound cannot prune (> 16384 survive), the full ranking pass cannot either (> 4096), the sweep is redone with three products,
+    whose own window overflows too and is narrowed — the suggestion is still the FP64 engine's to the contract's tolerance and
+    the caller can see how it was decided."""
     N, M, D = 1024, 30000, 6
     X, y, _ = O.synthetic(N, 10, D)
     th = O.theta_of_record(D)
     r = np.random.default_rng(5)
-    G = 0.5 + 1e-4 * (r.random((M, D)) - 0.5)
+    G = np.clip(X[int(np.argmin(y))] + 0.02 + 1e-4 * (r.random((M, D)) - 0.5), 0, 1)
     kw = dict(kind="matern52", acq="ei", **th)
     new = _engine(kw, "tc"); new.tell(X, y)
     e64 = _engine(kw, "f64"); e64.tell(X, y)
     bn, b6 = new.ask(G), e64.ask(G)
-    assert new.last_contenders() > 4096 and new.last_unrefined() in (1, 2)
+    print(f"\nflat: prefix survivors {new.last_prefix_survivors()} contenders {new.last_contenders()} decision {new.last_unrefined()} value {bn.value:.3e}")
+    assert new.last_prefix_survivors() > 16384 and new.last_contenders() > 4096 and new.last_unrefined() in (1, 2) and b6.value > 1e-6
     ref = O.suggest(X, y, G, kind="matern52", acq="ei", **th)
     assert abs(bn.value - ref["value"]) <= TOL_TC
     assert bn.index == b6.index or abs(ref["acq"][bn.index] - ref["value"]) <= TOL_TC
@@ -749,8 +756,12 @@ def test_cfg3_full_size_path_of_record():
     xc = torch.tensor(Xc, device="cuda")
     new = _engine(kw, "tc"); new.tell(X, y)
     bn = new.ask(xc)
-    surv, rerr, merr = new.last_contenders(), new.last_rank_error(), new.last_rank_mu_error()
-    assert new.last_unrefined() == 0
+    surv, rerr, merr, psurv = new.last_contenders(), new.last_rank_error(), new.last_rank_mu_error(), new.last_prefix_survivors()
+    assert new.last_unrefined() == 0 and 1 <= psurv <= 16384
+    full = _engine(kw, "tc", rank_prefix=0); full.tell(X, y)
+    bf = full.ask(xc)
+    assert (bf.index, bf.value) == (bn.index, bn.value) and full.last_prefix_survivors() == -1
+    full.close()
     old = _engine(kw, "tc", rank_tc=False); old.tell(X, y)
     bo = old.ask(xc)
     old.close()
@@ -763,7 +774,7 @@ def test_cfg3_full_size_path_of_record():
     fit = O.gp_fit(X, y, kind="matern52", **{k: th[k] for k in ("length_scale", "amplitude", "noise")})
     mu, std = O.gp_predict(fit, Xc[sample].astype(np.float64))
     a = O.acquisition(mu, std, float(y.min()), "ei", th["xi"], th["kappa"])
-    print(f"\ncfg3 full size: index {bn.index} value {bn.value:.10f} oracle {a[0]:.10f} |d|={abs(bn.value - a[0]):.2e} survivors {surv} "
+    print(f"\ncfg3 full size: index {bn.index} value {bn.value:.10f} oracle {a[0]:.10f} |d|={abs(bn.value - a[0]):.2e} prefix survivors {psurv} survivors {surv} "
           f"rank err var {rerr:.2e} mu {merr:.2e} next best of sample {np.max(a[1:]):.4f}")
     assert abs(bn.value - a[0]) <= TOL_TC
     assert a[0] >= np.max(a[1:])
