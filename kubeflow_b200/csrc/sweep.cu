@@ -1212,7 +1212,7 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
     KBO_TRY(calibration_rows(h, Xc, xc_dtype, M, &cal_n, s));
     KBO_TIME_END();
   }
-  h->last_prefix_survivors = -1;
+  if (!force_three) h->last_prefix_survivors = -1;   // (a three-product redo keeps what the failed ranking attempt recorded)
   if (rank_tc && h->rank_prefix != 0) {
     int pruned = 0;
     KBO_TRY(prune_sweep(h, Xc, xc_dtype, M, goff, cal_n, chunk, best_dev, &pruned, s));

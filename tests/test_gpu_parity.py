@@ -679,6 +679,9 @@ def test_tensor_core_ranking_pass_returns_the_fp64_suggestion(N, M, D, kind, acq
     assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value))
     assert new.last_unrefined() == 0 and 1 <= new.last_contenders() <= 4096
     assert 0 < new.last_rank_mu_error() < 1e-2 and old.last_rank_mu_error() == 0.0
+    if acq == "ei":
+        assert new.last_prefix_survivors() <= 16384     # EI is decided by the mean: the prefix bound prunes (PI, bounded by 1 wherever
+                                                        # the improvement is positive, may not — it then takes the full pass, or three products)
     print(f"\nN={N} M={M} D={D} {kind}/{acq}: prefix survivors {new.last_prefix_survivors()}, survivors new {new.last_contenders()} old {old.last_contenders()}, "
           f"rank err var {new.last_rank_error():.2e} / {old.last_rank_error():.2e}, mu {new.last_rank_mu_error():.2e}")
     parts = [new.ask(Xc[s:s + 7000], global_offset=s) for s in range(0, M, 7000)]
