@@ -381,7 +381,7 @@ def main():
                        "argmax_index": best.index, "argmax_value": best.value, "argmax_mu": best.mu, "argmax_std": best.std,
                        "survivors_decided_in_fp64": survivors, "decision": unrefined,
                        "ranking_pass": ({"variance_error_on_calibration_rows": rank_err, "mean_error_on_calibration_rows": rank_mu_err,
-                                         "calibration": "stratified rows i*M/n, n = 18944, through the FP64 K* kernel + three-product contraction; bounds = 8 x max error"}
+                                         "calibration": "stratified rows i*M/n, n = 9472, through the FP64 K* kernel + three-product contraction; bounds = 8 x max error"}
                                         if fast_rank else None)},
             "e2e": {"value": world * 1e3 / ms_step_e2e, "unit": "suggestions/s", "ms_per_step": ms_step_e2e,
                     "h2d_bytes_per_step": int(X.nbytes + y.nbytes + Xc.nbytes), "d2h_bytes_per_step": 32,

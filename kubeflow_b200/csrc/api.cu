@@ -50,6 +50,7 @@ void kbo_destroy(kbo_handle* h) {
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& e : h->ev_panel) cudaEventDestroy(e);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_hi) cudaStreamDestroy(h->s_hi);
   if (h->s_lo) cudaStreamDestroy(h->s_lo);
   for (auto* v : {&h->ev_var, &h->ev_cross, &h->ev_acq, &h->ev_cal})
@@ -237,17 +238,30 @@ int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N,
   h->time_kernels = true;
   h->ev_var_used = h->ev_cross_used = h->ev_acq_used = h->ev_cal_used = 0;
   cudaEventRecord(h->ev[0], s);
-  // H2D of everything up front (X, y, Xc), then tell + ask, then the 32-byte result back
+  // X, y go up first and the fit is enqueued; the candidate grid (the bulk of the bytes) is copied on a second stream WHILE the
+  // fit runs — it is not needed before the sweep.  (Issued after the fit's launches so that a pageable source, whose copy
+  // blocks the host, still overlaps the device work; a pinned source overlaps either way.)
   int r = kbo_fit(h, X, y, N, D, p, 1, s);
   cudaEventRecord(h->ev[1], s);
   if (r == KBO_OK) {
     const size_t bytes = (size_t)M * D * (xc_dtype == KBO_F64 ? 8 : 4);
     r = kbo_reserve(h, h->stage_Xc, bytes);
+    if (r == KBO_OK && !h->s_copy) {
+      cudaError_t e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking);
+      if (e != cudaSuccess) {
+        h->err = std::string("cudaStreamCreate failed: ") + cudaGetErrorString(e);
+        r = KBO_ERR_CUDA;
+      }
+    }
     if (r == KBO_OK) {
-      cudaError_t e = cudaMemcpyAsync(h->stage_Xc.p, Xc, bytes, cudaMemcpyHostToDevice, s);
+      cudaEventRecord(h->ev[5], h->s_copy);
+      cudaError_t e = cudaMemcpyAsync(h->stage_Xc.p, Xc, bytes, cudaMemcpyHostToDevice, h->s_copy);
+      cudaEventRecord(h->ev[6], h->s_copy);
       if (e != cudaSuccess) {
         h->err = std::string("H2D of candidates failed: ") + cudaGetErrorString(e);
         r = KBO_ERR_CUDA;
+      } else {
+        cudaStreamWaitEvent(s, h->ev[6], 0);
       }
     }
   }
@@ -261,7 +275,7 @@ int kbo_suggest_host(kbo_handle* h, const double* X, const double* y, int32_t N,
   h->time_kernels = false;
   kbo_timings t{};
   cudaEventElapsedTime(&t.fit_ms, h->ev[0], h->ev[1]);    // includes H2D of X, y
-  cudaEventElapsedTime(&t.h2d_ms, h->ev[1], h->ev[2]);    // H2D of the candidate grid
+  if (r == KBO_OK) cudaEventElapsedTime(&t.h2d_ms, h->ev[5], h->ev[6]);    // H2D of the candidate grid (second stream, overlapped with the fit)
   cudaEventElapsedTime(&t.sweep_ms, h->ev[2], h->ev[3]);
   cudaEventElapsedTime(&t.d2h_ms, h->ev[3], h->ev[4]);
   cudaEventElapsedTime(&t.total_ms, h->ev[0], h->ev[4]);

@@ -84,7 +84,7 @@ struct kbo_handle {
   float last_rank_mu_err = 0.f;    // largest |μ̃ − μ| (normalised units) on the calibration rows of the last ranking sweep
   int last_unrefined = 0;          // 1: the last tensor-core sweep could not decide in FP64 (more near-ties than the cap)
   // ---- fit: Cholesky chain on a high-priority stream, row-panel inverse on a second one (fit.cu) ----------------------
-  cudaStream_t s_hi = nullptr, s_lo = nullptr;
+  cudaStream_t s_hi = nullptr, s_lo = nullptr, s_copy = nullptr;
   std::vector<cudaEvent_t> ev_panel;
   // ---- multi-GPU exchange (comm.cu): NCCL communicator bound at run time ------------------------------------------------
   void* comm = nullptr;            // ncclComm_t

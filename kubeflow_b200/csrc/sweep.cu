@@ -1116,7 +1116,10 @@ static int fast_pick(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int
 // cal_idx (row indices), cal_mu (normalised mean), var_cal (normalised variance).  Uses the K* scratch planes, so it runs
 // before the first chunk.
 static int calibration_rows(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int* cal_n_out, cudaStream_t s) {
-  int64_t want = (int64_t)h->sm_count * 128;
+  // one wave of the three-product cluster kernel: 74 clusters × 128 rows on a B200.  The bounds are 8 × the largest error seen on
+  // these rows; the errors are sums of thousands of rounding terms (light-tailed: the maximum over 1e6 rows of a Gaussian exceeds
+  // the maximum over 1e4 by ~1.2×), so the sample size is not what the margin hinges on — its being stratified is.
+  int64_t want = (int64_t)h->sm_count * 64;
   const int cal_n = (int)(M < want ? M : want);
   const int64_t cal_pad = round_up64(cal_n, 128);
   KBO_TRY(kbo_reserve(h, h->cal_idx, sizeof(int) * (size_t)cal_pad));
