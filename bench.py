@@ -297,6 +297,19 @@ def main():
     acq_gbs, acq_launch_ms = acq_bw(M)
     acq_gbs16, acq_launch_ms16 = acq_bw(16_777_216)
 
+    # ---- the tensor-core kernel of record, measured on the FULL contraction (kbo_set_rank_prefix(h, 0)): the product path's
+    # pruning pass runs the same kernel over the first eighth of the trial tiles only, which is too short a launch to rate ----
+    prefix_survivors = eng.last_prefix_survivors()
+    full_tims = []
+    if args.var_mode == "tc" and rank == 0:
+        e_full = GPEngine(local, kernel=KERNEL, acq=ACQ, var_mode="tc", rank_prefix=0, tc_k_span=args.k_span, **th)
+        for i in range(5):
+            b_full, t_full = e_full.suggest_host(Xh, yh, Xch, global_offset=goff)
+            if i >= 2:
+                full_tims.append(t_full)
+        assert b_full.index == (best.index if world == 1 else b_full.index)
+        e_full.close()
+
     other = {}
     # ---- multi-GPU: the same 1M grid split R ways (strong scaling) and, at R = 8, BASELINE.json config 5 ----------------------
     if world > 1 and not args.no_extras:
@@ -317,6 +330,12 @@ def main():
             del X5_d
 
     # ---- single GPU extras: the three-product sweep and a flat landscape beside the headline, the other BASELINE configs ----------
+    if rank == 0 and full_tims:
+        other["full_ranking_pass"] = {"ms_per_step_e2e": float(np.mean([t["total_ms"] for t in full_tims])),
+                                      "variance_kernel_ms": float(np.mean([t["var_kernel_ms"] for t in full_tims])),
+                                      "kstar_kernel_ms": float(np.mean([t["cross_kernel_ms"] for t in full_tims])),
+                                      "note": "kbo_set_rank_prefix(h, 0): no pruning pass — tensor-core K* and cta_group::2 contraction over the whole grid "
+                                              "(also what a landscape too flat to prune costs, before any three-product redo)"}
     if rank == 0 and world == 1 and not args.no_extras:
         try:
             e3 = GPEngine(local, kernel=KERNEL, acq=ACQ, var_mode="tc", tc_fast=False, **th)
@@ -326,11 +345,13 @@ def main():
                                             "note": "kbo_set_tc_fast(h, 0): FP64 K* kernel + fp16x3 contraction over the whole grid — what a caller asking "
                                                     "for per-candidate arrays gets, and the fallback when the ranking pass cannot prune"}
             e3.close()
-            # a landscape the ranking pass cannot prune: all candidates in a 1e-4 cube (EI flat to ~1e-6) -> > 4096 survivors ->
-            # three-product redo -> window narrowing; reported so the headline's dependence on a peaked EI is visible
-            flat = torch.tensor((0.5 + 1e-4 * (np.random.default_rng(5).random((M, D)) - 0.5)).astype(np.float32), device=dev)
+            # a landscape nothing can prune: all candidates in a 1e-4 cube next to the incumbent (EI positive, flat to ~1e-6) -> the prefix
+            # bound keeps everything -> full ranking pass -> > 4096 survivors -> three-product redo -> window narrowing; reported so the
+            # headline's dependence on a peaked EI is visible
+            flat = torch.tensor(np.clip(X[int(np.argmin(y))] + 0.02 + 1e-4 * (np.random.default_rng(5).random((M, D)) - 0.5), 0, 1).astype(np.float32), device=dev)
             ms_f, b_f = timed(lambda: (eng.tell(Xd, yd), eng.ask(flat))[1], 2, 1)
-            other["flat_landscape"] = {"ms_per_step": ms_f, "suggestions_per_s": 1e3 / ms_f, "survivors_of_the_ranking_pass": eng.last_contenders(),
+            other["flat_landscape"] = {"ms_per_step": ms_f, "suggestions_per_s": 1e3 / ms_f, "kept_by_the_pruning_pass": eng.last_prefix_survivors(),
+                                       "survivors_of_the_ranking_pass": eng.last_contenders(),
                                        "decision": {0: "fp64 among all survivors", 1: "fp64 among the best 4096 by fp32 value", 2: "not refined"}[eng.last_unrefined()],
                                        "argmax_value": b_f.value}
             del flat
@@ -354,14 +375,18 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        rows_per_launch = M / max(chunks, 1)
-        var_launch_ms = mean("var_kernel_ms") / max(chunks, 1)
+        fast_rank = args.var_mode == "tc" and rank_err > 0.0
+        rank_tc = fast_rank and rank_mu_err > 0.0
+        pruned = rank_tc and 1 <= prefix_survivors <= 16384
+        fmean = (lambda k: float(np.mean([t[k] for t in full_tims]))) if full_tims else mean
+        fchunks = full_tims[-1]["chunks"] if full_tims else chunks
+        rows_per_launch = M / max(fchunks, 1)
+        var_launch_ms = fmean("var_kernel_ms") / max(fchunks, 1)
         cross_launch_ms = mean("cross_kernel_ms") / max(chunks, 1)
         flops_launch = rows_per_launch * float(N) * float(N)           # Σ_j Σ_{k<=j} 2 flops = N² per candidate row
         achieved_tf = flops_launch / (var_launch_ms * 1e-3) / 1e12
-        fast_rank = args.var_mode == "tc" and rank_err > 0.0
-        rank_tc = fast_rank and rank_mu_err > 0.0
         mma_products = 1.0 if fast_rank else 3.0
+        fit_tflops = (2.0 * N ** 3 / 3.0) / (mean("fit_ms") * 1e-3) / 1e12   # Cholesky N³/3 + inverse N³/3
         kernel = "tc_rank_kernel" if rank_tc else ("tc_variance_pair_kernel" if os.environ.get("KBO_TC_PAIR", "1") != "0" else "tc_variance_kernel")
         Npad = (N + 255) // 256 * 256
         kstar_bytes = rows_per_launch * Npad * 2.0
@@ -380,6 +405,8 @@ def main():
                        "l2": "inputs larger than L2 (Xc 128 MiB, W plane 128 MiB, K* scratch 4 GiB per chunk)",
                        "argmax_index": best.index, "argmax_value": best.value, "argmax_mu": best.mu, "argmax_std": best.std,
                        "survivors_decided_in_fp64": survivors, "decision": unrefined,
+                       "pruning_pass": ({"prefix_of_trial_tiles": "first eighth (1/64 of the contraction's MMAs)", "candidates_kept": prefix_survivors,
+                                         "pruned": bool(pruned)} if rank_tc else None),
                        "ranking_pass": ({"variance_error_on_calibration_rows": rank_err, "mean_error_on_calibration_rows": rank_mu_err,
                                          "calibration": "stratified rows i*M/n, n = 9472, through the FP64 K* kernel + three-product contraction; bounds = 8 x max error"}
                                         if fast_rank else None)},
@@ -394,7 +421,15 @@ def main():
                          "issued_mma_tflops": mma_products * achieved_tf * (1.0 + 256.0 / N), "mma_products_per_term": mma_products,
                          "traffic": kernel_traffic("tcrank_traffic.json" if rank_tc else "tcvar_traffic.json", rows_per_launch) if (rank_tc or not fast_rank) else None,
                          "launch_ms": var_launch_ms, "launches_per_step": chunks, "flops_per_launch": flops_launch,
-                         "launch_note": "variance phase time / chunks (CUDA events inside libkbo around tc_rank_kernel + its 6 µs finish kernel)"},
+                         "launch_note": "variance phase time / chunks (CUDA events inside libkbo around tc_rank_kernel + its 6 µs finish kernel)",
+                         "measured_on": ("the full contraction, kbo_set_rank_prefix(h, 0), 3 steps through kbo_suggest_host in this run (%.1f ms per step): the product "
+                                         "path above prunes with the same kernel over the first eighth of the trial tiles (%.2f ms per step) and contracts fully only "
+                                         "the %d candidates that survive" % (fmean("total_ms"), mean("var_kernel_ms"), prefix_survivors)) if pruned else "the product path"},
+            "fit_fp64": {"kernels": "dgemm64_kernel (DMMA m8n8k4) + potf2_inv/trsm panel chain", "flops": 2.0 * N ** 3 / 3.0, "ms": mean("fit_ms"),
+                         "achieved_tflops": fit_tflops, "fp64_ceiling_tflops_measured_here": 18.0, "frac": fit_tflops / 18.0,
+                         "note": "the step's largest phase since the pruning pass; FP64 by contract (fp32 Cholesky / alpha move EI by up to 4e-4). The ceiling is this "
+                                 "repo's own measurement of DFMA/DMMA GEMMs on B200 (profiles/README.md, FP64 ceiling), not a MEASURED_PEAKS.json entry; the "
+                                 "Cholesky is a chain of 128 single-CTA diagonal blocks, latency- not throughput-bound"},
             "kstar_hbm": {"bound": "hbm", "kernel": "tc_kstar_kernel" if rank_tc else "cross_mean_kernel", "bytes_per_launch": kstar_bytes,
                           "launch_ms": cross_launch_ms, "achieved": kstar_bytes / (cross_launch_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                           "frac": kstar_bytes / (cross_launch_ms * 1e-3) / 1e9 / pk["hbm"],
