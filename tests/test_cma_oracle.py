@@ -51,3 +51,38 @@ def test_ties_broken_by_sample_index():
     C.tell(s1, Y, np.array([1.0, 0.0, 0.0, 2.0, 0.0, 3.0]))
     C.tell(s2, Y[[1, 2, 4, 0, 3, 5]], np.array([0.0, 0.0, 0.0, 1.0, 2.0, 3.0]))
     np.testing.assert_allclose(s1.mean, s2.mean, atol=1e-15)
+
+
+def test_parameters_match_the_tutorial_formulas_evaluated_independently():
+    """tests/golden/cma_known_answers.json: Hansen's parameter formulas evaluated with `decimal` (oracle/make_golden_cma.py) — for
+    n = 10, λ = 10 these are the tutorial's default setting: w_1..5 = 0.4563, 0.2708, 0.1622, 0.0852, 0.0255, μ_eff = 3.167."""
+    import json, os
+    from tests.conftest import GOLDEN_DIR
+    cases = json.load(open(os.path.join(GOLDEN_DIR, "cma_known_answers.json")))["cases"]
+    assert abs(cases[0]["mu_eff"] - 3.1672992) < 1e-6 and abs(cases[0]["weights_first8"][0] - 0.45627265) < 1e-7   # the published 4-digit values
+    for g in cases:
+        p = C.CmaParams(g["n"], g["popsize"])
+        for k in ("mu_eff", "c1", "cmu", "c_sigma", "d_sigma", "cc", "chi_n"):
+            assert abs(getattr(p, k) - g[k]) <= 1e-13 * max(1.0, abs(g[k])), (g["n"], k, getattr(p, k), g[k])
+        np.testing.assert_allclose(p.weights[:8], g["weights_first8"], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(p.weights[-2:], g["weights_last2"], rtol=1e-13, atol=1e-15)
+        assert abs(p.weights.sum() - g["weights_sum"]) < 1e-12
+
+
+def test_oracle_replays_its_committed_run_bit_for_bit():
+    """tests/golden/cma_replay.npz: 12 seeded generations on the sphere and on Rastrigin.  Any change to the oracle's arithmetic
+    (and hence to what the GPU sampler is compared with) shows up here first."""
+    import os
+    from tests.conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "cma_replay.npz"))
+    for name, f in (("sphere", C.sphere), ("rastrigin", C.rastrigin)):
+        r = np.random.default_rng(20240917)
+        st = C.CmaState(np.full(5, 1.5), 0.8, 8)
+        for g in range(12):
+            X, Y = C.ask(st, r.standard_normal((8, 5)))
+            C.tell(st, Y, f(X))
+            np.testing.assert_allclose(st.mean, z[f"{name}_mean"][g], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(st.C, z[f"{name}_C"][g], rtol=0, atol=1e-13)
+            assert abs(st.sigma - z[f"{name}_sigma"][g]) <= 1e-13
+            np.testing.assert_allclose(st.p_sigma, z[f"{name}_p_sigma"][g], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(st.pc, z[f"{name}_pc"][g], rtol=0, atol=1e-13)
