@@ -170,6 +170,15 @@ int kbo_fit_info(kbo_handle* h, double* lml, double* y_mean, double* y_std, doub
 /* Gradient of the log-marginal likelihood of the last kbo_fit w.r.t. θ = (log amplitude, log noise, log ℓ_1..ℓ_P), P =
  * n_length_scale of that fit ($SK/_gpr.py:621-653).  grad_host: n_out = 2 + P doubles.  Synchronises. */
 int kbo_lml_grad(kbo_handle* h, double* grad_host, int32_t n_out, void* stream);
+/* Log-marginal likelihood of G hyper-parameter settings over ONE history (X, y as for kbo_fit), for theta search: what sklearn's
+ * optimiser evaluates one theta after another ($SK/_gpr.py:299-339, :604-618, :658-667).  The G factorisations run on G streams
+ * and hide each other's latency (a Cholesky of a few thousand trials is a chain of single-CTA blocks): 8 thetas cost about two
+ * fits.  Per theta: Gram, Cholesky, z = L^-1 yn by forward substitution, LML = -z.z/2 - sum log L_ii - N/2 log 2pi.  Does not
+ * touch the handle's fitted state.  params: G entries (kernel, amplitude, noise, length_scale, n_length_scale, normalize_y of
+ * entry 0 used); lml_host: G doubles (-inf where the Gram matrix is not positive definite); info_host (may be NULL): G failed
+ * pivots (0 = ok).  Synchronises.  1 <= G <= 64. */
+int kbo_lml_batch(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, int32_t G, const kbo_params* params,
+                  int x_on_host, double* lml_host, int32_t* info_host, void* stream);
 /* copies the fit state into caller-owned DEVICE buffers (any may be NULL): L_out, W_out are N×N row-major
  * (L: lower Cholesky factor, strict upper part zeroed; W = L^-1), alpha_out has N entries. For parity tests. */
 int kbo_fit_state(kbo_handle* h, double* L_out, double* W_out, double* alpha_out, void* stream);

@@ -39,11 +39,13 @@ void kbo_destroy(kbo_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   kbo_comm_destroy(h);
+  kbo_i_lml_batch_free(h);
+  if (h->lml_ev) cudaEventDestroy(h->lml_ev);
   DevBuf* bufs[] = {&h->d_inv_ls, &h->Xs, &h->nx, &h->yn, &h->K, &h->W, &h->Linv, &h->T, &h->alpha, &h->z, &h->Wh, &h->Wl,
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
                     &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal,
                     &h->ks_center, &h->ks_Xh, &h->ks_Xl, &h->ks_nxal, &h->ks_Ch, &h->ks_Cl, &h->ks_nc, &h->rk_part, &h->cal_idx, &h->cal_x, &h->cal_mu,
-                    &h->comm_buf, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
+                    &h->comm_buf, &h->lml_yn, &h->lml_scal, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
                     &h->rk_sched[6].dev, &h->rk_sched[7].dev, &h->pr_list, &h->pr_x, &h->pr_mu, &h->pr_var, &h->cal_mu_rk, &h->cal_var_rk};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -125,6 +127,24 @@ int kbo_fit(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t 
     y = (const double*)h->stage_y.p;
   }
   return kbo_i_fit(h, X, y, N, D, p, s);
+}
+
+int kbo_lml_batch(kbo_handle* h, const double* X, const double* y, int32_t N, int32_t D, int32_t G, const kbo_params* params, int x_on_host,
+                  double* lml_host, int32_t* info_host, void* stream) {
+  if (!h) return KBO_ERR_INVALID;
+  if (!X || !y || !params || !lml_host) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_batch: null argument");
+  if (N < 1 || D < 1) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_batch: need N >= 1 and D >= 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  KBO_CUDA(h, cudaSetDevice(h->device));
+  if (x_on_host) {
+    KBO_TRY(kbo_reserve(h, h->stage_X, sizeof(double) * (size_t)N * D));
+    KBO_TRY(kbo_reserve(h, h->stage_y, sizeof(double) * (size_t)N));
+    KBO_CUDA(h, cudaMemcpyAsync(h->stage_X.p, X, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, s));
+    KBO_CUDA(h, cudaMemcpyAsync(h->stage_y.p, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+    X = (const double*)h->stage_X.p;
+    y = (const double*)h->stage_y.p;
+  }
+  return kbo_i_lml_batch(h, X, y, N, D, G, params, lml_host, info_host, s);
 }
 
 int kbo_fit_append(kbo_handle* h, const double* x, double y, int x_on_host, void* stream) {

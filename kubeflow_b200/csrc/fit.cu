@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ P,
 // `panel_done` (optional) is called after each 256-column outer panel is final — all rows of L in those columns, before the
 // trailing update of the rest is enqueued — with the number of finished columns; the fit uses it to interleave L⁻¹.
 template <typename Hook>
-static int potrf_impl(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s, Hook panel_done) {
-  KBO_TRY(kbo_reserve(h, h->Linv, sizeof(double) * KBO_NB * KBO_NB));
+static int potrf_impl(kbo_handle* h, double* A, int N, int lda, int* info_dev, cudaStream_t s, Hook panel_done, double* Linv_lane = nullptr) {
+  if (!Linv_lane) KBO_TRY(kbo_reserve(h, h->Linv, sizeof(double) * KBO_NB * KBO_NB));
   const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
   if (!h->attr_fit) {
     KBO_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -271,7 +271,7 @@ static int potrf_impl(kbo_handle* h, double* A, int N, int lda, int* info_dev, c
     h->attr_fit = true;
   }
   KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
-  double* Linv = (double*)h->Linv.p;
+  double* Linv = Linv_lane ? Linv_lane : (double*)h->Linv.p;   // inverted diagonal block of the current step (one per concurrent factorisation)
   // Two-level blocking: 64-wide diagonal blocks (one CTA each) inside 256-wide outer panels.  Inside a panel only the
   // panel's own remaining columns are updated after each 64-block (K = 64, ≤ 192 columns); the rest of the trailing
   // matrix sees ONE update per outer panel with K = 256 — 4× less read-modify-write traffic on the trailing matrix than
@@ -694,6 +694,147 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   }
   h->fitted = true;
   return KBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kbo_lml_batch: log-marginal likelihood of G hyper-parameter settings at once ($SK/_gpr.py:604-618 per θ; the loop being
+// replaced is sklearn's optimiser evaluating them one after another, :299-339, :658-667).
+// The Cholesky of a few-thousand-trial history is a CHAIN of single-CTA diagonal blocks — most of the GPU idles — so the G
+// factorisations are enqueued on G streams and hide each other's latency: 8 θ at N = 2048 cost about as much as 2 fits.
+// Per θ only what the LML needs is computed: Gram, Cholesky, z = L⁻¹·yn by blocked forward substitution (no inverse, no
+// alpha: ynᵀK⁻¹yn = zᵀz), Σ log L_ii.
+__global__ void __launch_bounds__(256)
+trsv_lml_kernel(const double* __restrict__ L, int N, int ldl, const double* __restrict__ yn, const int* __restrict__ info, double* __restrict__ out) {
+  extern __shared__ double zs[];            // z, N doubles
+  __shared__ double rhs[KBO_NB];
+  __shared__ double Lb[KBO_NB][KBO_NB + 1];   // the diagonal block: the substitution below is a dependent chain, keep it off global memory
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  if (*info != 0) {
+    if (t == 0) out[0] = -INFINITY;
+    return;
+  }
+  double logdet = 0.0, quad = 0.0;
+  for (int b0 = 0; b0 < N; b0 += KBO_NB) {
+    const int jb = min(KBO_NB, N - b0);
+    // rhs_r = yn_r − Σ_{k < b0} L[r][k]·z[k]: one warp per 8 rows, lanes stride the columns, fixed-order butterfly
+    for (int rr = warp; rr < jb; rr += 8) {
+      const double* row = L + (size_t)(b0 + rr) * ldl;
+      double a = 0.0;
+      for (int k = lane; k < b0; k += 32) a = fma(row[k], zs[k], a);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) rhs[rr] = yn[b0 + rr] - a;
+    }
+    for (int e = t; e < KBO_NB * KBO_NB; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      Lb[r][c] = (r < jb && c <= r) ? L[(size_t)(b0 + r) * ldl + b0 + c] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {   // forward substitution inside the 64-block: lanes own rows lane and lane+32
+      double r0 = lane < jb ? rhs[lane] : 0.0, r1 = lane + 32 < jb ? rhs[lane + 32] : 0.0;
+      for (int c = 0; c < jb; c++) {
+        const double lcc = Lb[c][c];
+        const double zc = __shfl_sync(0xffffffffu, c < 32 ? r0 : r1, c & 31) / lcc;
+        if (lane == (c & 31)) {
+          if (c < 32) r0 = zc; else r1 = zc;
+        }
+        if (lane > c && lane < jb) r0 = fma(-Lb[lane][c], zc, r0);
+        if (lane + 32 > c && lane + 32 < jb) r1 = fma(-Lb[lane + 32][c], zc, r1);
+        if (lane == 0) {
+          logdet += log(lcc);
+          quad = fma(zc, zc, quad);
+        }
+      }
+      if (lane < jb) zs[b0 + lane] = r0;
+      if (lane + 32 < jb) zs[b0 + lane + 32] = r1;
+    }
+    __syncthreads();
+  }
+  if (t == 0) out[0] = -0.5 * quad - logdet - 0.5 * N * 1.8378770664093453;
+}
+
+struct LmlLane {
+  cudaStream_t s = nullptr;
+  DevBuf K, Xs, XsT, nx, inv_ls, Linv, info, out;
+};
+
+int kbo_i_lml_batch(kbo_handle* h, const double* X_dev, const double* y_dev, int N, int D, int G, const kbo_params* params, double* lml_host,
+                    int32_t* info_host, cudaStream_t s) {
+  if (N < 1 || D < 1 || D > 512 || G < 1 || G > 64) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_batch: need N >= 1, 1 <= D <= 512, 1 <= G <= 64");
+  const int ld = round_up(N, 64);
+  for (int g = 0; g < G; g++) {
+    const kbo_params* p = params + g;
+    if (!p->length_scale || (p->n_length_scale != 1 && p->n_length_scale != D)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_batch: theta %d: n_length_scale must be 1 or D", g);
+    if (!(p->noise >= 0.0) || !(p->amplitude > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_batch: theta %d: amplitude must be > 0 and noise >= 0", g);
+    if (p->kernel != KBO_KERNEL_RBF && p->kernel != KBO_KERNEL_MATERN52) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_batch: theta %d: unknown kernel", g);
+    for (int d = 0; d < p->n_length_scale; d++)
+      if (!(p->length_scale[d] > 0.0)) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_batch: theta %d: length_scale[%d] must be > 0", g, d);
+  }
+  auto* lanes = (std::vector<LmlLane>*)h->lml_lanes;
+  if (!lanes) h->lml_lanes = lanes = new std::vector<LmlLane>();
+  if ((int)lanes->size() < G) lanes->resize(G);
+  const int smem_pf = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
+  if (!h->attr_fit) {
+    KBO_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pf));
+    KBO_CUDA(h, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pf));
+    KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pf));
+    h->attr_fit = true;
+  }
+  const int zs_bytes = (int)sizeof(double) * N;
+  if (zs_bytes > 200 * 1024) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_batch: N <= 25600 supported (got %d)", N);
+  KBO_CUDA(h, cudaFuncSetAttribute(trsv_lml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, zs_bytes));
+  // y statistics are θ-independent: normalise once on the caller's stream
+  KBO_TRY(kbo_reserve(h, h->lml_yn, sizeof(double) * ld));
+  KBO_TRY(kbo_reserve(h, h->lml_scal, sizeof(double) * 16));
+  prep_y_kernel<<<1, 1024, 0, s>>>(y_dev, N, params[0].normalize_y, (double*)h->lml_yn.p, (double*)h->lml_scal.p);
+  KBO_LAUNCH_CHECK(h);
+  if (!h->lml_ev) KBO_CUDA(h, cudaEventCreateWithFlags(&h->lml_ev, cudaEventDisableTiming));
+  KBO_CUDA(h, cudaEventRecord(h->lml_ev, s));
+  std::vector<double> inv(512);
+  for (int g = 0; g < G; g++) {
+    LmlLane& L = (*lanes)[g];
+    const kbo_params* p = params + g;
+    if (!L.s) KBO_CUDA(h, cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
+    KBO_TRY(kbo_reserve(h, L.K, sizeof(double) * (size_t)ld * ld));
+    KBO_TRY(kbo_reserve(h, L.Xs, sizeof(double) * (size_t)ld * D));
+    KBO_TRY(kbo_reserve(h, L.XsT, sizeof(double) * (size_t)D * ld));
+    KBO_TRY(kbo_reserve(h, L.nx, sizeof(double) * ld));
+    KBO_TRY(kbo_reserve(h, L.inv_ls, sizeof(double) * 512));
+    KBO_TRY(kbo_reserve(h, L.Linv, sizeof(double) * KBO_NB * KBO_NB));
+    KBO_TRY(kbo_reserve(h, L.info, sizeof(int) * 4));
+    KBO_TRY(kbo_reserve(h, L.out, sizeof(double) * 2));
+    KBO_CUDA(h, cudaStreamWaitEvent(L.s, h->lml_ev, 0));
+    for (int d = 0; d < p->n_length_scale; d++) inv[d] = 1.0 / p->length_scale[d];
+    KBO_CUDA(h, cudaMemcpyAsync(L.inv_ls.p, inv.data(), sizeof(double) * p->n_length_scale, cudaMemcpyHostToDevice, L.s));   // pageable: staged before return
+    prep_x_kernel<<<(N + 127) / 128, 128, 0, L.s>>>(X_dev, N, D, (const double*)L.inv_ls.p, p->n_length_scale, (double*)L.Xs.p, (double*)L.XsT.p, ld,
+                                                   (double*)L.nx.p);
+    KBO_LAUNCH_CHECK(h);
+    KBO_TRY(kbo_i_gram(h, (const double*)L.Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)L.K.p, ld, L.s));
+    KBO_TRY(potrf_impl(h, (double*)L.K.p, N, ld, (int*)L.info.p, L.s, [](int, int) { return (int)KBO_OK; }, (double*)L.Linv.p));
+    trsv_lml_kernel<<<1, 256, zs_bytes, L.s>>>((const double*)L.K.p, N, ld, (const double*)h->lml_yn.p, (const int*)L.info.p, (double*)L.out.p);
+    KBO_LAUNCH_CHECK(h);
+  }
+  for (int g = 0; g < G; g++) {
+    LmlLane& L = (*lanes)[g];
+    int inf = 0;
+    KBO_CUDA(h, cudaMemcpyAsync(lml_host + g, L.out.p, sizeof(double), cudaMemcpyDeviceToHost, L.s));
+    KBO_CUDA(h, cudaMemcpyAsync(&inf, L.info.p, sizeof(int), cudaMemcpyDeviceToHost, L.s));
+    KBO_CUDA(h, cudaStreamSynchronize(L.s));
+    if (info_host) info_host[g] = inf;
+  }
+  return KBO_OK;
+}
+
+void kbo_i_lml_batch_free(kbo_handle* h) {
+  auto* lanes = (std::vector<LmlLane>*)h->lml_lanes;
+  if (!lanes) return;
+  for (auto& L : *lanes) {
+    for (DevBuf* b : {&L.K, &L.Xs, &L.XsT, &L.nx, &L.inv_ls, &L.Linv, &L.info, &L.out})
+      if (b->p) cudaFree(b->p);
+    if (L.s) cudaStreamDestroy(L.s);
+  }
+  delete lanes;
+  h->lml_lanes = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -86,6 +86,10 @@ struct kbo_handle {
   // ---- fit: Cholesky chain on a high-priority stream, row-panel inverse on a second one (fit.cu) ----------------------
   cudaStream_t s_hi = nullptr, s_lo = nullptr, s_copy = nullptr;
   std::vector<cudaEvent_t> ev_panel;
+  // ---- kbo_lml_batch: concurrent factorisations for several θ (fit.cu) --------------------------------------------------
+  void* lml_lanes = nullptr;       // std::vector<LmlLane>*
+  DevBuf lml_yn, lml_scal;
+  cudaEvent_t lml_ev = nullptr;
   // ---- multi-GPU exchange (comm.cu): NCCL communicator bound at run time ------------------------------------------------
   void* comm = nullptr;            // ncclComm_t
   int comm_ranks = 1, comm_rank = 0;
@@ -145,6 +149,9 @@ int kbo_i_fit_rebase(kbo_handle* h, int n_keep, const double* y_dev, cudaStream_
 int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int ldw, cudaStream_t s);
 int kbo_i_zero_upper(kbo_handle* h, double* A, int N, int lda, cudaStream_t s);
 int kbo_i_fit(kbo_handle* h, const double* X_dev, const double* y_dev, int N, int D, const kbo_params* p, cudaStream_t s);
+int kbo_i_lml_batch(kbo_handle* h, const double* X_dev, const double* y_dev, int N, int D, int G, const kbo_params* params, double* lml_host,
+                    int32_t* info_host, cudaStream_t s);
+void kbo_i_lml_batch_free(kbo_handle* h);
 // ---- sweep.cu ----------------------------------------------------------------------------------
 int kbo_i_sweep(kbo_handle* h, const void* Xc_dev, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out,
                 double* acq_out, kbo_best* best_dev, cudaStream_t s);

@@ -201,6 +201,31 @@ class GPEngine:
         L.check(self.lib, self._h, rc)
         return info["lml"], g
 
+    def lml_batch(self, X, y, thetas):
+        """Log-marginal likelihood of several θ over one history in one call (kbo_lml_batch: the factorisations run concurrently).
+        ``thetas``: list of dicts with any of length_scale / noise / amplitude (the engine's own values where absent).
+        Returns a float64 NumPy array, −inf where the Gram matrix is not positive definite.  The fitted state is untouched."""
+        X, y = self._as_host_f64(X), self._as_host_f64(y).reshape(-1)
+        N, D = X.shape
+        G = len(thetas)
+        arr = (L.KboParams * G)()
+        keep = []
+        for g, th in enumerate(thetas):
+            ls = np.atleast_1d(np.asarray(th.get("length_scale", self.length_scale), dtype=np.float64))
+            buf = (C.c_double * len(ls))(*ls)
+            keep.append(buf)
+            arr[g] = L.KboParams(kernel=L.KERNELS[self.kernel], acq=L.ACQS[self.acq], normalize_y=int(self.normalize_y),
+                                 var_mode=L.VAR_MODES[self.var_mode], amplitude=float(th.get("amplitude", self.amplitude)),
+                                 noise=float(th.get("noise", self.noise)), xi=self.xi, kappa=self.kappa, length_scale=buf,
+                                 n_length_scale=len(ls), tc_k_span=self.tc_k_span)
+        out = np.empty(G, dtype=np.float64)
+        info = (C.c_int32 * G)()
+        with torch.cuda.device(self.device):
+            rc = self.lib.kbo_lml_batch(self._h, X.ctypes.data, y.ctypes.data, int(N), int(D), int(G), arr, 1,
+                                        out.ctypes.data_as(C.POINTER(C.c_double)), info, self._stream())
+        L.check(self.lib, self._h, rc)
+        return out
+
     def state(self):
         """Copies of L (lower), W = L^-1 and alpha as float64 CUDA tensors (parity tests)."""
         N, dev = self.N, f"cuda:{self.device}"

@@ -167,16 +167,27 @@ class Optimizer:
                 cands += [(float(np.exp(tr.uniform(np.log(0.2), np.log(5.0)))), float(np.exp(tr.uniform(np.log(1e-6), np.log(1e-1)))))
                           for _ in range(self.theta_search)]
             best_lml, best_t = -np.inf, (1.0, self.noise)
-            self._fit_state = None
-            for m, nz in cands:
-                eng.length_scale, eng.noise = base * m, nz
-                eng.tell(Xt, ya)
-                try:
-                    lml = eng.fit_info()["lml"]
-                except Exception:   # not positive definite at this θ
-                    continue
-                if lml > best_lml:
-                    best_lml, best_t = lml, (m, nz)
+            if hasattr(eng, "lml_batch"):
+                # all candidates in a few calls: the factorisations of a batch run concurrently on the device (kbo_lml_batch) —
+                # the chain of diagonal blocks of one hides behind the others' — instead of one full fit per θ
+                gb = max(1, min(8, int(2 ** 31 // max(1, 8 * len(ya) * len(ya)))))      # ≤ 2 GiB of Gram matrices per batch
+                for i in range(0, len(cands), gb):
+                    part = cands[i:i + gb]
+                    lmls = eng.lml_batch(Xt, ya, [dict(length_scale=base * m, noise=nz) for m, nz in part])
+                    for (m, nz), lml in zip(part, lmls):
+                        if np.isfinite(lml) and lml > best_lml:
+                            best_lml, best_t = float(lml), (m, nz)
+            else:
+                self._fit_state = None
+                for m, nz in cands:
+                    eng.length_scale, eng.noise = base * m, nz
+                    eng.tell(Xt, ya)
+                    try:
+                        lml = eng.fit_info()["lml"]
+                    except Exception:   # not positive definite at this θ
+                        continue
+                    if lml > best_lml:
+                        best_lml, best_t = lml, (m, nz)
             eng.length_scale, eng.noise = base * best_t[0], best_t[1]
             self.last_theta = dict(length_scale=eng.length_scale.copy(), noise=eng.noise, lml=best_lml)
         if self.theta_fit == "lbfgs":

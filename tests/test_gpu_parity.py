@@ -782,3 +782,44 @@ def test_cfg3_full_size_path_of_record():
     assert abs(bn.value - a[0]) <= TOL_TC
     assert a[0] >= np.max(a[1:])
     new.close()
+
+
+@pytest.mark.parametrize("N,D,kind", [(700, 5, "matern52"), (2048, 16, "rbf"), (65, 3, "matern52")])
+def test_lml_batch_matches_one_fit_per_theta_and_the_oracle(N, D, kind):
+    """kbo_lml_batch: G factorisations on G streams.  Each value equals what a full fit at that θ reports
+    (and the oracle's $SK/_gpr.py:604-618 restatement); a θ whose Gram matrix is not positive definite reads −inf; ARD length
+    scales work; the handle's fitted state is untouched; 8 θ cost a small multiple of one fit."""
+    import time
+    X, y, Xc = O.synthetic(N, 100, D)
+    th = O.theta_of_record(D)
+    eng = _engine(dict(kind=kind, acq="ei", **th), "f64")
+    eng.tell(X, y)
+    before = eng.ask(Xc)
+    thetas = [dict(length_scale=th["length_scale"] * m, noise=nz) for m, nz in ((0.25, 1e-3), (0.5, 1e-2), (1.0, 1e-3), (1.0, 1e-6), (2.0, 1e-3),
+                                                                               (4.0, 1e-1), (0.7, 3e-4))]
+    thetas.append(dict(length_scale=np.linspace(0.5, 2.0, D) * th["length_scale"], noise=1e-3))       # anisotropic
+    got = eng.lml_batch(X, y, thetas)
+    for t, g in zip(thetas, got):
+        one = _engine(dict(kind=kind, acq="ei", **{**th, **t}), "f64")
+        one.tell(X, y)
+        ref = one.fit_info()["lml"]
+        orc = O.gp_fit(X, y, kind=kind, length_scale=t["length_scale"], amplitude=th["amplitude"], noise=t["noise"])["lml"]
+        assert abs(g - ref) <= 1e-9 * max(1.0, abs(ref)), (t, g, ref)
+        assert abs(g - orc) <= 1e-7 * max(1.0, abs(orc)), (t, g, orc)
+        one.close()
+    after = eng.ask(Xc)
+    assert (before.index, before.value) == (after.index, after.value)
+    # duplicate rows with zero noise: not positive definite -> -inf for that θ only
+    Xd, yd = np.concatenate([X, X[:1]]), np.concatenate([y, y[:1]])
+    got = eng.lml_batch(Xd, yd, [dict(noise=0.0), dict(noise=1e-3)])
+    assert got[0] == -np.inf and np.isfinite(got[1])
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(3):
+        eng.lml_batch(X, y, thetas)
+    torch.cuda.synchronize(); tb = (time.perf_counter() - t0) / 3
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.tell(X, y)
+    torch.cuda.synchronize(); t1 = (time.perf_counter() - t0) / 3
+    print(f"\nN={N}: lml_batch of {len(thetas)} thetas {tb * 1e3:.2f} ms, one fit {t1 * 1e3:.2f} ms (ratio {tb / t1:.2f})")
+    eng.close()
