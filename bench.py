@@ -141,7 +141,7 @@ def cpu_reference(n_trials, dim, batches, rows_per_batch=8192, m_total=M_CAND):
             "fit_s": t_fit, "sweep_sample_s": t_sweep, "host_cpus": os.cpu_count(), "seconds_per_suggestion": t_full}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out_fd):
     if rank != 0:
         return
     # BASELINE.md §3.4 asks for 16 batches of 8192 rows: they are spread over the timed steps (each step pays the full fit, as
@@ -165,10 +165,23 @@ def run_reference(args, rank):
             "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": 1.0 / t, "unit": "suggestions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line["cpu_baseline"]["value"] = line["value"]
-    print(json.dumps(line), flush=True)
+    _emit(out_fd, line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """stdout carries ONE JSON line.  Libraries write banners to file descriptor 1 behind Python's back (NCCL prints its version on
+    the first communicator of a process): fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line: dict):
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,8 +199,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    out_fd = _claim_stdout()
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, out_fd)
         return
 
     import torch
@@ -446,7 +460,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference(N, D, 2, m_total=M).items() if k != "seconds_per_suggestion"}
-        print(json.dumps(line), flush=True)
+        _emit(out_fd, line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
