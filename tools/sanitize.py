@@ -19,7 +19,7 @@ def theta_of_record(D):
     return dict(length_scale=0.3 * np.sqrt(D), amplitude=1.0, noise=1e-3, xi=0.01, kappa=1.96)
 
 
-for N, M, D, mode in ((70, 300, 3, "f64"), (135, 515, 5, "tc"), (300, 700, 33, "tc")):
+for N, M, D, mode in ((70, 300, 3, "f64"), (135, 515, 5, "tc"), (300, 700, 33, "tc"), (700, 1900, 40, "tc")):   # the last: 2 tile pairs -> pruning pass
     X, y, Xc = synthetic(N, M, D)
     th = theta_of_record(D)
     e = GPEngine(0, kernel="matern52", acq="ei", var_mode=mode, **th)
@@ -33,8 +33,16 @@ for N, M, D, mode in ((70, 300, 3, "f64"), (135, 515, 5, "tc"), (300, 700, 33, "
     e.rebase(N - 5, y[:N - 5] * 0.5)
     b4 = e.ask(Xc)
     g = e.lml_grad()[1]
-    print(N, M, D, mode, b.index, b2.index, b3.index, b4.index, e.last_contenders(), float(g[0]))
+    lm = e.lml_batch(X, y, [dict(noise=1e-3), dict(noise=1e-2, length_scale=th["length_scale"] * 2)])
+    b5, _, _, _ = e.ask(Xc, return_arrays=True)      # three-product / FP64 array path
+    print(N, M, D, mode, b.index, b2.index, b3.index, b4.index, b5.index, e.last_contenders(), e.last_prefix_survivors(), float(g[0]), lm.tolist())
     e.close()
+    if mode == "tc":                                  # the ranking pass without pruning, and the round-1 ranking pass
+        for kw in (dict(rank_prefix=0), dict(rank_tc=False)):
+            e = GPEngine(0, kernel="matern52", acq="ei", var_mode=mode, **th, **kw)
+            e.tell(X, y)
+            print("   ", kw, e.ask(Xc.astype(np.float32)).index)
+            e.close()
 es = CmaEs(np.zeros(9), 1.0, popsize=20, seed=1)
 print(es.run_synthetic("sphere", 3))
 es.close()
