@@ -479,6 +479,166 @@ static int factor_and_invert(kbo_handle* h, double* A, int N, int lda, double* W
 }
 
 // ------------------------------------------------------------------------------------------------
+// Version 2 of the joint factorisation: LOOK-AHEAD.  In potrf_impl every 64-block step touches all N−k rows below it (panel
+// solve + in-panel update: ~125 CTAs each), so when a trailing update runs beside the chain those kernels queue for SM slots
+// behind 70 µs GEMM blocks and the chain doubles in length (round 1's look-ahead attempt: no gain).  Here the dependent chain
+// of a 256-column panel works on its 256×256 DIAGONAL block only — four single-CTA factorisations, ≤ 3-CTA solves, ≤ 9-CTA
+// updates — then inverts that block (needed for L⁻¹ anyway) and solves the whole panel below it with ONE GEMM against the
+// inverse.  The trailing update is issued on a second stream as [next column block | rest]: the next panel's chain starts as
+// soon as its own column block is up to date, while the rest of the update and the inverse's row panels (third stream) fill
+// the SMs the chain leaves idle.
+static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s) {
+  const int OW = 256, n_panels = (N + OW - 1) / OW;
+  KBO_TRY(fit_streams(h, 2 * n_panels + 8));
+  if (!h->s_upd) {
+    int lo = 0, hi = 0;
+    KBO_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s_upd, cudaStreamNonBlocking, (lo + hi) / 2));
+  }
+  KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
+  KBO_TRY(kbo_reserve(h, h->T2, sizeof(double) * (size_t)N * OW));
+  KBO_TRY(kbo_reserve(h, h->Linv, sizeof(double) * KBO_NB * KBO_NB));
+  const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
+  if (!h->attr_fit) {
+    KBO_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KBO_CUDA(h, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    h->attr_fit = true;
+  }
+  double* T = (double*)h->T.p;
+  double* T2 = (double*)h->T2.p;
+  double* Linv = (double*)h->Linv.p;
+  cudaStream_t shi = h->s_hi, supd = h->s_upd, sinv = h->s_lo;
+  cudaEvent_t* ev_solve = h->ev_panel.data();                  // [n_panels]
+  cudaEvent_t* ev_col = h->ev_panel.data() + n_panels;         // [n_panels + 1]
+  cudaEvent_t e_start = h->ev_panel[2 * n_panels + 2], e_hi = h->ev_panel[2 * n_panels + 3], e_upd = h->ev_panel[2 * n_panels + 4],
+              e_inv = h->ev_panel[2 * n_panels + 5];
+  static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
+  cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (trace) {
+    for (auto& e : tr) cudaEventCreate(&e);
+    cudaEventRecord(tr[0], s);
+  }
+  KBO_CUDA(h, cudaEventRecord(e_start, s));
+  KBO_CUDA(h, cudaStreamWaitEvent(shi, e_start, 0));
+  KBO_CUDA(h, cudaStreamWaitEvent(supd, e_start, 0));
+  KBO_CUDA(h, cudaStreamWaitEvent(sinv, e_start, 0));
+  KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), shi));
+  KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, shi));
+  const int RW = 512;
+  int rp0 = 0;
+  int rc = KBO_OK;
+  auto body = [&]() -> int {
+    for (int K0 = 0, P = 0; K0 < N; K0 += OW, P++) {
+      const int Wd = min(OW, N - K0);
+      if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(shi, ev_col[P], 0));   // this panel's column block carries every earlier panel's update
+      // ---- the chain: the diagonal block only -------------------------------------------------------------------------
+      for (int k = K0; k < K0 + Wd; k += KBO_NB) {
+        const int jb = min(KBO_NB, N - k);
+        potf2_inv_kernel<<<1, 1024, smem, shi>>>(A + (size_t)k * lda + k, lda, jb, k, Linv, info_dev);
+        KBO_LAUNCH_CHECK(h);
+        const int rows_in = K0 + Wd - (k + jb);
+        if (rows_in > 0) {
+          double* Pn = A + (size_t)(k + jb) * lda + k;
+          trsm_panel_kernel<<<(rows_in + 63) / 64, 256, smem, shi>>>(Pn, lda, rows_in, jb, Linv, info_dev);
+          KBO_LAUNCH_CHECK(h);
+          dgemm64_launch<true, EPI_STORE>(shi, rows_in, rows_in, jb, Pn, lda, Pn, lda, A + (size_t)(k + jb) * lda + (k + jb), lda, -1.0, 1.0, KM_FULL, 0,
+                                          TS_LOWER);
+          KBO_LAUNCH_CHECK(h);
+        }
+      }
+      // ---- W_PP = L_PP⁻¹ (64-block inverses, recursive doubling inside the panel) -----------------------------------------
+      double* Wpp = W + (size_t)K0 * ldw + K0;
+      const double* Lpp = A + (size_t)K0 * lda + K0;
+      diag_inv_kernel<<<(Wd + KBO_NB - 1) / KBO_NB, 1024, smem, shi>>>(Lpp, Wd, lda, Wpp, ldw);
+      KBO_LAUNCH_CHECK(h);
+      for (int b = KBO_NB; b < Wd; b *= 2)
+        for (int r0 = 0; r0 + b < Wd; r0 += 2 * b) {
+          const int rows2 = min(b, Wd - (r0 + b));
+          double* T21 = T + (size_t)(K0 + r0 + b) * ldw + K0 + r0;
+          dgemm64_launch<false, EPI_STORE>(shi, rows2, b, b, Lpp + (size_t)(r0 + b) * lda + r0, lda, Wpp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
+                                           KM_FROM_N, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+          dgemm64_launch<false, EPI_STORE>(shi, rows2, b, rows2, Wpp + (size_t)(r0 + b) * ldw + r0 + b, ldw, T21, ldw,
+                                           Wpp + (size_t)(r0 + b) * ldw + r0, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+        }
+      // ---- the panel below the diagonal block: L_>P,P = A_>P,P · W_PPᵀ, one GEMM (W_PP lower triangular: k <= n) ------------------
+      const int rows_t = N - (K0 + Wd);
+      if (rows_t > 0) {
+        double* Pp = A + (size_t)(K0 + Wd) * lda + K0;
+        dgemm64_launch<true, EPI_STORE>(shi, rows_t, Wd, Wd, Pp, lda, Wpp, ldw, T2, OW, 1.0, 0.0, KM_UPTO_N, 0, TS_NONE);
+        KBO_LAUNCH_CHECK(h);
+        KBO_CUDA(h, cudaMemcpy2DAsync(Pp, sizeof(double) * lda, T2, sizeof(double) * OW, sizeof(double) * Wd, rows_t, cudaMemcpyDeviceToDevice, shi));
+      }
+      KBO_CUDA(h, cudaEventRecord(ev_solve[P], shi));
+      // ---- trailing update, second stream: next column block first (look-ahead), then the rest ---------------------------------
+      if (rows_t > 0) {
+        KBO_CUDA(h, cudaStreamWaitEvent(supd, ev_solve[P], 0));
+        const double* Pp = A + (size_t)(K0 + Wd) * lda + K0;
+        const int nb = min(OW, rows_t);
+        dgemm64_launch<true, EPI_STORE>(supd, rows_t, nb, Wd, Pp, lda, Pp, lda, A + (size_t)(K0 + Wd) * lda + (K0 + Wd), lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+        KBO_LAUNCH_CHECK(h);
+        KBO_CUDA(h, cudaEventRecord(ev_col[P + 1], supd));
+        const int rows_r = rows_t - nb;
+        if (rows_r > 0) {
+          const double* Pr = Pp + (size_t)nb * lda;
+          dgemm64_launch<true, EPI_STORE>(supd, rows_r, rows_r, Wd, Pr, lda, Pr, lda, A + (size_t)(K0 + Wd + nb) * lda + (K0 + Wd + nb), lda, -1.0, 1.0,
+                                          KM_FULL, 0, TS_LOWER);
+          KBO_LAUNCH_CHECK(h);
+        }
+      }
+      // ---- the inverse's row panel (512 rows = two panels), third stream ------------------------------------------------------
+      const int done = K0 + Wd;
+      if (done - rp0 >= RW || done >= N) {
+        const int P0 = rp0, Pw = done - rp0;
+        rp0 = done;
+        KBO_CUDA(h, cudaStreamWaitEvent(sinv, ev_solve[P], 0));
+        double* Wrp = W + (size_t)P0 * ldw + P0;
+        const double* Lrp = A + (size_t)P0 * lda + P0;
+        for (int b = OW; b < Pw; b *= 2)      // levels above the 256-panel inside the row panel
+          for (int r0 = 0; r0 + b < Pw; r0 += 2 * b) {
+            const int rows2 = min(b, Pw - (r0 + b));
+            double* T21 = T + (size_t)(P0 + r0 + b) * ldw + P0 + r0;
+            dgemm64_launch<false, EPI_STORE>(sinv, rows2, b, b, Lrp + (size_t)(r0 + b) * lda + r0, lda, Wrp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
+                                             KM_FROM_N, 0, TS_NONE);
+            KBO_LAUNCH_CHECK(h);
+            dgemm64_launch<false, EPI_STORE>(sinv, rows2, b, rows2, Wrp + (size_t)(r0 + b) * ldw + r0 + b, ldw, T21, ldw,
+                                             Wrp + (size_t)(r0 + b) * ldw + r0, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+            KBO_LAUNCH_CHECK(h);
+          }
+        if (P0 > 0) {
+          double* Trow = T + (size_t)P0 * ldw;
+          dgemm64_launch<false, EPI_STORE>(sinv, Pw, P0, P0, A + (size_t)P0 * lda, lda, W, ldw, Trow, ldw, 1.0, 0.0, KM_FROM_N, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+          dgemm64_launch<false, EPI_STORE>(sinv, Pw, P0, Pw, Wrp, ldw, Trow, ldw, W + (size_t)P0 * ldw, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+        }
+      }
+    }
+    return KBO_OK;
+  };
+  rc = body();
+  cudaEventRecord(e_hi, shi);
+  cudaEventRecord(e_upd, supd);
+  cudaEventRecord(e_inv, sinv);
+  cudaStreamWaitEvent(s, e_hi, 0);
+  cudaStreamWaitEvent(s, e_upd, 0);
+  cudaStreamWaitEvent(s, e_inv, 0);
+  if (tr[0]) {
+    cudaEventRecord(tr[1], shi);
+    cudaEventRecord(tr[2], supd);
+    cudaEventRecord(tr[3], sinv);
+    cudaStreamSynchronize(shi); cudaStreamSynchronize(supd); cudaStreamSynchronize(sinv);
+    float a = 0.f, b = 0.f, c = 0.f;
+    cudaEventElapsedTime(&a, tr[0], tr[1]); cudaEventElapsedTime(&b, tr[0], tr[2]); cudaEventElapsedTime(&c, tr[0], tr[3]);
+    fprintf(stderr, "[kbo fit v2 N=%d] chain stream done at %.3f ms, update stream at %.3f ms, inverse stream at %.3f ms\n", N, a, b, c);
+    for (auto& e : tr) cudaEventDestroy(e);
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // z = W·yn (one warp per row, lower triangle only) ; alpha = Wᵀ·z (one thread per column, coalesced across k)
 __global__ void trmv_lower_kernel(const double* __restrict__ W, int N, int ldw, const double* __restrict__ x, double* __restrict__ z) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -676,7 +836,11 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
     if (trace) cudaEventRecord(te[2], s);
     KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
   } else {
-    KBO_TRY(factor_and_invert(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s));
+    static const bool v1 = getenv("KBO_FIT_V1") != nullptr;   // A/B: the interleaved inverse without the look-ahead restructuring
+    if (v1)
+      KBO_TRY(factor_and_invert(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s));
+    else
+      KBO_TRY(factor_and_invert_v2(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s));
     if (trace) cudaEventRecord(te[2], s);
   }
   if (trace) cudaEventRecord(te[3], s);

@@ -84,7 +84,8 @@ struct kbo_handle {
   float last_rank_mu_err = 0.f;    // largest |μ̃ − μ| (normalised units) on the calibration rows of the last ranking sweep
   int last_unrefined = 0;          // 1: the last tensor-core sweep could not decide in FP64 (more near-ties than the cap)
   // ---- fit: Cholesky chain on a high-priority stream, row-panel inverse on a second one (fit.cu) ----------------------
-  cudaStream_t s_hi = nullptr, s_lo = nullptr, s_copy = nullptr;
+  cudaStream_t s_hi = nullptr, s_lo = nullptr, s_upd = nullptr, s_copy = nullptr;
+  DevBuf T2;                        // N × 256 panel-solve scratch of the look-ahead factorisation
   std::vector<cudaEvent_t> ev_panel;
   // ---- kbo_lml_batch: concurrent factorisations for several θ (fit.cu) --------------------------------------------------
   void* lml_lanes = nullptr;       // std::vector<LmlLane>*
