@@ -138,6 +138,14 @@ double kbo_last_rank_mu_error(kbo_handle* h);
  * 0 = no pruning pass.  kbo_last_prefix_survivors: how many candidates the last pruning pass kept (-1: it did not run).
  * The environment variable KBO_RANK_PREFIX sets the initial value. */
 int kbo_set_rank_prefix(kbo_handle* h, int tile_pairs);
+/* Lazy inverse (default on).  A tensor-core fit whose sweeps will prune forms only the rows of W = L^-1 the pruning pass reads
+ * (the first 512·tile_pairs; plus the 256×256 diagonal blocks of every panel, which the look-ahead factorisation needs anyway):
+ * alpha comes from two panel solves with L, the survivors' exact variances from panel solves with L (solve.cu), the lower bound
+ * on the maximum from the sigma -> 0 limit of the acquisition function.  N³/3 FP64 flop — a third of the fit — are not spent.
+ * The rest of W (and the full fp16 planes) are formed on demand by anything that needs them: array-returning sweeps, FP64-mode
+ * sweeps, kbo_fit_append / kbo_fit_rebase, kbo_lml_grad, kbo_fit_state, and the sweep itself when more than 64 candidates
+ * pass the prefix bound.  0 = always form W in kbo_fit.  Results do not depend on the setting beyond FP64 rounding. */
+int kbo_set_lazy_inverse(kbo_handle* h, int enabled);
 int kbo_last_prefix_survivors(kbo_handle* h);
 /* How the last tensor-core sweep decided its suggestion: 0 = FP64 evaluation of every candidate that could still be the
  * maximum; 1 = more such candidates than the cap (4096), FP64 decision among the best 4096 by fp32 value; 2 = not refined

@@ -26,6 +26,7 @@ int kbo_create(kbo_handle** out, int device) {
   if (const char* e = getenv("KBO_TC_PAIR")) h->tc_pair = atoi(e) != 0;
   if (const char* e = getenv("KBO_RANK_TC")) h->rank_tc = atoi(e) != 0;
   if (const char* e = getenv("KBO_RANK_PREFIX")) h->rank_prefix = atoi(e);
+  if (const char* e = getenv("KBO_LAZY_W")) h->lazy_w = atoi(e) != 0;
   if (prop.major != 10) {
     // sm_100a cubin only: refuse politely instead of failing at the first launch
     h->err = "libkbo is built for sm_100a (B200) only";
@@ -45,7 +46,7 @@ void kbo_destroy(kbo_handle* h) {
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
                     &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal,
                     &h->ks_center, &h->ks_Xh, &h->ks_Xl, &h->ks_nxal, &h->ks_Ch, &h->ks_Cl, &h->ks_nc, &h->rk_part, &h->cal_idx, &h->cal_x, &h->cal_mu,
-                    &h->comm_buf, &h->T2, &h->lml_yn, &h->lml_scal, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
+                    &h->comm_buf, &h->T2, &h->sv_B, &h->sv_V, &h->lml_yn, &h->lml_scal, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
                     &h->rk_sched[6].dev, &h->rk_sched[7].dev, &h->pr_list, &h->pr_x, &h->pr_mu, &h->pr_var, &h->cal_mu_rk, &h->cal_var_rk};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -98,6 +99,12 @@ int kbo_set_rank_prefix(kbo_handle* h, int tile_pairs) {
 }
 
 int kbo_last_prefix_survivors(kbo_handle* h) { return h ? h->last_prefix_survivors : KBO_ERR_INVALID; }
+
+int kbo_set_lazy_inverse(kbo_handle* h, int enabled) {
+  if (!h) return KBO_ERR_INVALID;
+  h->lazy_w = enabled != 0;
+  return KBO_OK;
+}
 
 int kbo_set_rank_tc(kbo_handle* h, int enabled) {
   if (!h) return KBO_ERR_INVALID;
@@ -201,6 +208,7 @@ int kbo_fit_state(kbo_handle* h, double* L_out, double* W_out, double* alpha_out
   if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_state: call kbo_fit first");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t N = h->N, ld = h->ld;
+  if (W_out) KBO_TRY(kbo_i_ensure_w(h, s));
   if (L_out) {
     KBO_CUDA(h, cudaMemcpy2DAsync(L_out, N * 8, h->K.p, ld * 8, N * 8, N, cudaMemcpyDeviceToDevice, s));
     KBO_TRY(kbo_i_zero_upper(h, L_out, (int)N, (int)N, s));
@@ -360,6 +368,7 @@ int kbo_debug_rank_pass(kbo_handle* h, const void* Xc, int32_t xc_dtype, int64_t
   KBO_TRY(kbo_reserve(h, h->Ksl, sizeof(__half) * (size_t)rows_pad * Npad));
   KBO_TRY(kbo_reserve(h, h->mun, sizeof(float) * (size_t)(rows_pad + 256)));
   KBO_TRY(kbo_reserve(h, h->varn, sizeof(float) * (size_t)(rows_pad + 256)));
+  KBO_TRY(kbo_i_ensure_w(h, s));
   if (mode == 1) {
     if (!h->ks_ready) KBO_FAIL(h, KBO_ERR_STATE, "kbo_debug_rank_pass: tensor-core K* operands not available (D > 128?)");
     KBO_TRY(kbo_i_tc_kstar(h, Xc, xc_dtype, M, (__half*)h->Ksh.p, (float*)h->mun.p, s));

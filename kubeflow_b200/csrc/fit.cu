@@ -487,7 +487,8 @@ static int factor_and_invert(kbo_handle* h, double* A, int N, int lda, double* W
 // inverse.  The trailing update is issued on a second stream as [next column block | rest]: the next panel's chain starts as
 // soon as its own column block is up to date, while the rest of the update and the inverse's row panels (third stream) fill
 // the SMs the chain leaves idle.
-static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s) {
+// `lead`: rows of the inverse to form (N: all of them).  The diagonal 256-blocks of W are formed for every panel either way.
+static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s, int lead) {
   const int OW = 256, n_panels = (N + OW - 1) / OW;
   KBO_TRY(fit_streams(h, 2 * n_panels + 8));
   if (!h->s_upd) {
@@ -590,7 +591,7 @@ static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double
       }
       // ---- the inverse's row panel (512 rows = two panels), third stream ------------------------------------------------------
       const int done = K0 + Wd;
-      if (done - rp0 >= RW || done >= N) {
+      if (rp0 < lead && (done - rp0 >= RW || done >= N)) {
         const int P0 = rp0, Pw = done - rp0;
         rp0 = done;
         KBO_CUDA(h, cudaStreamWaitEvent(sinv, ev_solve[P], 0));
@@ -747,6 +748,9 @@ int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double
 static int fit_finish(kbo_handle* h, cudaStream_t s, bool new_center) {
   const int N = h->N, ld = h->ld;
   const kbo_params* p = &h->prm;
+  if (!h->w_full) {
+    KBO_TRY(kbo_i_alpha_by_solves(h, s));   // alpha = L⁻ᵀ(L⁻¹ yn): two panel solves instead of Wᵀ(W yn)
+  } else {
   trmv_lower_kernel<<<(N + 7) / 8, 256, 0, s>>>((const double*)h->W.p, N, ld, (const double*)h->yn.p, (double*)h->z.p);
   KBO_LAUNCH_CHECK(h);
   {
@@ -758,6 +762,7 @@ static int fit_finish(kbo_handle* h, cudaStream_t s, bool new_center) {
     trmv_t_reduce_kernel<<<(N + 127) / 128, 128, 0, s>>>((const double*)h->T.p, N, nslab, (double*)h->alpha.p);
     KBO_LAUNCH_CHECK(h);
   }
+  }
   lml_kernel<<<1, 1024, 0, s>>>((const double*)h->K.p, N, ld, (const double*)h->yn.p, (const double*)h->alpha.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
   if (p->var_mode == KBO_VAR_TC_F16X3 || (p->var_mode == KBO_VAR_AUTO && N > 1024)) {
@@ -767,10 +772,12 @@ static int fit_finish(kbo_handle* h, cudaStream_t s, bool new_center) {
     KBO_TRY(kbo_reserve(h, h->Wl, sizeof(__half) * (size_t)Npad * Npad));
     unsigned long long* amax = (unsigned long long*)((double*)h->scal.p + 8);
     KBO_CUDA(h, cudaMemsetAsync(amax, 0, sizeof(unsigned long long), s));
-    absmax_kernel<<<h->sm_count * 4, 256, 0, s>>>((const double*)h->W.p, N, ld, amax);
+    // with a lazy inverse only the leading w_lead rows of W exist: planes (and their scale) cover those rows; kbo_i_ensure_w redoes both
+    const int Nw = h->w_full ? N : h->w_lead;
+    absmax_kernel<<<h->sm_count * 4, 256, 0, s>>>((const double*)h->W.p, Nw, ld, amax);
     KBO_LAUNCH_CHECK(h);
-    dim3 g((Npad + 255) / 256, Npad);
-    split_w_kernel<<<g, 256, 0, s>>>((const double*)h->W.p, N, ld, Npad, amax, (__half*)h->Wh.p, (__half*)h->Wl.p, (double*)h->scal.p + 6);
+    dim3 g((Npad + 255) / 256, h->w_full ? Npad : round_up(Nw, 256));
+    split_w_kernel<<<g, 256, 0, s>>>((const double*)h->W.p, Nw, ld, Npad, amax, (__half*)h->Wh.p, (__half*)h->Wl.p, (double*)h->scal.p + 6);
     KBO_LAUNCH_CHECK(h);
     // trial-side operands of the tensor-core K* kernel (alpha changes with every fit / append / rebase)
     KBO_TRY(kbo_i_tc_trials_prep(h, new_center, s));
@@ -831,6 +838,8 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   KBO_TRY(kbo_i_gram(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, s));
   if (trace) cudaEventRecord(te[1], s);
   static const bool serial = getenv("KBO_FIT_SERIAL") != nullptr;   // A/B: Cholesky, then recursive-doubling inverse, on one stream
+  h->w_full = true;
+  h->w_lead = N;
   if (serial) {
     KBO_TRY(kbo_i_potrf(h, (double*)h->K.p, N, ld, (int*)h->info.p, s));
     if (trace) cudaEventRecord(te[2], s);
@@ -839,8 +848,20 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
     static const bool v1 = getenv("KBO_FIT_V1") != nullptr;   // A/B: the interleaved inverse without the look-ahead restructuring
     if (v1)
       KBO_TRY(factor_and_invert(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s));
-    else
-      KBO_TRY(factor_and_invert_v2(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s));
+    else {
+      // Lazy inverse: a tensor-core fit whose sweeps will prune (kbo_set_rank_prefix) forms only the rows of W the pruning pass
+      // contracts with — the first 512·P1 — and leaves the rest to kbo_i_ensure_w, which runs if something asks for all of W.
+      int lead = N;
+      const bool planes = p->var_mode == KBO_VAR_TC_F16X3 || (p->var_mode == KBO_VAR_AUTO && N > 1024);
+      if (h->lazy_w && planes && h->rank_tc && h->rank_prefix != 0 && h->tc_fast && h->tc_refine && h->tc_pair && D <= 128) {
+        const int n_pairs = (h->Npad / 256 + 1) / 2;
+        const int P1 = h->rank_prefix < 0 ? (n_pairs + 7) / 8 : h->rank_prefix;
+        if (P1 >= 1 && P1 < n_pairs && P1 * 512 + 512 <= N) lead = round_up(P1 * 512, 512);
+      }
+      KBO_TRY(factor_and_invert_v2(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s, lead));
+      h->w_lead = lead < N ? lead : N;
+      h->w_full = lead >= N;
+    }
     if (trace) cudaEventRecord(te[2], s);
   }
   if (trace) cudaEventRecord(te[3], s);
@@ -857,6 +878,55 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
     for (auto& e : te) cudaEventDestroy(e);
   }
   h->fitted = true;
+  return KBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The rows of W a lazy fit left out (and the full fp16 planes): row panels [w_lead, N) of W_i,<i = −W_ii·(L_i,<i·W_<i,<i), the
+// 512-wide diagonal blocks first.  ~10 ms at N = 8192 — what the fit saved; paid only by callers that need all of W.
+int kbo_i_ensure_w(kbo_handle* h, cudaStream_t s) {
+  if (!h->fitted && !h->w_lead) return KBO_OK;
+  if (h->w_full) return KBO_OK;
+  const int N = h->N, ld = h->ld, OW = 256, RW = 512;
+  double* A = (double*)h->K.p;
+  double* W = (double*)h->W.p;
+  KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ld));
+  double* T = (double*)h->T.p;
+  for (int P0 = h->w_lead; P0 < N; P0 += RW) {
+    const int Pw = min(RW, N - P0);
+    double* Wrp = W + (size_t)P0 * ld + P0;
+    const double* Lrp = A + (size_t)P0 * ld + P0;
+    for (int b = OW; b < Pw; b *= 2)
+      for (int r0 = 0; r0 + b < Pw; r0 += 2 * b) {
+        const int rows2 = min(b, Pw - (r0 + b));
+        double* T21 = T + (size_t)(P0 + r0 + b) * ld + P0 + r0;
+        dgemm64_launch<false, EPI_STORE>(s, rows2, b, b, Lrp + (size_t)(r0 + b) * ld + r0, ld, Wrp + (size_t)r0 * ld + r0, ld, T21, ld, 1.0, 0.0, KM_FROM_N, 0,
+                                         TS_NONE);
+        KBO_LAUNCH_CHECK(h);
+        dgemm64_launch<false, EPI_STORE>(s, rows2, b, rows2, Wrp + (size_t)(r0 + b) * ld + r0 + b, ld, T21, ld, Wrp + (size_t)(r0 + b) * ld + r0, ld, -1.0,
+                                         0.0, KM_UPTO_M, 0, TS_NONE);
+        KBO_LAUNCH_CHECK(h);
+      }
+    if (P0 > 0) {
+      double* Trow = T + (size_t)P0 * ld;
+      dgemm64_launch<false, EPI_STORE>(s, Pw, P0, P0, A + (size_t)P0 * ld, ld, W, ld, Trow, ld, 1.0, 0.0, KM_FROM_N, 0, TS_NONE);
+      KBO_LAUNCH_CHECK(h);
+      dgemm64_launch<false, EPI_STORE>(s, Pw, P0, Pw, Wrp, ld, Trow, ld, W + (size_t)P0 * ld, ld, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+      KBO_LAUNCH_CHECK(h);
+    }
+  }
+  h->w_full = true;
+  h->w_lead = N;
+  if (h->have_planes) {
+    const int Npad = h->Npad;
+    unsigned long long* amax = (unsigned long long*)((double*)h->scal.p + 8);
+    KBO_CUDA(h, cudaMemsetAsync(amax, 0, sizeof(unsigned long long), s));
+    absmax_kernel<<<h->sm_count * 4, 256, 0, s>>>((const double*)h->W.p, N, ld, amax);
+    KBO_LAUNCH_CHECK(h);
+    dim3 g((Npad + 255) / 256, Npad);
+    split_w_kernel<<<g, 256, 0, s>>>((const double*)h->W.p, N, ld, Npad, amax, (__half*)h->Wh.p, (__half*)h->Wl.p, (double*)h->scal.p + 6);
+    KBO_LAUNCH_CHECK(h);
+  }
   return KBO_OK;
 }
 
@@ -1068,6 +1138,7 @@ __global__ void append_wrow_kernel(const double* __restrict__ wtl, int row, int 
 
 int kbo_i_fit_append(kbo_handle* h, const double* x_dev, double y, cudaStream_t s) {
   if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_append: call kbo_fit first");
+  KBO_TRY(kbo_i_ensure_w(h, s));   // the bordered row is l = W·k
   const int row = h->N, ld = h->ld, D = h->D;
   if (row + 1 > ld) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_append: no room (N=%d fills its %d-row pitch): call kbo_fit with the whole history", row, ld);
   double* Krow = (double*)h->K.p + (size_t)row * ld;
@@ -1117,6 +1188,7 @@ __global__ void clear_info_above_kernel(int* info, int n_keep) {
 int kbo_i_fit_rebase(kbo_handle* h, int n_keep, const double* y_dev, cudaStream_t s) {
   if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_fit_rebase: call kbo_fit first");
   if (n_keep < 1 || n_keep > h->N) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_fit_rebase: need 1 <= n_keep <= N=%d (got %d)", h->N, n_keep);
+  KBO_TRY(kbo_i_ensure_w(h, s));   // keeps the bookkeeping simple: a rebased history carries all of W
   if (y_dev) KBO_CUDA(h, cudaMemcpyAsync(h->yraw.p, y_dev, sizeof(double) * n_keep, cudaMemcpyDeviceToDevice, s));
   h->N = n_keep;
   h->Npad = round_up(n_keep, 256);

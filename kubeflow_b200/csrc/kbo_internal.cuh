@@ -87,6 +87,11 @@ struct kbo_handle {
   cudaStream_t s_hi = nullptr, s_lo = nullptr, s_upd = nullptr, s_copy = nullptr;
   DevBuf T2;                        // N × 256 panel-solve scratch of the look-ahead factorisation
   std::vector<cudaEvent_t> ev_panel;
+  // ---- lazy inverse (fit.cu, solve.cu): the product path never needs all of W = L⁻¹ -----------------------------------------
+  bool lazy_w = true;              // kbo_set_lazy_inverse: tensor-core fits form only the leading rows of W the pruning pass reads
+  bool w_full = true;              // all rows of W (and the full fp16 planes) exist
+  int w_lead = 0;                  // rows of W formed so far (the diagonal 256-blocks exist for every panel)
+  DevBuf sv_B, sv_V;               // N × 8 right-hand sides / solutions of the panel solves
   // ---- kbo_lml_batch: concurrent factorisations for several θ (fit.cu) --------------------------------------------------
   void* lml_lanes = nullptr;       // std::vector<LmlLane>*
   DevBuf lml_yn, lml_scal;
@@ -153,6 +158,10 @@ int kbo_i_fit(kbo_handle* h, const double* X_dev, const double* y_dev, int N, in
 int kbo_i_lml_batch(kbo_handle* h, const double* X_dev, const double* y_dev, int N, int D, int G, const kbo_params* params, double* lml_host,
                     int32_t* info_host, cudaStream_t s);
 void kbo_i_lml_batch_free(kbo_handle* h);
+int kbo_i_ensure_w(kbo_handle* h, cudaStream_t s);   // form the rest of W and the full planes if the fit left them out
+// ---- solve.cu ----------------------------------------------------------------------------------
+int kbo_i_alpha_by_solves(kbo_handle* h, cudaStream_t s);
+int kbo_i_variance_by_solves(kbo_handle* h, const double* Ks, int n, double* varn64, cudaStream_t s);
 // ---- sweep.cu ----------------------------------------------------------------------------------
 int kbo_i_sweep(kbo_handle* h, const void* Xc_dev, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out,
                 double* acq_out, kbo_best* best_dev, cudaStream_t s);
@@ -171,4 +180,4 @@ int kbo_i_tc_rank(kbo_handle* h, const __half* Ksh, int64_t rows, const __half* 
 // ---- tc_var.cu ---------------------------------------------------------------------------------
 // var_n[m] = amp − Σ_j (Σ_k K*[m,k] W[j,k])²  for the rows of one chunk, on tcgen05 tensor cores.
 int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl,
-                      int Npad, double w_scale_inv, double amp, float* var_n_out, int k_span, cudaStream_t s, int nprod = 3);
+                      int Npad, double w_scale_inv, double amp, float* var_n_out, int k_span, cudaStream_t s, int nprod = 3, int jtiles = -1);

@@ -138,6 +138,7 @@ __global__ void lml_grad_reduce_kernel(const double* __restrict__ partial, int n
 extern "C" int kbo_lml_grad(kbo_handle* h, double* grad_host, int32_t n_out, void* stream) {
   if (!h) return KBO_ERR_INVALID;
   if (!h->fitted) KBO_FAIL(h, KBO_ERR_STATE, "kbo_lml_grad: call kbo_fit first");
+  KBO_TRY(kbo_i_ensure_w(h, (cudaStream_t)stream));   // K⁻¹ = WᵀW
   const int N = h->N, D = h->D, ld = h->ld, P = (int)h->inv_ls.size(), ncomp = 2 + P;
   if (!grad_host || n_out != ncomp) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_lml_grad: output must hold 2 + n_length_scale = %d doubles", ncomp);
   cudaStream_t s = (cudaStream_t)stream;

@@ -773,13 +773,19 @@ static int refine_evaluate(kbo_handle* h, const void* Xc, int xc_dtype, int n, i
   KBO_LAUNCH_CHECK(h);
   refine_mu_kernel<<<n, 256, 0, s>>>((const double*)h->Ks64.p, ld, N, (const double*)h->alpha.p, mun64);
   KBO_LAUNCH_CHECK(h);
-  if (n <= 2)   // the usual case: one contender — no point carrying eight accumulators through the triangle of W
-    refine_var_kernel<1><<<dim3(njt, n), 256, 0, s>>>((const double*)h->W.p, ld, N, (const double*)h->Ks64.p, n, (double*)h->part.p, njt);
-  else
-    refine_var_kernel<8><<<dim3(njt, (n + 7) / 8), 256, 0, s>>>((const double*)h->W.p, ld, N, (const double*)h->Ks64.p, n, (double*)h->part.p, njt);
-  KBO_LAUNCH_CHECK(h);
-  var_from_parts_kernel<<<(n + 255) / 256, 256, 0, s>>>((const double*)h->part.p, n, njt, h->prm.amplitude, varn64);
-  KBO_LAUNCH_CHECK(h);
+  if (!h->w_full && n <= 64) {
+    // lazy inverse: ‖L⁻¹k*‖² by panel solves with the factor itself (solve.cu) — no W
+    KBO_TRY(kbo_i_variance_by_solves(h, (const double*)h->Ks64.p, n, varn64, s));
+  } else {
+    KBO_TRY(kbo_i_ensure_w(h, s));
+    if (n <= 2)   // the usual case: one contender — no point carrying eight accumulators through the triangle of W
+      refine_var_kernel<1><<<dim3(njt, n), 256, 0, s>>>((const double*)h->W.p, ld, N, (const double*)h->Ks64.p, n, (double*)h->part.p, njt);
+    else
+      refine_var_kernel<8><<<dim3(njt, (n + 7) / 8), 256, 0, s>>>((const double*)h->W.p, ld, N, (const double*)h->Ks64.p, n, (double*)h->part.p, njt);
+    KBO_LAUNCH_CHECK(h);
+    var_from_parts_kernel<<<(n + 255) / 256, 256, 0, s>>>((const double*)h->part.p, n, njt, h->prm.amplitude, varn64);
+    KBO_LAUNCH_CHECK(h);
+  }
   refine_best_kernel<<<1, 1024, 0, s>>>(mun64, varn64, list, n, h->prm.acq, scal, h->prm.xi, h->prm.kappa, goff, best_dev);
   KBO_LAUNCH_CHECK(h);
   return KBO_OK;
@@ -981,7 +987,144 @@ survivor_final_kernel(const float* __restrict__ mun, const float* __restrict__ v
   }
 }
 
+static int calibration_rows(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int* cal_n_out, cudaStream_t s, int jtiles = -1);
+
+// lower bound of the acquisition value over sigma² in (0, var_ub] at mean mu_n (normalised): EI and LCB grow with sigma, so the
+// bound is their sigma -> 0 limit (max(improvement, 0) and −mu: no variance needed at all); PI falls with sigma where the
+// improvement is positive, so its bound there sits at var_ub
+__device__ __forceinline__ float acq_lower_f32(int acq, float mu_n, float var_ub, float ym, float ys, float yo, float x, float kp) {
+  const float mu = fmaf(ys, mu_n, ym);
+  if (acq == KBO_ACQ_LCB) return -mu;
+  const float imp = yo - x - mu;
+  if (acq == KBO_ACQ_EI) return fmaxf(imp, 0.f);
+  return imp > 0.f ? acq_any_f32(acq, mu_n, var_ub, ym, ys, yo, x, kp) : 0.f;
+}
+__global__ void __launch_bounds__(256)
+grid_lower_bound_kernel(const float* __restrict__ mun, const float* __restrict__ var_ub, int64_t M, int acq, const double* __restrict__ scal, double xi,
+                        double kappa, float* __restrict__ fs) {
+  const float ym = (float)scal[S_YMEAN], ys = (float)scal[S_YSTD], yo = (float)scal[S_YOPT], x = (float)xi, kp = (float)kappa;
+  const float E = fs[0], Em = fs[3];
+  float best = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256) {
+    const float lb = acq_lower_f32(acq, mun[i] + Em, fmaxf(var_ub[i], 0.f) + E, ym, ys, yo, x, kp);
+    if (lb > best) best = lb;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best > -INFINITY) atomicMax((unsigned*)fs + 1, ordered_bits(best - 1e-5f * fmaxf(1.f, fabsf(best))));
+}
+// E, Emu from the calibration rows (ranking arithmetic vs exact, both over the same prefix of the trial tiles); lower bound reset
+__global__ void __launch_bounds__(1024)
+calib_prefix_kernel(const float* __restrict__ v_rk, const float* __restrict__ v_ex, const float* __restrict__ mu_rk, const float* __restrict__ mu_ex, int n,
+                    float* __restrict__ fs) {
+  __shared__ float red[1024], redm[1024];
+  float m = 0.f, mm = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    m = fmaxf(m, fabsf(v_rk[i] - v_ex[i]));
+    mm = fmaxf(mm, fabsf(mu_rk[i] - mu_ex[i]));
+  }
+  red[threadIdx.x] = m;
+  redm[threadIdx.x] = mm;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+      redm[threadIdx.x] = fmaxf(redm[threadIdx.x], redm[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    fs[0] = 8.f * red[0] + 1e-6f;
+    fs[2] = red[0];
+    fs[3] = 8.f * redm[0] + 1e-7f;
+    fs[4] = redm[0];
+    ((unsigned*)fs)[1] = 0u;
+  }
+}
+
 #define KBO_PRUNE_CAP 16384
+#define KBO_SOLVE_CAP 64
+// The pruning sweep of a LAZY fit (only the leading rows of W exist): everything it touches is the factor L, alpha, and the
+// leading block of W.  Calibration: exact mean (FP64 K* kernel) and exact PREFIX variance (three products over the prefix's
+// tiles) against the ranking arithmetic over the same prefix -> E, Emu.  Lower bound on the maximum: the sigma -> 0 limit of
+// the acquisition function over the whole grid (for EI: the largest predicted improvement) — free.  Candidates whose prefix
+// upper bound reaches it (normally a handful) are evaluated EXACTLY in FP64 by panel solves with L and the first-index
+// argmax is taken over those values: no ranking pass, no interval test.  *pruned = 0 (more than 64 such candidates, or no
+// usable lower bound): the caller forms the rest of W and runs the sweep of a full fit.
+static int prune_sweep_lead(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, int64_t chunk, kbo_best* best_dev, int* pruned,
+                            cudaStream_t s) {
+  *pruned = 0;
+  const int D = h->D, Npad = h->Npad;
+  const size_t esz = xc_dtype == KBO_F64 ? 8 : 4;
+  const double* scal = (const double*)h->scal.p;
+  const int n_pairs = (Npad / 256 + 1) / 2;
+  int P1 = h->rank_prefix < 0 ? (n_pairs + 7) / 8 : h->rank_prefix;
+  if (P1 < 1 || P1 >= n_pairs || P1 * 512 > h->w_lead) return KBO_OK;
+  const int prefix_cols = P1 * 512;
+  KBO_TRY(kbo_reserve(h, h->refine, sizeof(int) * (KBO_REFINE_CAP + 16)));
+  int* count = (int*)h->refine.p + KBO_REFINE_CAP;
+  float* fs = (float*)(count + 4);
+  KBO_TRY(kbo_reserve(h, h->pr_list, sizeof(int) * (KBO_PRUNE_CAP + 16)));
+  int* plist = (int*)h->pr_list.p;
+  int* pcount = plist + KBO_PRUNE_CAP;
+  int cal_n = 0;
+  {
+    KBO_TIME_BEGIN(ev_cal, ev_cal_used);
+    KBO_TRY(calibration_rows(h, Xc, xc_dtype, M, &cal_n, s, 2 * P1));   // cal_mu exact, var_cal = exact prefix bound
+    const int64_t cal_pad = round_up64(cal_n, 256);
+    KBO_TRY(kbo_reserve(h, h->cal_mu_rk, sizeof(float) * (size_t)(cal_pad + 256)));
+    KBO_TRY(kbo_reserve(h, h->cal_var_rk, sizeof(float) * (size_t)(cal_pad + 256)));
+    KBO_TRY(kbo_i_tc_kstar(h, h->cal_x.p, KBO_F64, cal_n, (__half*)h->Ksh.p, (float*)h->cal_mu_rk.p, s, prefix_cols));
+    KBO_TRY(kbo_i_tc_rank(h, (const __half*)h->Ksh.p, cal_pad, (const __half*)h->Wh.p, Npad, h->prm.amplitude, (float*)h->cal_var_rk.p, s, 0, P1));
+    calib_prefix_kernel<<<1, 1024, 0, s>>>((const float*)h->cal_var_rk.p, (const float*)h->var_cal.p, (const float*)h->cal_mu_rk.p, (const float*)h->cal_mu.p,
+                                           cal_n, fs);
+    KBO_LAUNCH_CHECK(h);
+    KBO_TIME_END();
+  }
+  for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+    const int64_t rows = (M - c0 < chunk) ? (M - c0) : chunk;
+    const unsigned char* xc = (const unsigned char*)Xc + (size_t)c0 * D * esz;
+    h->tim.chunks++;
+    {
+      KBO_TIME_BEGIN(ev_cross, ev_cross_used);
+      KBO_TRY(kbo_i_tc_kstar(h, xc, xc_dtype, rows, (__half*)h->Ksh.p, (float*)h->mun.p + c0, s, prefix_cols));
+      KBO_TIME_END();
+    }
+    {
+      KBO_TIME_BEGIN(ev_var, ev_var_used);
+      KBO_TRY(kbo_i_tc_rank(h, (const __half*)h->Ksh.p, round_up64(rows, 256), (const __half*)h->Wh.p, Npad, h->prm.amplitude, (float*)h->varn.p + c0, s, 0,
+                            P1));
+      KBO_TIME_END();
+    }
+  }
+  KBO_TIME_BEGIN(ev_acq, ev_acq_used);
+  KBO_CUDA(h, cudaMemsetAsync(pcount, 0, sizeof(int), s));
+  grid_lower_bound_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs);
+  KBO_LAUNCH_CHECK(h);
+  prefix_survivor_kernel<<<acq_grid(h, M), 256, 0, s>>>((const float*)h->mun.p, (const float*)h->varn.p, M, h->prm.acq, scal, h->prm.xi, h->prm.kappa, fs, plist,
+                                                       pcount, KBO_PRUNE_CAP);
+  KBO_LAUNCH_CHECK(h);
+  struct { int n; int pad[3]; float fs[8]; } host;
+  int n1 = 0;
+  KBO_CUDA(h, cudaMemcpyAsync(&n1, pcount, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaMemcpyAsync(&host, count, sizeof host, cudaMemcpyDeviceToHost, s));
+  KBO_CUDA(h, cudaStreamSynchronize(s));
+  h->last_prefix_survivors = n1;
+  h->last_rank_err = host.fs[2];
+  h->last_rank_mu_err = host.fs[4];
+  if (n1 < 1 || n1 > KBO_SOLVE_CAP) {
+    KBO_TIME_END();
+    return KBO_OK;
+  }
+  h->last_contenders = n1;
+  h->last_unrefined = 0;
+  KBO_TRY(refine_evaluate(h, Xc, xc_dtype, n1, plist, pcount, goff, best_dev, s));
+  KBO_TIME_END();
+  *pruned = 1;
+  return KBO_OK;
+}
+
+
 // The pruning sweep.  *pruned = 1: best_dev holds the FP64-decided suggestion.  *pruned = 0: too many candidates survive the
 // prefix bound (or the interval test) — the caller runs the full ranking pass; the calibration buffers stay valid for it.
 static int prune_sweep(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, int cal_n, int64_t chunk, kbo_best* best_dev, int* pruned,
@@ -1115,7 +1258,7 @@ static int fast_pick(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int
 // The stratified calibration rows of a ranking sweep through the FP64 K* kernel and the three-product contraction:
 // cal_idx (row indices), cal_mu (normalised mean), var_cal (normalised variance).  Uses the K* scratch planes, so it runs
 // before the first chunk.
-static int calibration_rows(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int* cal_n_out, cudaStream_t s) {
+static int calibration_rows(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int* cal_n_out, cudaStream_t s, int jtiles) {
   // one wave of the three-product cluster kernel: 74 clusters × 128 rows on a B200.  The bounds are 8 × the largest error seen on
   // these rows; the errors are sums of thousands of rounding terms (light-tailed: the maximum over 1e6 rows of a Gaussian exceeds
   // the maximum over 1e4 by ~1.2×), so the sample size is not what the margin hinges on — its being stratified is.
@@ -1135,8 +1278,9 @@ static int calibration_rows(kbo_handle* h, const void* Xc, int xc_dtype, int64_t
   KBO_LAUNCH_CHECK(h);
   KBO_TRY((launch_cross<double, float, 1>(h, (const double*)h->cal_x.p, cal_n, cal_pad, nullptr, 0, (__half*)h->Ksh.p, (__half*)h->Ksl.p,
                                           (float*)h->cal_mu.p, s)));
+  // jtiles > 0: the exact variance bound from a PREFIX of the trial tiles (needs the leading rows of W only)
   KBO_TRY(kbo_i_tc_variance(h, (const __half*)h->Ksh.p, (const __half*)h->Ksl.p, cal_pad, (const __half*)h->Wh.p, (const __half*)h->Wl.p, h->Npad,
-                            0.0, h->prm.amplitude, (float*)h->var_cal.p, h->prm.tc_k_span, s, 3));
+                            0.0, h->prm.amplitude, (float*)h->var_cal.p, h->prm.tc_k_span, s, 3, jtiles));
   *cal_n_out = cal_n;
   return KBO_OK;
 }
@@ -1210,12 +1354,22 @@ static int sweep_impl(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, in
     KBO_TRY(kbo_reserve(h, h->varn, sizeof(double) * (size_t)M));
   }
   h->tim.chunks = 0;
+  if (!force_three) h->last_prefix_survivors = -1;   // (a three-product redo keeps what the failed ranking attempt recorded)
+  if (!h->w_full) {
+    // a lazy fit: try the sweep that needs the leading rows of W only; anything else forms the rest first
+    if (tc && rank_tc && h->rank_prefix != 0) {
+      int pruned = 0;
+      KBO_TRY(prune_sweep_lead(h, Xc, xc_dtype, M, goff, chunk, best_dev, &pruned, s));
+      if (pruned) return KBO_OK;
+      h->tim.chunks = 0;
+    }
+    KBO_TRY(kbo_i_ensure_w(h, s));
+  }
   if (fast) {   // the calibration rows borrow the K* scratch, so they go first
     KBO_TIME_BEGIN(ev_cal, ev_cal_used);
     KBO_TRY(calibration_rows(h, Xc, xc_dtype, M, &cal_n, s));
     KBO_TIME_END();
   }
-  if (!force_three) h->last_prefix_survivors = -1;   // (a three-product redo keeps what the failed ranking attempt recorded)
   if (rank_tc && h->rank_prefix != 0) {
     int pruned = 0;
     KBO_TRY(prune_sweep(h, Xc, xc_dtype, M, goff, cal_n, chunk, best_dev, &pruned, s));

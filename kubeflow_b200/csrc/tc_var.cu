@@ -401,7 +401,8 @@ int encode_map(kbo_handle* h, CUtensorMap* out, const void* base, uint64_t inner
 }
 
 int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl, int Npad,
-              const double* w_scale_dev, double amp, float* var_out, double* sumsq_out, int k_span, cudaStream_t s, int nprod = 3) {
+              const double* w_scale_dev, double amp, float* var_out, double* sumsq_out, int k_span, cudaStream_t s, int nprod = 3, int jtiles = -1) {
+  const int n_jt = (jtiles > 0 && jtiles < Npad / TC_BN) ? jtiles : Npad / TC_BN;   // a prefix of the trial tiles: an upper bound on the variance
   if (nprod != 3 && !h->tc_pair) KBO_FAIL(h, KBO_ERR_STATE, "tc_variance: the one-product ranking pass needs the cluster kernel (kbo_set_tc_pair)");
   if (rows % TC_BM != 0 || Npad % TC_BN != 0) KBO_FAIL(h, KBO_ERR_INVALID, "tc_variance: rows %% 128 and Npad %% 256 must be 0");
   // TMEM accumulation rounds toward zero (one-sided error ≈ 5e-9·k_span relative on Σv², profiles/README.md): 128 puts the
@@ -425,14 +426,14 @@ int tc_launch(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows,
     KBO_TRY(encode_map(h, &tmAh64, Ksh, (uint64_t)Npad, (uint64_t)rows, 64));
     KBO_TRY(encode_map(h, &tmAl64, Ksl, (uint64_t)Npad, (uint64_t)rows, 64));
     KBO_TRY(kbo_reserve(h, h->part, sizeof(double) * 2 * (size_t)rows));
-    tc_variance_pair_kernel<<<(unsigned)(2 * (rows / TC_BM)), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh64, tmAl64, tmBh, tmBl, Npad / TC_BN, span_chunks,
+    tc_variance_pair_kernel<<<(unsigned)(2 * (rows / TC_BM)), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh64, tmAl64, tmBh, tmBl, n_jt, span_chunks,
                                                                                              (double*)h->part.p, rows, nprod);
     KBO_LAUNCH_CHECK(h);
     tc_pair_finish_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>((const double*)h->part.p, rows, w_scale_dev, amp, var_out, sumsq_out);
     KBO_LAUNCH_CHECK(h);
     return KBO_OK;
   }
-  tc_variance_kernel<<<(unsigned)(rows / TC_BM), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh, tmAl, tmBh, tmBl, Npad / TC_BN, span_chunks, w_scale_dev,
+  tc_variance_kernel<<<(unsigned)(rows / TC_BM), TC_THREADS, TC_SMEM_BYTES, s>>>(tmAh, tmAl, tmBh, tmBl, n_jt, span_chunks, w_scale_dev,
                                                                                 amp, var_out, sumsq_out);
   KBO_LAUNCH_CHECK(h);
   return KBO_OK;
@@ -465,8 +466,8 @@ int kbo_i_encode_map_f16(kbo_handle* h, CUtensorMap* out, const void* base, uint
 }
 
 int kbo_i_tc_variance(kbo_handle* h, const __half* Ksh, const __half* Ksl, int64_t rows, const __half* Wh, const __half* Wl, int Npad,
-                      double /*unused*/, double amp, float* var_n_out, int k_span, cudaStream_t s, int nprod) {
-  return tc_launch(h, Ksh, Ksl, rows, Wh, Wl, Npad, (const double*)h->scal.p + 6, amp, var_n_out, nullptr, k_span, s, nprod);
+                      double /*unused*/, double amp, float* var_n_out, int k_span, cudaStream_t s, int nprod, int jtiles) {
+  return tc_launch(h, Ksh, Ksl, rows, Wh, Wl, Npad, (const double*)h->scal.p + 6, amp, var_n_out, nullptr, k_span, s, nprod, jtiles);
 }
 
 // Raw entry for the kernel-level parity test: caller supplies fp16 planes and the scale pair on the device.

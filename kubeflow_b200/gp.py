@@ -29,7 +29,7 @@ class GPEngine:
                  noise: float = 1e-10, acq: str = "ei", xi: float = 0.01, kappa: float = 1.96,
                  normalize_y: bool = True, var_mode: str = "auto", tc_k_span: int = 0, scratch_limit: int | None = None,
                  tc_pair: bool | None = None, tc_refine: bool | None = None, tc_fast: bool | None = None,
-                 rank_tc: bool | None = None, rank_prefix: int | None = None):
+                 rank_tc: bool | None = None, rank_prefix: int | None = None, lazy_inverse: bool | None = None):
         if kernel not in L.KERNELS:
             raise ValueError(f"kernel must be one of {sorted(L.KERNELS)}, got {kernel!r}")
         if acq not in L.ACQS:
@@ -59,6 +59,8 @@ class GPEngine:
             L.check(self.lib, self._h, self.lib.kbo_set_tc_fast(self._h, int(bool(tc_fast))))
         if rank_tc is not None:
             L.check(self.lib, self._h, self.lib.kbo_set_rank_tc(self._h, int(bool(rank_tc))))
+        if lazy_inverse is not None:
+            L.check(self.lib, self._h, self.lib.kbo_set_lazy_inverse(self._h, int(bool(lazy_inverse))))
         if rank_prefix is not None:
             L.check(self.lib, self._h, self.lib.kbo_set_rank_prefix(self._h, int(rank_prefix)))
         self._best_dev = torch.empty(4, dtype=torch.float64, device=f"cuda:{self.device}")

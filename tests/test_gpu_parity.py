@@ -823,3 +823,40 @@ def test_lml_batch_matches_one_fit_per_theta_and_the_oracle(N, D, kind):
     torch.cuda.synchronize(); t1 = (time.perf_counter() - t0) / 3
     print(f"\nN={N}: lml_batch of {len(thetas)} thetas {tb * 1e3:.2f} ms, one fit {t1 * 1e3:.2f} ms (ratio {tb / t1:.2f})")
     eng.close()
+
+
+@pytest.mark.parametrize("N,M,D,kind,acq", [(2048, 30000, 32, "matern52", "ei"), (3000, 20000, 12, "matern52", "lcb"), (2600, 25000, 8, "rbf", "ei")])
+def test_lazy_inverse_sweep_matches_the_full_fit(N, M, D, kind, acq):
+    """kbo_set_lazy_inverse (default): a tensor-core fit forms only the leading rows of W; alpha, the survivors' exact variances
+    and the lower bound on the maximum come from panel solves with L and from the sigma -> 0 limit.  The suggestion must equal
+    the eager fit's (W formed) and the FP64 engine's to FP64 rounding; everything that needs all of W (arrays, append, LML
+    gradient, state) still works afterwards and agrees with the eager engine."""
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    kw = dict(kind=kind, acq=acq, **th)
+    lazy = _engine(kw, "tc"); lazy.tell(X, y)
+    eager = _engine(kw, "tc", lazy_inverse=False); eager.tell(X, y)
+    e64 = _engine(kw, "f64"); e64.tell(X, y)
+    il, ie = lazy.fit_info(), eager.fit_info()
+    assert abs(il["lml"] - ie["lml"]) <= 1e-9 * max(1.0, abs(ie["lml"]))       # alpha by solves vs Wᵀ(W yn)
+    bl, be, b6 = lazy.ask(Xc), eager.ask(Xc), e64.ask(Xc)
+    print(f"\\nN={N} {kind}/{acq}: lazy kept {lazy.last_prefix_survivors()} (decided among {lazy.last_contenders()}), eager kept {eager.last_prefix_survivors()}")
+    assert bl.index == be.index == b6.index
+    assert abs(bl.value - b6.value) <= 1e-10 * max(1.0, abs(b6.value)) and abs(bl.value - be.value) <= 1e-10 * max(1.0, abs(be.value))
+    assert abs(bl.mu - b6.mu) <= 1e-9 and abs(bl.std - b6.std) <= 1e-8
+    assert lazy.last_unrefined() == 0
+    # consumers of the whole inverse after a lazy fit
+    for a_, b_ in zip(lazy.state(), eager.state()):
+        np.testing.assert_allclose(a_.cpu().numpy(), b_.cpu().numpy(), rtol=0, atol=5e-10)
+    gl, ge = lazy.lml_grad()[1], eager.lml_grad()[1]
+    np.testing.assert_allclose(gl, ge, rtol=1e-8, atol=1e-8)
+    _, _, _, al = lazy.ask(Xc[:3000], return_arrays=True)
+    _, _, _, ae = eager.ask(Xc[:3000], return_arrays=True)
+    np.testing.assert_allclose(al.cpu().numpy(), ae.cpu().numpy(), rtol=0, atol=1e-9)
+    lazy.tell(X[:N - 2], y[:N - 2]); eager.tell(X[:N - 2], y[:N - 2])             # lazy again, then append forms W
+    for i in (N - 2, N - 1):
+        lazy.append(X[i], y[i]); eager.append(X[i], y[i])
+    b2l, b2e = lazy.ask(Xc), eager.ask(Xc)
+    assert b2l.index == b2e.index and abs(b2l.value - b2e.value) <= 1e-9
+    for e in (lazy, eager, e64):
+        e.close()
