@@ -23,6 +23,13 @@ def _engine(g_or_kw, var_mode, **over):
     return GPEngine(0, **kw)
 
 
+def _same(a, b, tol=1e-10):
+    """Same suggestion: identical index, value / mu / std equal to FP64 rounding.  (Bit-equality held while every path ended in the
+    same W-based FP64 evaluation; a lazy fit evaluates the survivors by panel solves with L, an eager one through W = L⁻¹.)"""
+    return (a.index == b.index and abs(a.value - b.value) <= tol * max(1.0, abs(b.value)) and abs(a.mu - b.mu) <= tol * max(1.0, abs(b.mu))
+            and abs(a.std - b.std) <= 1e-8 * max(1.0, abs(b.std)))
+
+
 def _check_argmax(best, acq_ref, tol):
     i_ref = int(np.argmax(acq_ref))
     if best.index != i_ref:
@@ -300,8 +307,8 @@ def test_tc_mode_suggestion_is_refined_in_fp64(golden):
     assert 1 <= n <= 4096
     i_ref = int(np.argmax(golden["acq"]))
     assert btc.index == b64.index == i_ref
-    assert abs(btc.value - b64.value) <= 1e-12 * max(1.0, abs(b64.value)) and abs(btc.value - golden["acq"][i_ref]) <= TOL_F64
-    assert abs(btc.mu - b64.mu) <= 1e-12 * max(1.0, abs(b64.mu)) and abs(btc.std - b64.std) <= 1e-10
+    assert abs(btc.value - b64.value) <= 1e-10 * max(1.0, abs(b64.value)) and abs(btc.value - golden["acq"][i_ref]) <= TOL_F64
+    assert abs(btc.mu - b64.mu) <= 1e-10 * max(1.0, abs(b64.mu)) and abs(btc.std - b64.std) <= 1e-10
     raw = _engine(golden, "tc", tc_refine=False); raw.tell(golden["X"], golden["y"])
     braw = raw.ask(golden["Xc"])
     _check_argmax(braw, golden["acq"], 5e-5 if golden["acq_kind"] == "lcb" else TOL_TC)
@@ -568,8 +575,8 @@ def test_one_product_ranking_pass_returns_the_same_suggestion(N, M, D, kind, acq
     slow = _engine(kw, "tc", tc_fast=False); slow.tell(X, y)
     e64 = _engine(kw, "f64"); e64.tell(X, y)
     bf, bs, b6 = fast.ask(Xc), slow.ask(Xc), e64.ask(Xc)
-    assert (bf.index, bf.value, bf.mu, bf.std) == (bs.index, bs.value, bs.mu, bs.std)
-    assert bf.index == b6.index and abs(bf.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value))
+    assert _same(bf, bs)
+    assert bf.index == b6.index and abs(bf.value - b6.value) <= 1e-10 * max(1.0, abs(b6.value))
     assert 1 <= fast.last_contenders() <= 4096
     assert 1e-7 < fast.last_rank_error() < 0.5           # fp16 hi planes only: |d sigma²| ~ 1e-4 … 1e-3, 3e-2 on ill-conditioned low-D fits
     assert slow.last_rank_error() == 0.0
@@ -672,11 +679,11 @@ def test_tensor_core_ranking_pass_returns_the_fp64_suggestion(N, M, D, kind, acq
     slow = _engine(kw, "tc", tc_fast=False); slow.tell(X, y)
     e64 = _engine(kw, "f64"); e64.tell(X, y)
     bn, bf, bo, bs, b6 = new.ask(Xc), full.ask(Xc), old.ask(Xc), slow.ask(Xc), e64.ask(Xc)
-    assert (bn.index, bn.value, bn.mu, bn.std) == (bf.index, bf.value, bf.mu, bf.std)
+    assert _same(bn, bf)
     assert full.last_prefix_survivors() == -1 and new.last_prefix_survivors() >= 1
     full.close()
-    assert (bn.index, bn.value, bn.mu, bn.std) == (bo.index, bo.value, bo.mu, bo.std) == (bs.index, bs.value, bs.mu, bs.std)
-    assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value))
+    assert _same(bn, bo) and _same(bn, bs) and (bo.index, bo.value, bo.mu, bo.std) == (bs.index, bs.value, bs.mu, bs.std)
+    assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-10 * max(1.0, abs(b6.value))
     assert new.last_unrefined() == 0 and 1 <= new.last_contenders() <= 4096
     assert 0 < new.last_rank_mu_error() < 1e-2 and old.last_rank_mu_error() == 0.0
     if acq == "ei":
@@ -718,8 +725,8 @@ def test_ranking_pass_on_non_exchangeable_candidate_orders():
     e64 = _engine(kw, "f64"); e64.tell(X, y)
     for name, G in _adversarial_grids(X, y, Xc):
         bn, bo, bs, b6 = new.ask(G), old.ask(G), slow.ask(G), e64.ask(G)
-        assert (bn.index, bn.value) == (bo.index, bo.value) == (bs.index, bs.value), name
-        assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-11 * max(1.0, abs(b6.value)), name
+        assert _same(bn, bo) and _same(bn, bs) and (bo.index, bo.value) == (bs.index, bs.value), name
+        assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-10 * max(1.0, abs(b6.value)), name
         print(f"\n{name}: index {bn.index} prefix survivors {new.last_prefix_survivors()} survivors {new.last_contenders()} rank err {new.last_rank_error():.2e} mu {new.last_rank_mu_error():.2e}")
     for e in (new, old, slow, e64):
         e.close()
@@ -763,7 +770,7 @@ def test_cfg3_full_size_path_of_record():
     assert new.last_unrefined() == 0 and 1 <= psurv <= 16384
     full = _engine(kw, "tc", rank_prefix=0); full.tell(X, y)
     bf = full.ask(xc)
-    assert (bf.index, bf.value) == (bn.index, bn.value) and full.last_prefix_survivors() == -1
+    assert _same(bf, bn) and full.last_prefix_survivors() == -1
     full.close()
     old = _engine(kw, "tc", rank_tc=False); old.tell(X, y)
     bo = old.ask(xc)
@@ -771,7 +778,7 @@ def test_cfg3_full_size_path_of_record():
     e64 = _engine(kw, "f64"); e64.tell(X, y)
     b6 = e64.ask(xc)
     e64.close()
-    assert (bn.index, bn.value) == (bo.index, bo.value)
+    assert _same(bn, bo)
     assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-10 * max(1.0, abs(b6.value))
     sample = np.concatenate([[bn.index], np.random.default_rng(9).choice(M, 4096, replace=False)])
     fit = O.gp_fit(X, y, kind="matern52", **{k: th[k] for k in ("length_scale", "amplitude", "noise")})
