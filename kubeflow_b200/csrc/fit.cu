@@ -748,6 +748,12 @@ int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double
 static int fit_finish(kbo_handle* h, cudaStream_t s, bool new_center) {
   const int N = h->N, ld = h->ld;
   const kbo_params* p = &h->prm;
+  static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
+  cudaEvent_t fe[5];
+  if (trace) {
+    for (auto& e : fe) cudaEventCreate(&e);
+    cudaEventRecord(fe[0], s);
+  }
   if (!h->w_full) {
     KBO_TRY(kbo_i_alpha_by_solves(h, s));   // alpha = L⁻ᵀ(L⁻¹ yn): two panel solves instead of Wᵀ(W yn)
   } else {
@@ -763,8 +769,10 @@ static int fit_finish(kbo_handle* h, cudaStream_t s, bool new_center) {
     KBO_LAUNCH_CHECK(h);
   }
   }
+  if (trace) cudaEventRecord(fe[1], s);
   lml_kernel<<<1, 1024, 0, s>>>((const double*)h->K.p, N, ld, (const double*)h->yn.p, (const double*)h->alpha.p, (double*)h->scal.p);
   KBO_LAUNCH_CHECK(h);
+  if (trace) cudaEventRecord(fe[2], s);
   if (p->var_mode == KBO_VAR_TC_F16X3 || (p->var_mode == KBO_VAR_AUTO && N > 1024)) {
     h->have_planes = true;
     const int Npad = h->Npad;
@@ -779,10 +787,23 @@ static int fit_finish(kbo_handle* h, cudaStream_t s, bool new_center) {
     dim3 g((Npad + 255) / 256, h->w_full ? Npad : round_up(Nw, 256));
     split_w_kernel<<<g, 256, 0, s>>>((const double*)h->W.p, Nw, ld, Npad, amax, (__half*)h->Wh.p, (__half*)h->Wl.p, (double*)h->scal.p + 6);
     KBO_LAUNCH_CHECK(h);
+    if (trace) cudaEventRecord(fe[3], s);
     // trial-side operands of the tensor-core K* kernel (alpha changes with every fit / append / rebase)
     KBO_TRY(kbo_i_tc_trials_prep(h, new_center, s));
   } else {
     h->ks_ready = false;
+    if (trace) cudaEventRecord(fe[3], s);
+  }
+  if (trace) {
+    cudaEventRecord(fe[4], s);
+    cudaEventSynchronize(fe[4]);
+    float a, b, c, d;
+    cudaEventElapsedTime(&a, fe[0], fe[1]);
+    cudaEventElapsedTime(&b, fe[1], fe[2]);
+    cudaEventElapsedTime(&c, fe[2], fe[3]);
+    cudaEventElapsedTime(&d, fe[3], fe[4]);
+    fprintf(stderr, "[kbo fit finish N=%d] alpha %.3f ms | lml %.3f ms | planes %.3f ms | trial operands %.3f ms\n", N, a, b, c, d);
+    for (auto& e : fe) cudaEventDestroy(e);
   }
   return KBO_OK;
 }

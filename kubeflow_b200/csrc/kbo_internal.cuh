@@ -92,6 +92,7 @@ struct kbo_handle {
   bool w_full = true;              // all rows of W (and the full fp16 planes) exist
   int w_lead = 0;                  // rows of W formed so far (the diagonal 256-blocks exist for every panel)
   DevBuf sv_B, sv_V;               // N × 8 right-hand sides / solutions of the panel solves
+  DevBuf sv_bar;                   // grid-barrier counter of the cooperative solve kernels
   // ---- kbo_lml_batch: concurrent factorisations for several θ (fit.cu) --------------------------------------------------
   void* lml_lanes = nullptr;       // std::vector<LmlLane>*
   DevBuf lml_yn, lml_scal;

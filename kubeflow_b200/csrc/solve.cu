@@ -7,7 +7,7 @@
 // buffer).  Forward, right-looking:   v_P = W_PP·b_P ;  b_>P −= L_>P,P·v_P      (P = 0, 1, …)
 // backward (alpha = L⁻ᵀ z):            a_P = W_PPᵀ·z_P ; z_<P −= (L_P,<P)ᵀ·a_P   (P = last, …, 0)
 // Up to 8 right-hand sides ride together (row-major N × 8): one pass over the triangle of L (268 MB at N = 8192) serves all of
-// them, 2 small launches per panel.  Every right-hand side goes through the same operations in the same order whatever
+// them, in one cooperative launch per solve (two grid barriers per panel).  Every right-hand side goes through the same operations in the same order whatever
 // rides beside it, so a candidate's value does not depend on which other survivors it was grouped with.
 #include "kbo_internal.cuh"
 
@@ -16,92 +16,167 @@
 
 namespace {
 
-// V_P = W_PP · B_P : one warp per row of the panel (lanes stride the columns k <= r), butterfly reduction in a fixed order
-__global__ void __launch_bounds__(256)
-sv_diag_fwd_kernel(const double* __restrict__ Wpp, int ldw, int Wd, const double* __restrict__ Bp, double* __restrict__ Vp) {
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= Wd) return;
-  double acc[SV_R];
-#pragma unroll
-  for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
-  const double* w = Wpp + (size_t)r * ldw;
-  for (int k = lane; k <= r; k += 32) {
-    const double wv = w[k];
-#pragma unroll
-    for (int q = 0; q < SV_R; q++) acc[q] = fma(wv, Bp[(size_t)k * SV_R + q], acc[q]);
+// Grid-wide barrier of a cooperative launch: every CTA adds one to a counter and spins until it reaches the running target.
+// Release / acquire through __threadfence around the atomic: the panels written before the barrier are read (with plain,
+// L2 loads: __ldcg — B, V, Z, A carry no __restrict__/const) after it.
+__device__ __forceinline__ void sv_grid_barrier(unsigned* ctr, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
   }
+  __syncthreads();
+}
+
+// V = L⁻¹·B, the whole solve in ONE cooperative launch (one CTA per SM, two grid barriers per panel) — 64 dependent launches
+// per solve cost more than the 268 MB of L they read.  Per panel P:
+//   (a) V_P = W_PP·B_P — one warp per row of the panel (the first 32 CTAs), B_P in shared memory as [rhs][k];
+//   (b) B_>P −= L_>P,P·V_P — one warp per row below, grid-strided, V_P in shared memory as [rhs][k] (conflict-free).
+// Fixed-order butterfly reductions: a right-hand side's result does not depend on the grid size or on what rides beside it.
+__global__ void __launch_bounds__(256)
+sv_forward_kernel(const double* __restrict__ L, const double* __restrict__ W, int N, int ld, double* B, double* V, unsigned* bar) {
+  __shared__ double vs[SV_R * SV_P];
+  unsigned target = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
+  for (int K0 = 0; K0 < N; K0 += SV_P) {
+    const int Wd = min(SV_P, N - K0);
+    if (blockIdx.x * 8 < Wd) {   // (a)
+      for (int e = threadIdx.x; e < SV_P * SV_R; e += 256) {
+        const int k = e / SV_R, q = e % SV_R;
+        vs[q * SV_P + k] = k < Wd ? __ldcg(B + (size_t)(K0 + k) * SV_R + q) : 0.0;
+      }
+      __syncthreads();
+      const int r = gwarp;
+      if (r < Wd) {
+        const double* w = W + (size_t)(K0 + r) * ld + K0;
+        double wv[SV_P / 32];
 #pragma unroll
-  for (int q = 0; q < SV_R; q++) {
-    double v = acc[q];
+        for (int i = 0; i < SV_P / 32; i++) wv[i] = lane + 32 * i <= r ? w[lane + 32 * i] : 0.0;
+        double acc[SV_R];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) Vp[(size_t)r * SV_R + q] = v;
+        for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
+#pragma unroll
+        for (int i = 0; i < SV_P / 32; i++)
+#pragma unroll
+          for (int q = 0; q < SV_R; q++) acc[q] = fma(wv[i], vs[q * SV_P + lane + 32 * i], acc[q]);
+#pragma unroll
+        for (int q = 0; q < SV_R; q++) {
+          double v = acc[q];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) V[(size_t)(K0 + r) * SV_R + q] = v;
+        }
+      }
+    }
+    sv_grid_barrier(bar, target);
+    const int below = N - (K0 + Wd);
+    if (below > 0) {   // (b)
+      for (int e = threadIdx.x; e < SV_P * SV_R; e += 256) {
+        const int k = e / SV_R, q = e % SV_R;
+        vs[q * SV_P + k] = k < Wd ? __ldcg(V + (size_t)(K0 + k) * SV_R + q) : 0.0;
+      }
+      __syncthreads();
+      for (int r = gwarp; r < below; r += nwarps) {
+        const double* l = L + (size_t)(K0 + Wd + r) * ld + K0;
+        double lv[SV_P / 32];
+#pragma unroll
+        for (int i = 0; i < SV_P / 32; i++) lv[i] = lane + 32 * i < Wd ? l[lane + 32 * i] : 0.0;
+        double acc[SV_R];
+#pragma unroll
+        for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
+#pragma unroll
+        for (int i = 0; i < SV_P / 32; i++)
+#pragma unroll
+          for (int q = 0; q < SV_R; q++) acc[q] = fma(lv[i], vs[q * SV_P + lane + 32 * i], acc[q]);
+#pragma unroll
+        for (int q = 0; q < SV_R; q++) {
+          double v = acc[q];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) {
+            double* o = B + (size_t)(K0 + Wd + r) * SV_R + q;
+            *o = __ldcg(o) - v;
+          }
+        }
+      }
+      sv_grid_barrier(bar, target);
+    }
   }
 }
-// B_>P −= L_>P,P · V_P : one warp per row below the panel, V_P (≤ 256 × 8) in shared memory
-__global__ void __launch_bounds__(256)
-sv_update_fwd_kernel(const double* __restrict__ Lp /* rows below, panel's columns */, int ldl, int rows, int Wd, const double* __restrict__ Vp,
-                     double* __restrict__ Bb /* rows below */) {
-  __shared__ double vs[SV_P * SV_R];
-  for (int e = threadIdx.x; e < Wd * SV_R; e += 256) vs[e] = Vp[e];
-  __syncthreads();
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= rows) return;
+
+// One 32-column unit of a transposed panel product:  out[c][q] (−)= Σ_r M[r][c0 + c]·x[r][q], r < rows.  Lanes own the columns
+// (coalesced 256-byte row segments), the 8 warps take rows r ≡ warp (mod 8) with all their loads in flight, and the 8
+// partial sums meet in shared memory in warp order.
+template <bool TRI, bool SUB>
+__device__ __forceinline__ void sv_unit_t(const double* __restrict__ M, int ldm, int rows, int c0, int ncols, const double* xs /* smem [r][q] */,
+                                          double* red /* smem [8][32][SV_R] */, double* out /* global, row c0.. */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = c0 + lane;
   double acc[SV_R];
 #pragma unroll
   for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
-  const double* l = Lp + (size_t)r * ldl;
-  for (int k = lane; k < Wd; k += 32) {
-    const double lv = l[k];
+  for (int rb = 0; rb < SV_P / 8; rb += 16) {
+    double mv[16];
 #pragma unroll
-    for (int q = 0; q < SV_R; q++) acc[q] = fma(lv, vs[k * SV_R + q], acc[q]);
+    for (int i = 0; i < 16; i++) {
+      const int r = (rb + i) * 8 + warp;
+      mv[i] = (r < rows && lane < ncols && (!TRI || r >= c)) ? M[(size_t)r * ldm + c] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int r = min((rb + i) * 8 + warp, rows - 1);
+#pragma unroll
+      for (int q = 0; q < SV_R; q++) acc[q] = fma(mv[i], xs[r * SV_R + q], acc[q]);
+    }
   }
 #pragma unroll
-  for (int q = 0; q < SV_R; q++) {
-    double v = acc[q];
+  for (int q = 0; q < SV_R; q++) red[(warp * 32 + lane) * SV_R + q] = acc[q];
+  __syncthreads();
+  {
+    const int cc = threadIdx.x >> 3, q = threadIdx.x & 7;   // 32 columns × 8 right-hand sides = 256 threads
+    double v = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) Bb[(size_t)r * SV_R + q] -= v;
+    for (int w = 0; w < 8; w++) v += red[(w * 32 + cc) * SV_R + q];
+    if (cc < ncols) {
+      double* o = out + (size_t)(c0 + cc) * SV_R + q;
+      *o = SUB ? __ldcg(o) - v : v;
+    }
   }
+  __syncthreads();
 }
-// A_P = W_PPᵀ · Z_P : thread c owns output row c, walks column c of W_PP (k >= c) — coalesced across the threads
+
+// A = L⁻ᵀ·Z in one cooperative launch.  Per panel P, last to first:
+//   (a) A_P = W_PPᵀ·Z_P — 8 units of 32 columns;   (b) Z_<P −= (L_P,<P)ᵀ·A_P — K0/32 units, grid-strided.
 __global__ void __launch_bounds__(256)
-sv_diag_bwd_kernel(const double* __restrict__ Wpp, int ldw, int Wd, const double* __restrict__ Zp, double* __restrict__ Ap) {
-  __shared__ double zs[SV_P * SV_R];
-  for (int e = threadIdx.x; e < Wd * SV_R; e += 256) zs[e] = Zp[e];
-  __syncthreads();
-  const int c = threadIdx.x;
-  if (c >= Wd) return;
-  double acc[SV_R];
-#pragma unroll
-  for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
-  for (int k = c; k < Wd; k++) {
-    const double wv = Wpp[(size_t)k * ldw + c];
-#pragma unroll
-    for (int q = 0; q < SV_R; q++) acc[q] = fma(wv, zs[k * SV_R + q], acc[q]);
+sv_backward_kernel(const double* __restrict__ L, const double* __restrict__ W, int N, int ld, double* Z, double* A, unsigned* bar) {
+  __shared__ double xs[SV_P * SV_R];
+  __shared__ double red[8 * 32 * SV_R];
+  unsigned target = 0;
+  const int last = (N - 1) / SV_P * SV_P;
+  for (int K0 = last; K0 >= 0; K0 -= SV_P) {
+    const int Wd = min(SV_P, N - K0);
+    const int units_a = (Wd + 31) / 32;
+    if ((int)blockIdx.x < units_a) {   // (a)
+      for (int e = threadIdx.x; e < Wd * SV_R; e += 256) xs[e] = __ldcg(Z + (size_t)K0 * SV_R + e);
+      __syncthreads();
+      for (int u = blockIdx.x; u < units_a; u += gridDim.x)
+        sv_unit_t<true, false>(W + (size_t)K0 * ld + K0, ld, Wd, u * 32, min(32, Wd - u * 32), xs, red, A + (size_t)K0 * SV_R);
+    }
+    sv_grid_barrier(bar, target);
+    if (K0 > 0) {   // (b)
+      for (int e = threadIdx.x; e < Wd * SV_R; e += 256) xs[e] = __ldcg(A + (size_t)K0 * SV_R + e);
+      __syncthreads();
+      for (int u = blockIdx.x; u < K0 / 32; u += gridDim.x) sv_unit_t<false, true>(L + (size_t)K0 * ld, ld, Wd, u * 32, 32, xs, red, Z);
+      sv_grid_barrier(bar, target);
+    }
   }
-#pragma unroll
-  for (int q = 0; q < SV_R; q++) Ap[(size_t)c * SV_R + q] = acc[q];
-}
-// Z_<P −= (L_P,<P)ᵀ · A_P : thread k owns row k < K0 of Z, walks the panel's rows r — coalesced across the threads
-__global__ void __launch_bounds__(256)
-sv_update_bwd_kernel(const double* __restrict__ Lrow /* panel's rows, columns 0.. */, int ldl, int K0, int Wd, const double* __restrict__ Ap,
-                     double* __restrict__ Z) {
-  __shared__ double as[SV_P * SV_R];
-  for (int e = threadIdx.x; e < Wd * SV_R; e += 256) as[e] = Ap[e];
-  __syncthreads();
-  const int k = blockIdx.x * 256 + threadIdx.x;
-  if (k >= K0) return;
-  double acc[SV_R];
-#pragma unroll
-  for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
-  for (int r = 0; r < Wd; r++) {
-    const double lv = Lrow[(size_t)r * ldl + k];
-#pragma unroll
-    for (int q = 0; q < SV_R; q++) acc[q] = fma(lv, as[r * SV_R + q], acc[q]);
-  }
-#pragma unroll
-  for (int q = 0; q < SV_R; q++) Z[(size_t)k * SV_R + q] -= acc[q];
 }
 
 // right-hand sides of one group: B[j][q] = Ks[(c0 + q)·ld + j] (q < nq; the rest zero)
@@ -135,40 +210,21 @@ __global__ void sv_col_kernel(const double* __restrict__ src, int N, int stride_
 
 }  // namespace
 
+static int sv_coop_launch(kbo_handle* h, const void* fn, double* X0, double* X1, cudaStream_t s) {
+  KBO_TRY(kbo_reserve(h, h->sv_bar, 256));
+  KBO_CUDA(h, cudaMemsetAsync(h->sv_bar.p, 0, sizeof(unsigned), s));
+  const double* L = (const double*)h->K.p;
+  const double* W = (const double*)h->W.p;
+  int N = h->N, ld = h->ld;
+  unsigned* bar = (unsigned*)h->sv_bar.p;
+  void* args[] = {(void*)&L, (void*)&W, (void*)&N, (void*)&ld, (void*)&X0, (void*)&X1, (void*)&bar};
+  KBO_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(h->sm_count), dim3(256), args, 0, s));   // one CTA per SM: co-resident by construction
+  return KBO_OK;
+}
 // B (N × 8, overwritten: scratch) -> V = L⁻¹·B (N × 8).  Needs the diagonal-block inverses in W's diagonal 256-blocks.
-int kbo_i_solve_fwd(kbo_handle* h, double* B, double* V, cudaStream_t s) {
-  const int N = h->N, ld = h->ld;
-  const double* L = (const double*)h->K.p;
-  const double* W = (const double*)h->W.p;
-  for (int K0 = 0; K0 < N; K0 += SV_P) {
-    const int Wd = N - K0 < SV_P ? N - K0 : SV_P;
-    sv_diag_fwd_kernel<<<(Wd + 7) / 8, 256, 0, s>>>(W + (size_t)K0 * ld + K0, ld, Wd, B + (size_t)K0 * SV_R, V + (size_t)K0 * SV_R);
-    KBO_LAUNCH_CHECK(h);
-    const int rows = N - (K0 + Wd);
-    if (rows > 0) {
-      sv_update_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(L + (size_t)(K0 + Wd) * ld + K0, ld, rows, Wd, V + (size_t)K0 * SV_R, B + (size_t)(K0 + Wd) * SV_R);
-      KBO_LAUNCH_CHECK(h);
-    }
-  }
-  return KBO_OK;
-}
+int kbo_i_solve_fwd(kbo_handle* h, double* B, double* V, cudaStream_t s) { return sv_coop_launch(h, (const void*)sv_forward_kernel, B, V, s); }
 // Z (N × 8, overwritten) -> A = L⁻ᵀ·Z (N × 8)
-int kbo_i_solve_bwd(kbo_handle* h, double* Z, double* A, cudaStream_t s) {
-  const int N = h->N, ld = h->ld;
-  const double* L = (const double*)h->K.p;
-  const double* W = (const double*)h->W.p;
-  const int last = (N - 1) / SV_P * SV_P;
-  for (int K0 = last; K0 >= 0; K0 -= SV_P) {
-    const int Wd = N - K0 < SV_P ? N - K0 : SV_P;
-    sv_diag_bwd_kernel<<<1, 256, 0, s>>>(W + (size_t)K0 * ld + K0, ld, Wd, Z + (size_t)K0 * SV_R, A + (size_t)K0 * SV_R);
-    KBO_LAUNCH_CHECK(h);
-    if (K0 > 0) {
-      sv_update_bwd_kernel<<<(K0 + 255) / 256, 256, 0, s>>>(L + (size_t)K0 * ld, ld, K0, Wd, A + (size_t)K0 * SV_R, Z);
-      KBO_LAUNCH_CHECK(h);
-    }
-  }
-  return KBO_OK;
-}
+int kbo_i_solve_bwd(kbo_handle* h, double* Z, double* A, cudaStream_t s) { return sv_coop_launch(h, (const void*)sv_backward_kernel, Z, A, s); }
 
 // alpha = L⁻ᵀ(L⁻¹·yn) into h->alpha (what fit_finish computes as Wᵀ(W·yn) when W is formed)
 int kbo_i_alpha_by_solves(kbo_handle* h, cudaStream_t s) {
