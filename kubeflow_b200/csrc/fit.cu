@@ -152,52 +152,7 @@ __device__ __forceinline__ void tri_inverse_64(double (*S)[KBO_NB + 1], double (
   }
 }
 
-__global__ void __launch_bounds__(1024) potf2_inv_kernel(double* __restrict__ A, int lda, int jb, int k_global,
-                                                         double* __restrict__ Linv, int* __restrict__ info) {
-  extern __shared__ double sm[];
-  double(*S)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm);
-  double(*T)[KBO_NB + 1] = reinterpret_cast<double(*)[KBO_NB + 1]>(sm + KBO_NB * (KBO_NB + 1));
-  __shared__ double invd[KBO_NB];
-  const int t = threadIdx.x;
-  if (*info != 0) return;  // an earlier panel already failed
-  for (int e = t; e < KBO_NB * KBO_NB; e += 1024) {
-    const int r = e >> 6, c = e & 63;
-    S[r][c] = (r < jb && c <= r) ? A[(size_t)r * lda + c] : (r == c ? 1.0 : 0.0);
-  }
-  __syncthreads();
-  {
-    const int i = t >> 4, c0 = (t & 15) * 4;
-    for (int j = 0; j < jb; j++) {
-      const double djj = S[j][j];
-      if (!(djj > 0.0)) {  // uniform: every thread reads the same value
-        if (t == 0) *info = k_global + j + 1;
-        return;
-      }
-      const double rd = rsqrt(djj);
-      const double lij = (i > j && i < jb) ? S[i][j] * rd : 0.0;
-      if (i > j && i < jb) {
-#pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-          const int c = c0 + cc;
-          if (c > j && c <= i) S[i][c] = fma(-lij, S[c][j] * rd, S[i][c]);
-        }
-      }
-      __syncthreads();
-      if ((t & 15) == 0) {
-        if (i == j) S[j][j] = sqrt(djj);
-        else if (i > j && i < jb) S[i][j] = lij;
-      }
-    }
-  }
-  __syncthreads();
-  tri_inverse_64(S, T, invd, t);
-  __syncthreads();
-  for (int e = t; e < KBO_NB * KBO_NB; e += 1024) {
-    const int r = e >> 6, c = e & 63;
-    if (r < jb && c <= r) A[(size_t)r * lda + c] = S[r][c];
-    Linv[e] = T[r][c];
-  }
-}
+#include "potf2.cuh"
 
 // batched inverse of the 64×64 diagonal blocks of a lower-triangular L (for kbo_trtri); one CTA per block
 __global__ void __launch_bounds__(1024) diag_inv_kernel(const double* __restrict__ L, int N, int ldl, double* __restrict__ W, int ldw) {
@@ -282,7 +237,7 @@ static int potrf_impl(kbo_handle* h, double* A, int N, int lda, int* info_dev, c
     for (int k = K0; k < K0 + W; k += KBO_NB) {
       const int jb = min(KBO_NB, N - k);
       double* Akk = A + (size_t)k * lda + k;
-      potf2_inv_kernel<<<1, 1024, smem, s>>>(Akk, lda, jb, k, Linv, info_dev);
+      potf2_inv_kernel<<<1, POTF2_THREADS, smem, s>>>(Akk, lda, jb, k, Linv, info_dev);
       KBO_LAUNCH_CHECK(h);
       const int rows = N - k - jb;
       if (rows > 0) {
@@ -516,6 +471,14 @@ static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double
               e_inv = h->ev_panel[2 * n_panels + 5];
   static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
   cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> tp;   // KBO_FIT_TRACE: per panel, on the chain stream: [enqueued | column block ready | diagonal block done | W_PP done | panel solved]
+  auto mark = [&]() {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, h->s_hi);
+    tp.push_back(e);
+  };
   if (trace) {
     for (auto& e : tr) cudaEventCreate(&e);
     cudaEventRecord(tr[0], s);
@@ -532,11 +495,13 @@ static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double
   auto body = [&]() -> int {
     for (int K0 = 0, P = 0; K0 < N; K0 += OW, P++) {
       const int Wd = min(OW, N - K0);
+      mark();
       if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(shi, ev_col[P], 0));   // this panel's column block carries every earlier panel's update
+      mark();
       // ---- the chain: the diagonal block only -------------------------------------------------------------------------
       for (int k = K0; k < K0 + Wd; k += KBO_NB) {
         const int jb = min(KBO_NB, N - k);
-        potf2_inv_kernel<<<1, 1024, smem, shi>>>(A + (size_t)k * lda + k, lda, jb, k, Linv, info_dev);
+        potf2_inv_kernel<<<1, POTF2_THREADS, smem, shi>>>(A + (size_t)k * lda + k, lda, jb, k, Linv, info_dev, W + (size_t)k * ldw + k, ldw);
         KBO_LAUNCH_CHECK(h);
         const int rows_in = K0 + Wd - (k + jb);
         if (rows_in > 0) {
@@ -548,11 +513,11 @@ static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double
           KBO_LAUNCH_CHECK(h);
         }
       }
+      mark();
       // ---- W_PP = L_PP⁻¹ (64-block inverses, recursive doubling inside the panel) -----------------------------------------
       double* Wpp = W + (size_t)K0 * ldw + K0;
       const double* Lpp = A + (size_t)K0 * lda + K0;
-      diag_inv_kernel<<<(Wd + KBO_NB - 1) / KBO_NB, 1024, smem, shi>>>(Lpp, Wd, lda, Wpp, ldw);
-      KBO_LAUNCH_CHECK(h);
+      // (the 64-blocks' inverses were written into W's diagonal by potf2_inv_kernel)
       for (int b = KBO_NB; b < Wd; b *= 2)
         for (int r0 = 0; r0 + b < Wd; r0 += 2 * b) {
           const int rows2 = min(b, Wd - (r0 + b));
@@ -564,6 +529,7 @@ static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double
                                            Wpp + (size_t)(r0 + b) * ldw + r0, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
           KBO_LAUNCH_CHECK(h);
         }
+      mark();
       // ---- the panel below the diagonal block: L_>P,P = A_>P,P · W_PPᵀ, one GEMM (W_PP lower triangular: k <= n) ------------------
       const int rows_t = N - (K0 + Wd);
       if (rows_t > 0) {
@@ -572,6 +538,7 @@ static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double
         KBO_LAUNCH_CHECK(h);
         KBO_CUDA(h, cudaMemcpy2DAsync(Pp, sizeof(double) * lda, T2, sizeof(double) * OW, sizeof(double) * Wd, rows_t, cudaMemcpyDeviceToDevice, shi));
       }
+      mark();
       KBO_CUDA(h, cudaEventRecord(ev_solve[P], shi));
       // ---- trailing update, second stream: next column block first (look-ahead), then the rest ---------------------------------
       if (rows_t > 0) {
@@ -634,7 +601,298 @@ static int factor_and_invert_v2(kbo_handle* h, double* A, int N, int lda, double
     float a = 0.f, b = 0.f, c = 0.f;
     cudaEventElapsedTime(&a, tr[0], tr[1]); cudaEventElapsedTime(&b, tr[0], tr[2]); cudaEventElapsedTime(&c, tr[0], tr[3]);
     fprintf(stderr, "[kbo fit v2 N=%d] chain stream done at %.3f ms, update stream at %.3f ms, inverse stream at %.3f ms\n", N, a, b, c);
+    double sum[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i + 4 < tp.size() + 0 && i + 4 <= tp.size() - 1; i += 5) {
+      float w, d, iv, so;
+      cudaEventElapsedTime(&w, tp[i], tp[i + 1]);
+      cudaEventElapsedTime(&d, tp[i + 1], tp[i + 2]);
+      cudaEventElapsedTime(&iv, tp[i + 2], tp[i + 3]);
+      cudaEventElapsedTime(&so, tp[i + 3], tp[i + 4]);
+      sum[0] += w; sum[1] += d; sum[2] += iv; sum[3] += so;
+      if ((i / 5) % 8 == 0) fprintf(stderr, "   panel %2d: wait for column block %.3f | diagonal block %.3f | W_PP %.3f | panel solve %.3f ms\n", (int)(i / 5), w, d, iv, so);
+    }
+    fprintf(stderr, "   chain totals: waiting %.3f | diagonal blocks %.3f | W_PP %.3f | panel solves %.3f ms\n", sum[0], sum[1], sum[2], sum[3]);
+    for (auto& e : tp) cudaEventDestroy(e);
     for (auto& e : tr) cudaEventDestroy(e);
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Version 3: the chain on its OWN SMs, the panel below it solved in its shadow.
+// What v2's chain-stream trace showed (KBO_FIT_TRACE, N = 8192): the four single-CTA factorisations of a panel take 0.21 ms
+// on an idle GPU and up to 0.55 ms while trailing updates run — the update GEMMs hold two 128-register CTAs per SM, i.e. the
+// whole register file, so a chain kernel waits until an SM drains (stream priority orders pending CTAs; it does not preempt) —
+// and W_PP plus the one-GEMM panel solve add 0.2 ms of dependent launches per panel.  Here
+//  * a GREEN CONTEXT (CUDA 12.4+) gives the chain stream 8 SMs of its own; everything else runs on the other 140.  If the
+//    driver cannot split the device the same streams are created unpartitioned and only the second point applies;
+//  * the rows below the diagonal block are solved column block by column block on a second stream AS the chain produces the
+//    64×64 inverses (four buffers): after the last factorisation only one 64-column solve remains before the trailing update
+//    can start.  W_PP (for L⁻¹ and the triangular solves) moves to the inverse stream, off the critical path.
+// Driver entry points come from cudaGetDriverEntryPoint: libkbo links the runtime only.
+#include <cuda.h>
+namespace {
+struct DrvApi {
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  bool ok = false;
+};
+DrvApi load_drv() {
+  DrvApi d;
+  auto get = [](const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult q;
+    return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+  };
+  d.ok = get("cuDeviceGet", (void**)&d.DeviceGet) && get("cuDeviceGetDevResource", (void**)&d.DeviceGetDevResource) &&
+         get("cuDevSmResourceSplitByCount", (void**)&d.DevSmResourceSplitByCount) && get("cuDevResourceGenerateDesc", (void**)&d.DevResourceGenerateDesc) &&
+         get("cuGreenCtxCreate", (void**)&d.GreenCtxCreate) && get("cuGreenCtxDestroy", (void**)&d.GreenCtxDestroy) &&
+         get("cuGreenCtxStreamCreate", (void**)&d.GreenCtxStreamCreate);
+  if (!d.ok) cudaGetLastError();
+  return d;
+}
+const DrvApi& drv() {
+  static const DrvApi d = load_drv();
+  return d;
+}
+}  // namespace
+
+static int fit_partition(kbo_handle* h) {
+  if (h->part_tried) return KBO_OK;
+  h->part_tried = true;
+  int lo = 0, hi = 0;
+  KBO_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  const int mid = (lo + hi) / 2;
+  static const bool off = getenv("KBO_FIT_NO_PARTITION") != nullptr;
+  const DrvApi& d = drv();
+  if (!off && d.ok) {
+    CUdevice dev;
+    CUdevResource all, chain, rest;
+    unsigned int nb = 1;
+    CUdevResourceDesc dc = nullptr, dr = nullptr;
+    CUgreenCtx gc = nullptr, gr = nullptr;
+    bool ok = d.DeviceGet(&dev, h->device) == CUDA_SUCCESS && d.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+              d.DevSmResourceSplitByCount(&chain, &nb, &all, &rest, 0, 8) == CUDA_SUCCESS && nb == 1 && rest.sm.smCount >= 64 &&
+              d.DevResourceGenerateDesc(&dc, &chain, 1) == CUDA_SUCCESS && d.DevResourceGenerateDesc(&dr, &rest, 1) == CUDA_SUCCESS &&
+              d.GreenCtxCreate(&gc, dc, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    ok = ok && d.GreenCtxCreate(&gr, dr, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    ok = ok && d.GreenCtxStreamCreate((CUstream*)&h->s3_chain, gc, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
+         d.GreenCtxStreamCreate((CUstream*)&h->s3_solve, gr, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
+         d.GreenCtxStreamCreate((CUstream*)&h->s3_upd, gr, CU_STREAM_NON_BLOCKING, mid) == CUDA_SUCCESS &&
+         d.GreenCtxStreamCreate((CUstream*)&h->s3_inv, gr, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS;
+    if (ok) {
+      h->gctx_chain = gc;
+      h->gctx_rest = gr;
+      h->part_ok = true;
+      static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
+      if (trace) fprintf(stderr, "[kbo fit] SM partition: chain %u SMs, rest %u SMs\n", chain.sm.smCount, rest.sm.smCount);
+      return KBO_OK;
+    }
+    for (cudaStream_t* st : {&h->s3_chain, &h->s3_solve, &h->s3_upd, &h->s3_inv})
+      if (*st) {
+        cudaStreamDestroy(*st);
+        *st = nullptr;
+      }
+    if (gc) d.GreenCtxDestroy(gc);
+    if (gr) d.GreenCtxDestroy(gr);
+    cudaGetLastError();
+  }
+  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_chain, cudaStreamNonBlocking, hi));
+  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_solve, cudaStreamNonBlocking, hi));
+  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_upd, cudaStreamNonBlocking, mid));
+  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_inv, cudaStreamNonBlocking, lo));
+  return KBO_OK;
+}
+void kbo_i_fit_partition_free(kbo_handle* h) {
+  for (cudaStream_t* st : {&h->s3_chain, &h->s3_solve, &h->s3_upd, &h->s3_inv})
+    if (*st) {
+      cudaStreamDestroy(*st);
+      *st = nullptr;
+    }
+  if (h->gctx_chain) drv().GreenCtxDestroy((CUgreenCtx)h->gctx_chain);
+  if (h->gctx_rest) drv().GreenCtxDestroy((CUgreenCtx)h->gctx_rest);
+  h->gctx_chain = h->gctx_rest = nullptr;
+}
+
+static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s, int lead) {
+  const int OW = 256, NB = KBO_NB, n_panels = (N + OW - 1) / OW;
+  KBO_TRY(fit_streams(h, 3 * n_panels + 16));
+  KBO_TRY(fit_partition(h));
+  KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
+  KBO_TRY(kbo_reserve(h, h->Linv4, sizeof(double) * 4 * NB * NB));
+  const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
+  if (!h->attr_fit) {
+    KBO_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KBO_CUDA(h, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    h->attr_fit = true;
+  }
+  double* T = (double*)h->T.p;
+  double* Linv4 = (double*)h->Linv4.p;
+  cudaStream_t sc = h->s3_chain, ss = h->s3_solve, su = h->s3_upd, si = h->s3_inv;
+  cudaEvent_t* ev_solve = h->ev_panel.data();                    // [n_panels]     panel's rows below the diagonal block are L
+  cudaEvent_t* ev_col = h->ev_panel.data() + n_panels;           // [n_panels + 1] column block P carries every earlier panel's update
+  cudaEvent_t* ev_chain = h->ev_panel.data() + 2 * n_panels + 1; // [n_panels]     diagonal block factored, its 64-block inverses in W
+  cudaEvent_t* ev_x = h->ev_panel.data() + 3 * n_panels + 1;     // pf[4], tr[4], start, 4 joins
+  cudaEvent_t *ev_pf = ev_x, *ev_tr = ev_x + 4, e_start = ev_x[8], *e_join = ev_x + 9;
+  static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
+  cudaEvent_t tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> tp;   // per panel on the chain stream: enqueued | column block ready | diagonal block done
+  auto mark = [&]() {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, sc);
+    tp.push_back(e);
+  };
+  if (trace) {
+    for (auto& e : tr) cudaEventCreate(&e);
+    cudaEventRecord(tr[0], s);
+  }
+  KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+  KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));   // on the caller's stream: all SMs, not the chain's 8
+  KBO_CUDA(h, cudaEventRecord(e_start, s));
+  for (cudaStream_t st : {sc, ss, su, si}) KBO_CUDA(h, cudaStreamWaitEvent(st, e_start, 0));
+  const int RW = 512;
+  int rp0 = 0;
+  auto body = [&]() -> int {
+    for (int K0 = 0, P = 0; K0 < N; K0 += OW, P++) {
+      const int Wd = min(OW, N - K0), rows_t = N - (K0 + Wd);
+      const int nblk = (Wd + NB - 1) / NB;
+      mark();
+      if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(sc, ev_col[P], 0));
+      mark();
+      // ---- the chain (own SMs): the diagonal block only ------------------------------------------------------------------
+      for (int b = 0; b < nblk; b++) {
+        const int k = K0 + b * NB, jb = min(NB, N - k);
+        double* Li = Linv4 + (size_t)b * NB * NB;
+        potf2_inv_kernel<<<1, POTF2_THREADS, smem, sc>>>(A + (size_t)k * lda + k, lda, jb, k, Li, info_dev, W + (size_t)k * ldw + k, ldw);
+        KBO_LAUNCH_CHECK(h);
+        KBO_CUDA(h, cudaEventRecord(ev_pf[b], sc));
+        const int rows_in = K0 + Wd - (k + jb);
+        if (rows_in > 0) {
+          double* Pn = A + (size_t)(k + jb) * lda + k;
+          trsm_panel_kernel<<<(rows_in + 63) / 64, 256, smem, sc>>>(Pn, lda, rows_in, jb, Li, info_dev);
+          KBO_LAUNCH_CHECK(h);
+          KBO_CUDA(h, cudaEventRecord(ev_tr[b], sc));
+          dgemm64_launch<true, EPI_STORE>(sc, rows_in, rows_in, jb, Pn, lda, Pn, lda, A + (size_t)(k + jb) * lda + (k + jb), lda, -1.0, 1.0, KM_FULL, 0,
+                                          TS_LOWER);
+          KBO_LAUNCH_CHECK(h);
+        }
+      }
+      mark();
+      KBO_CUDA(h, cudaEventRecord(ev_chain[P], sc));
+      // ---- the shadow: rows below the diagonal block, one 64-column block behind the chain --------------------------------------
+      if (rows_t > 0) {
+        if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(ss, ev_col[P], 0));   // these rows of the column block carry the earlier updates too
+        for (int b = 0; b < nblk; b++) {
+          const int k = K0 + b * NB, jb = min(NB, N - k);
+          KBO_CUDA(h, cudaStreamWaitEvent(ss, ev_pf[b], 0));
+          double* Xb = A + (size_t)(K0 + Wd) * lda + k;
+          trsm_panel_kernel<<<(rows_t + 63) / 64, 256, smem, ss>>>(Xb, lda, rows_t, jb, Linv4 + (size_t)b * NB * NB, info_dev);
+          KBO_LAUNCH_CHECK(h);
+          const int ncols = K0 + Wd - (k + jb);   // the panel's columns right of this block
+          if (ncols > 0) {
+            KBO_CUDA(h, cudaStreamWaitEvent(ss, ev_tr[b], 0));   // L of the diagonal block's rows in this column block (the chain's trsm)
+            dgemm64_launch<true, EPI_STORE>(ss, rows_t, ncols, jb, Xb, lda, A + (size_t)(k + jb) * lda + k, lda, Xb + jb, lda, -1.0, 1.0, KM_FULL, 0, TS_NONE);
+            KBO_LAUNCH_CHECK(h);
+          }
+        }
+        KBO_CUDA(h, cudaEventRecord(ev_solve[P], ss));
+        // ---- trailing update: next column block first (the next panel's chain and shadow wait for it), then the rest --------------
+        KBO_CUDA(h, cudaStreamWaitEvent(su, ev_solve[P], 0));
+        const double* Pp = A + (size_t)(K0 + Wd) * lda + K0;
+        const int nb = min(OW, rows_t);
+        dgemm64_launch<true, EPI_STORE>(su, rows_t, nb, Wd, Pp, lda, Pp, lda, A + (size_t)(K0 + Wd) * lda + (K0 + Wd), lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+        KBO_LAUNCH_CHECK(h);
+        KBO_CUDA(h, cudaEventRecord(ev_col[P + 1], su));
+        const int rows_r = rows_t - nb;
+        if (rows_r > 0) {
+          const double* Pr = Pp + (size_t)nb * lda;
+          dgemm64_launch<true, EPI_STORE>(su, rows_r, rows_r, Wd, Pr, lda, Pr, lda, A + (size_t)(K0 + Wd + nb) * lda + (K0 + Wd + nb), lda, -1.0, 1.0,
+                                          KM_FULL, 0, TS_LOWER);
+          KBO_LAUNCH_CHECK(h);
+        }
+      }
+      // ---- inverse stream: W_PP = L_PP⁻¹ by recursive doubling from the 64-block inverses, then the row panels of L⁻¹ -------------
+      KBO_CUDA(h, cudaStreamWaitEvent(si, ev_chain[P], 0));
+      {
+        double* Wpp = W + (size_t)K0 * ldw + K0;
+        const double* Lpp = A + (size_t)K0 * lda + K0;
+        for (int b = NB; b < Wd; b *= 2)
+          for (int r0 = 0; r0 + b < Wd; r0 += 2 * b) {
+            const int rows2 = min(b, Wd - (r0 + b));
+            double* T21 = T + (size_t)(K0 + r0 + b) * ldw + K0 + r0;
+            dgemm64_launch<false, EPI_STORE>(si, rows2, b, b, Lpp + (size_t)(r0 + b) * lda + r0, lda, Wpp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
+                                             KM_FROM_N, 0, TS_NONE);
+            KBO_LAUNCH_CHECK(h);
+            dgemm64_launch<false, EPI_STORE>(si, rows2, b, rows2, Wpp + (size_t)(r0 + b) * ldw + r0 + b, ldw, T21, ldw,
+                                             Wpp + (size_t)(r0 + b) * ldw + r0, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+            KBO_LAUNCH_CHECK(h);
+          }
+      }
+      const int done = K0 + Wd;
+      if (rp0 < lead && (done - rp0 >= RW || done >= N)) {
+        const int P0 = rp0, Pw = done - rp0;
+        rp0 = done;
+        if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(si, ev_solve[P - 1], 0));   // rows [P0, done) of L left of this panel: the earlier shadows
+        double* Wrp = W + (size_t)P0 * ldw + P0;
+        const double* Lrp = A + (size_t)P0 * lda + P0;
+        for (int b = OW; b < Pw; b *= 2)
+          for (int r0 = 0; r0 + b < Pw; r0 += 2 * b) {
+            const int rows2 = min(b, Pw - (r0 + b));
+            double* T21 = T + (size_t)(P0 + r0 + b) * ldw + P0 + r0;
+            dgemm64_launch<false, EPI_STORE>(si, rows2, b, b, Lrp + (size_t)(r0 + b) * lda + r0, lda, Wrp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
+                                             KM_FROM_N, 0, TS_NONE);
+            KBO_LAUNCH_CHECK(h);
+            dgemm64_launch<false, EPI_STORE>(si, rows2, b, rows2, Wrp + (size_t)(r0 + b) * ldw + r0 + b, ldw, T21, ldw,
+                                             Wrp + (size_t)(r0 + b) * ldw + r0, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+            KBO_LAUNCH_CHECK(h);
+          }
+        if (P0 > 0) {
+          double* Trow = T + (size_t)P0 * ldw;
+          dgemm64_launch<false, EPI_STORE>(si, Pw, P0, P0, A + (size_t)P0 * lda, lda, W, ldw, Trow, ldw, 1.0, 0.0, KM_FROM_N, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+          dgemm64_launch<false, EPI_STORE>(si, Pw, P0, Pw, Wrp, ldw, Trow, ldw, W + (size_t)P0 * ldw, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+        }
+      }
+    }
+    return KBO_OK;
+  };
+  const int rc = body();
+  {
+    int j = 0;
+    for (cudaStream_t st : {sc, ss, su, si}) {
+      cudaEventRecord(e_join[j], st);
+      cudaStreamWaitEvent(s, e_join[j], 0);
+      j++;
+    }
+  }
+  if (tr[0]) {
+    int j = 1;
+    for (cudaStream_t st : {sc, ss, su, si}) cudaEventRecord(tr[j++], st);
+    for (cudaStream_t st : {sc, ss, su, si}) cudaStreamSynchronize(st);
+    float t[5] = {0, 0, 0, 0, 0};
+    for (int i = 1; i < 5; i++) cudaEventElapsedTime(&t[i], tr[0], tr[i]);
+    fprintf(stderr, "[kbo fit v3 N=%d%s] chain stream done at %.3f ms, shadow %.3f, update %.3f, inverse %.3f ms\n", N, h->part_ok ? ", partitioned" : "", t[1],
+            t[2], t[3], t[4]);
+    double sum[2] = {0, 0};
+    for (size_t i = 0; i + 2 < tp.size(); i += 3) {
+      float w, d;
+      cudaEventElapsedTime(&w, tp[i], tp[i + 1]);
+      cudaEventElapsedTime(&d, tp[i + 1], tp[i + 2]);
+      sum[0] += w;
+      sum[1] += d;
+      if ((i / 3) % 8 == 0) fprintf(stderr, "   panel %2d: wait for column block %.3f | diagonal block %.3f ms\n", (int)(i / 3), w, d);
+    }
+    fprintf(stderr, "   chain totals: waiting %.3f | diagonal blocks %.3f ms\n", sum[0], sum[1]);
+    for (auto& e : tr) cudaEventDestroy(e);
+    for (auto& e : tp) cudaEventDestroy(e);
   }
   return rc;
 }
@@ -879,7 +1137,11 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
         const int P1 = h->rank_prefix < 0 ? (n_pairs + 7) / 8 : h->rank_prefix;
         if (P1 >= 1 && P1 < n_pairs && P1 * 512 + 512 <= N) lead = round_up(P1 * 512, 512);
       }
-      KBO_TRY(factor_and_invert_v2(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s, lead));
+      static const bool v2 = getenv("KBO_FIT_V2") != nullptr;   // A/B: look-ahead without the SM partition and the shadow solve
+      if (v2)
+        KBO_TRY(factor_and_invert_v2(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s, lead));
+      else
+        KBO_TRY(factor_and_invert_v3(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s, lead));
       h->w_lead = lead < N ? lead : N;
       h->w_full = lead >= N;
     }

@@ -85,7 +85,12 @@ struct kbo_handle {
   int last_unrefined = 0;          // 1: the last tensor-core sweep could not decide in FP64 (more near-ties than the cap)
   // ---- fit: Cholesky chain on a high-priority stream, row-panel inverse on a second one (fit.cu) ----------------------
   cudaStream_t s_hi = nullptr, s_lo = nullptr, s_upd = nullptr, s_copy = nullptr;
-  DevBuf T2;                        // N × 256 panel-solve scratch of the look-ahead factorisation
+  DevBuf T2;                        // N × 256 panel-solve scratch of the look-ahead factorisation (v2)
+  // v3: the chain runs on its own SM partition (green contexts); shadow panel solve / trailing update / inverse share the rest
+  bool part_tried = false, part_ok = false;
+  void *gctx_chain = nullptr, *gctx_rest = nullptr;   // CUgreenCtx
+  cudaStream_t s3_chain = nullptr, s3_solve = nullptr, s3_upd = nullptr, s3_inv = nullptr;
+  DevBuf Linv4;                     // the four 64×64 block inverses of the current panel
   std::vector<cudaEvent_t> ev_panel;
   // ---- lazy inverse (fit.cu, solve.cu): the product path never needs all of W = L⁻¹ -----------------------------------------
   bool lazy_w = true;              // kbo_set_lazy_inverse: tensor-core fits form only the leading rows of W the pruning pass reads
@@ -159,6 +164,7 @@ int kbo_i_fit(kbo_handle* h, const double* X_dev, const double* y_dev, int N, in
 int kbo_i_lml_batch(kbo_handle* h, const double* X_dev, const double* y_dev, int N, int D, int G, const kbo_params* params, double* lml_host,
                     int32_t* info_host, cudaStream_t s);
 void kbo_i_lml_batch_free(kbo_handle* h);
+void kbo_i_fit_partition_free(kbo_handle* h);
 int kbo_i_ensure_w(kbo_handle* h, cudaStream_t s);   // form the rest of W and the full planes if the fit left them out
 // ---- solve.cu ----------------------------------------------------------------------------------
 int kbo_i_alpha_by_solves(kbo_handle* h, cudaStream_t s);
