@@ -12,8 +12,14 @@ enum { TS_NONE = 0, TS_LOWER = 1 };
 #define DG_BM 128
 #define DG_BN 64
 #define DG_BK 16
-#define DG_LDA (DG_BM + 8)   // ≡ 8 (mod 32) doubles: the 32 lanes of a DMMA fragment load (4 k-rows × 8 consecutive m) hit 32
-#define DG_LDB (DG_BN + 8)   // distinct 8-byte words → 2 shared-memory wavefronts, conflict-free
+// Shared-memory tiles are [row][k] with a row pitch of 20 doubles (NN's B tile: [k][n], pitch 68).  A 64-bit shared access is
+// served per half-warp over 16 eight-byte banks, so both access patterns must touch 16 distinct banks per half-warp:
+//  * the slab store — lanes = 16 consecutive k of one row — is contiguous;
+//  * the DMMA fragment load — lanes (g, t) = (row, k) — lands on bank (g·pitch + t) mod 16 = 4g + t for g < 4: distinct.
+// (The first layout, [k][row] with pitch ≡ 8, had the loads 2-way and the stores 8-way conflicted: ncu showed the tensor pipe 53 %
+// active, `mio_throttle` the top stall — profiles/README.md.)
+#define DG_LDK (DG_BK + 4)
+#define DG_LDB (DG_BN + 4)
 
 // FP64 tensor-core MMA (DMMA), warp-level: D(8×8) += A(8×4)·B(4×8).  Fragments (lane = 4g + t): a = A[g][t], b = B[t][g],
 // c/d = C[g][2t], C[g][2t+1].  B200's FP64 tensor rate is about twice its vector DFMA rate, and a fragment load feeds 256
@@ -33,8 +39,10 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   A += (long long)blockIdx.z * strideA;
   B += (long long)blockIdx.z * strideB;
   C += (long long)blockIdx.z * strideC;
-  __shared__ double As[DG_BK][DG_LDA];
-  __shared__ double Bs[DG_BK][DG_LDB];
+  __shared__ double As[DG_BM][DG_LDK];
+  __shared__ double Bs_raw[DG_BN * DG_LDK > DG_BK * DG_LDB ? DG_BN * DG_LDK : DG_BK * DG_LDB];
+  double(*Bt)[DG_LDK] = reinterpret_cast<double(*)[DG_LDK]>(Bs_raw);   // TRANSB: [n][k]
+  double(*Bn)[DG_LDB] = reinterpret_cast<double(*)[DG_LDB]>(Bs_raw);   // NN:     [k][n]
   const int m0 = blockIdx.y * DG_BM, n0 = blockIdx.x * DG_BN;
   if (tileskip == TS_LOWER && n0 > m0 + DG_BM - 1) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -47,11 +55,28 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   if (kmode == KM_FROM_M) kb = max(kbegin, m0);
   kb = kb & ~(DG_BK - 1);
 
+  // alpha = ±1, beta = 1 (every update of the factorisation): the accumulators START from ±C, so the tile of C is read while the
+  // first slab is in flight instead of in a serialised read-modify-write epilogue — at K = 256 that epilogue was a quarter of the
+  // kernel.  (Accumulating onto C instead of adding C last changes the rounding order, not the error bound.)
+  const bool preload = EPI == EPI_STORE && beta == 1.0 && (alpha == 1.0 || alpha == -1.0);
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  if (preload) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int gm = m0 + wm + 8 * i + g;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int gn = n0 + wn + 8 * j + 2 * t + e;
+          if (gm < M && gn < N) acc[i][j][e] = alpha * C[(size_t)gm * ldc + gn];
+        }
+    }
+  }
 
   double pa[8], pb[4];
   auto prefetch = [&](int k0) {
@@ -83,13 +108,13 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   };
   auto commit = [&]() {
 #pragma unroll
-    for (int i = 0; i < 8; i++) As[tid & 15][(tid >> 4) + 16 * i] = pa[i];
+    for (int i = 0; i < 8; i++) As[(tid >> 4) + 16 * i][tid & 15] = pa[i];
     if (TRANSB) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) Bs[tid & 15][(tid >> 4) + 16 * i] = pb[i];
+      for (int i = 0; i < 4; i++) Bt[(tid >> 4) + 16 * i][tid & 15] = pb[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; i++) Bs[(tid >> 6) + 4 * i][tid & 63] = pb[i];
+      for (int i = 0; i < 4; i++) Bn[(tid >> 6) + 4 * i][tid & 63] = pb[i];
     }
   };
   if (kb < ke) {
@@ -104,9 +129,9 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
     for (int k4 = 0; k4 < DG_BK; k4 += 4) {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = As[k4 + t][wm + 8 * i + g];
+      for (int i = 0; i < 4; i++) a[i] = As[wm + 8 * i + g][k4 + t];
 #pragma unroll
-      for (int j = 0; j < 4; j++) b[j] = Bs[k4 + t][wn + 8 * j + g];
+      for (int j = 0; j < 4; j++) b[j] = TRANSB ? Bt[wn + 8 * j + g][k4 + t] : Bn[k4 + t][wn + 8 * j + g];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -130,7 +155,7 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
           const int gn = n0 + wn + 8 * j + 2 * t + e;
           if (gn >= N) continue;
           double* c = C + (size_t)gm * ldc + gn;
-          *c = (beta == 0.0) ? alpha * acc[i][j][e] : alpha * acc[i][j][e] + beta * (*c);
+          *c = (beta == 0.0 || preload) ? alpha * acc[i][j][e] : alpha * acc[i][j][e] + beta * (*c);
         }
     }
   } else {  // EPI_ROWSUMSQ: C is part[M × ldc], column = this block's n-tile; fixed reduction order
