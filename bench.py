@@ -400,7 +400,13 @@ def main():
         flops_launch = rows_per_launch * float(N) * float(N)           # Σ_j Σ_{k<=j} 2 flops = N² per candidate row
         achieved_tf = flops_launch / (var_launch_ms * 1e-3) / 1e12
         mma_products = 1.0 if fast_rank else 3.0
-        fit_tflops = (2.0 * N ** 3 / 3.0) / (mean("fit_ms") * 1e-3) / 1e12   # Cholesky N³/3 + inverse N³/3
+        # FP64 flops of the fit: Cholesky N³/3; the lazy inverse (default when the sweep prunes) adds only the leading rows of L⁻¹
+        # the pruning pass contracts with (lead³/3) and two triangular solves; a full inverse adds N³/3
+        lazy_fit = bool(pruned)
+        lead = min(N, 512 * ((((N + 255) // 256 + 1) // 2 + 7) // 8))
+        fit_flops = N ** 3 / 3.0 + (lead ** 3 / 3.0 + 4.0 * N * N if lazy_fit else N ** 3 / 3.0)
+        fit_tflops = fit_flops / (mean("fit_ms") * 1e-3) / 1e12
+        fp64_peak = eng.fp64_peak_tflops()
         kernel = "tc_rank_kernel" if rank_tc else ("tc_variance_pair_kernel" if os.environ.get("KBO_TC_PAIR", "1") != "0" else "tc_variance_kernel")
         Npad = (N + 255) // 256 * 256
         kstar_bytes = rows_per_launch * Npad * 2.0
@@ -439,11 +445,14 @@ def main():
                          "measured_on": ("the full contraction, kbo_set_rank_prefix(h, 0), 3 steps through kbo_suggest_host in this run (%.1f ms per step): the product "
                                          "path above prunes with the same kernel over the first eighth of the trial tiles (%.2f ms per step) and contracts fully only "
                                          "the %d candidates that survive" % (fmean("total_ms"), mean("var_kernel_ms"), prefix_survivors)) if pruned else "the product path"},
-            "fit_fp64": {"kernels": "dgemm64_kernel (DMMA m8n8k4) + potf2_inv/trsm panel chain", "flops": 2.0 * N ** 3 / 3.0, "ms": mean("fit_ms"),
-                         "achieved_tflops": fit_tflops, "fp64_ceiling_tflops_measured_here": 18.0, "frac": fit_tflops / 18.0,
-                         "note": "the step's largest phase since the pruning pass; FP64 by contract (fp32 Cholesky / alpha move EI by up to 4e-4). The ceiling is this "
-                                 "repo's own measurement of DFMA/DMMA GEMMs on B200 (profiles/README.md, FP64 ceiling), not a MEASURED_PEAKS.json entry; the "
-                                 "Cholesky is a chain of 128 single-CTA diagonal blocks, latency- not throughput-bound"},
+            "fit_fp64": {"bound": "tensor (FP64 DMMA)", "kernels": "dgemm64_kernel (DMMA m8n8k4) + potf2_inv / trsm_panel chain on its own SM partition",
+                         "flops": fit_flops, "ms": mean("fit_ms"), "achieved": fit_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fit_tflops / fp64_peak,
+                         "peak_source": "measured in this run: DMMA m8n8k4 on register operands, one 256-thread CTA per SM (kbo_debug_fp64_peak; "
+                                        "MEASURED_PEAKS.json has no FP64 entry)",
+                         "inverse": "lazy: leading %d rows of L^-1 + two panel solves" % lead if lazy_fit else "full",
+                         "note": "the step's largest phase; FP64 by contract (fp32 Cholesky / alpha move EI by up to 4e-4). The trailing updates run at "
+                                 "~24 TFLOP/s (K = 256 GEMMs, tests/studies/dgemm_probe.cu); the rest of the gap is the dependent chain of 128 "
+                                 "single-CTA diagonal blocks, which the second half of the factorisation waits on"},
             "kstar_hbm": {"bound": "hbm", "kernel": "tc_kstar_kernel" if rank_tc else "cross_mean_kernel", "bytes_per_launch": kstar_bytes,
                           "launch_ms": cross_launch_ms, "achieved": kstar_bytes / (cross_launch_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                           "frac": kstar_bytes / (cross_launch_ms * 1e-3) / 1e9 / pk["hbm"],

@@ -112,6 +112,7 @@ def load() -> C.CDLL:
     lib.kbo_comm_size.argtypes = [vp]
     lib.kbo_allreduce_argmax.argtypes = [vp, vp, vp]
     lib.kbo_debug_rank_pass.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, vp]
+    lib.kbo_debug_fp64_peak.argtypes = [vp, pd]
     lib.kbo_fit.argtypes = [vp, vp, vp, i32, i32, C.POINTER(KboParams), C.c_int, vp]
     lib.kbo_fit_info.argtypes = [vp, pd, pd, pd, pd, C.POINTER(i32), vp]
     lib.kbo_fit_state.argtypes = [vp, vp, vp, vp, vp]
@@ -134,7 +135,7 @@ def load() -> C.CDLL:
     lib.kbo_cma_state.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
     lib.kbo_cma_run_synthetic.argtypes = [vp, vp, i32, i32, pd, C.POINTER(C.c_float), pd]
     lib.kbo_tc_variance_raw.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp, dbl, vp, vp, i32, vp]
-    for name in EXPORTS + ["kbo_tc_variance_raw", "kbo_debug_rank_pass"]:
+    for name in EXPORTS + ["kbo_tc_variance_raw", "kbo_debug_rank_pass", "kbo_debug_fp64_peak"]:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("kbo_version",):
             fn.restype = C.c_int

@@ -46,7 +46,7 @@ void kbo_destroy(kbo_handle* h) {
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
                     &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal,
                     &h->ks_center, &h->ks_Xh, &h->ks_Xl, &h->ks_nxal, &h->ks_Ch, &h->ks_Cl, &h->ks_nc, &h->rk_part, &h->cal_idx, &h->cal_x, &h->cal_mu,
-                    &h->comm_buf, &h->T2, &h->Linv4, &h->sv_B, &h->sv_V, &h->sv_bar, &h->lml_yn, &h->lml_scal, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
+                    &h->comm_buf, &h->T2, &h->Linv4, &h->mu_part, &h->sv_B, &h->sv_V, &h->sv_bar, &h->lml_yn, &h->lml_scal, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
                     &h->rk_sched[6].dev, &h->rk_sched[7].dev, &h->pr_list, &h->pr_x, &h->pr_mu, &h->pr_var, &h->cal_mu_rk, &h->cal_var_rk};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -353,6 +353,50 @@ int kbo_acq_argmax(kbo_handle* h, const float* mu_n, const float* var_n, int64_t
   if (acq < KBO_ACQ_EI || acq > KBO_ACQ_PI) KBO_FAIL(h, KBO_ERR_INVALID, "kbo_acq_argmax: unknown acquisition %d", acq);
   return kbo_i_acq_argmax_f32(h, mu_n, var_n, M, global_offset, acq, y_mean, y_std, y_opt, xi, kappa, 1.0, acq_out, best_dev,
                               (cudaStream_t)stream);
+}
+
+// Test hook (not in kbo.h): the FP64 tensor-core rate of this GPU — DMMA m8n8k4 on register-resident operands, 8 independent
+// accumulator tiles per warp, 8 warps per CTA, one CTA per SM — the denominator bench.py's fit roofline uses (there is no FP64 entry
+// in MEASURED_PEAKS.json).  Same loop as tests/studies/dmma_probe.cu.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) {
+  double a = threadIdx.x * 1e-3, b = threadIdx.x * 1e-4 + 1.0, c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; j++) c[j][0] = c[j][1] = 0.0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s += c[j][0] + c[j][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+int kbo_debug_fp64_peak(kbo_handle* h, double* tflops_out) {
+  if (!h || !tflops_out) return KBO_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const int iters = 20000, ctas = h->sm_count;
+  double* out = nullptr;
+  KBO_CUDA(h, cudaMalloc(&out, sizeof(double) * (size_t)ctas * 256));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0, 0);
+    fp64_peak_kernel<<<ctas, 256>>>(out, iters);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  KBO_CUDA(h, cudaGetLastError());
+  *tflops_out = 2.0 * 8 * 8 * 4 * 8.0 * iters * 8 * ctas / (best * 1e-3) * 1e-12;
+  return KBO_OK;
 }
 
 // Test hook (not in kbo.h): the ranking pass alone over M candidates (device pointer), normalised mean / variance copied to

@@ -20,6 +20,10 @@ enum { TS_NONE = 0, TS_LOWER = 1 };
 // active, `mio_throttle` the top stall — profiles/README.md.)
 #define DG_LDK (DG_BK + 4)
 #define DG_LDB (DG_BN + 4)
+#define DG_A_DOUBLES (DG_BM * DG_LDK)
+#define DG_B_DOUBLES (DG_BN * DG_LDK > DG_BK * DG_LDB ? DG_BN * DG_LDK : DG_BK * DG_LDB)
+#define DG_STAGE_DOUBLES (DG_A_DOUBLES + DG_B_DOUBLES)
+#define DG_SMEM_BYTES (2 * DG_STAGE_DOUBLES * 8 + 2 * DG_BM * 8)   // two slabs + the row-sum epilogue's scratch
 
 // FP64 tensor-core MMA (DMMA), warp-level: D(8×8) += A(8×4)·B(4×8).  Fragments (lane = 4g + t): a = A[g][t], b = B[t][g],
 // c/d = C[g][2t], C[g][2t+1].  B200's FP64 tensor rate is about twice its vector DFMA rate, and a fragment load feeds 256
@@ -39,10 +43,18 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   A += (long long)blockIdx.z * strideA;
   B += (long long)blockIdx.z * strideB;
   C += (long long)blockIdx.z * strideC;
-  __shared__ double As[DG_BM][DG_LDK];
-  __shared__ double Bs_raw[DG_BN * DG_LDK > DG_BK * DG_LDB ? DG_BN * DG_LDK : DG_BK * DG_LDB];
+  // two slabs of shared memory: the next slab is stored while the current one is consumed, one barrier per slab
+  extern __shared__ __align__(16) double dg_smem[];
+  double(*As)[DG_LDK] = reinterpret_cast<double(*)[DG_LDK]>(dg_smem);
+  double* Bs_raw = dg_smem + DG_A_DOUBLES;
   double(*Bt)[DG_LDK] = reinterpret_cast<double(*)[DG_LDK]>(Bs_raw);   // TRANSB: [n][k]
   double(*Bn)[DG_LDB] = reinterpret_cast<double(*)[DG_LDB]>(Bs_raw);   // NN:     [k][n]
+  auto flip = [&](int buf) {
+    As = reinterpret_cast<double(*)[DG_LDK]>(dg_smem + buf * DG_STAGE_DOUBLES);
+    Bs_raw = dg_smem + buf * DG_STAGE_DOUBLES + DG_A_DOUBLES;
+    Bt = reinterpret_cast<double(*)[DG_LDK]>(Bs_raw);
+    Bn = reinterpret_cast<double(*)[DG_LDB]>(Bs_raw);
+  };
   const int m0 = blockIdx.y * DG_BM, n0 = blockIdx.x * DG_BN;
   if (tileskip == TS_LOWER && n0 > m0 + DG_BM - 1) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -120,11 +132,23 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
   if (kb < ke) {
     prefetch(kb);
     commit();
+    if (kb + DG_BK < ke) prefetch(kb + DG_BK);
   }
   __syncthreads();
+  int buf = 0;
   for (int k0 = kb; k0 < ke; k0 += DG_BK) {
     const bool more = k0 + DG_BK < ke;
-    if (more) prefetch(k0 + DG_BK);
+    if (more) {   // the next slab (in registers since the previous iteration) goes to the other buffer, the one after it is requested
+      double(*Ac)[DG_LDK] = As;
+      double(*Btc)[DG_LDK] = Bt;
+      double(*Bnc)[DG_LDB] = Bn;
+      flip(buf ^ 1);
+      commit();
+      if (k0 + 2 * DG_BK < ke) prefetch(k0 + 2 * DG_BK);
+      As = Ac;
+      Bt = Btc;
+      Bn = Bnc;
+    }
 #pragma unroll
     for (int k4 = 0; k4 < DG_BK; k4 += 4) {
       double a[4], b[4];
@@ -137,8 +161,8 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
 #pragma unroll
         for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    __syncthreads();
-    if (more) commit();
+    if (more) flip(buf ^ 1);
+    buf ^= 1;
     __syncthreads();
   }
 
@@ -159,7 +183,7 @@ dgemm64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const
         }
     }
   } else {  // EPI_ROWSUMSQ: C is part[M × ldc], column = this block's n-tile; fixed reduction order
-    __shared__ double rs[2][DG_BM];
+    double(*rs)[DG_BM] = reinterpret_cast<double(*)[DG_BM]>(dg_smem + 2 * DG_STAGE_DOUBLES);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       double s = 0.0;
@@ -184,6 +208,13 @@ static inline void dgemm64_launch(cudaStream_t s, int M, int N, int K, const dou
                                   double* C, int ldc, double alpha, double beta, int kmode, int kbegin, int tileskip,
                                   int batch = 1, long long strideA = 0, long long strideB = 0, long long strideC = 0) {
   dim3 grid((N + DG_BN - 1) / DG_BN, (M + DG_BM - 1) / DG_BM, batch);
-  dgemm64_kernel<TRANSB, EPI><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kmode, kbegin, tileskip,
+  static bool attr_set[16] = {};   // per instantiation and device: more than 48 KB of dynamic shared memory needs the opt-in
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    cudaFuncSetAttribute(dgemm64_kernel<TRANSB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES);
+    attr_set[dev] = true;
+  }
+  dgemm64_kernel<TRANSB, EPI><<<grid, 256, DG_SMEM_BYTES, s>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kmode, kbegin, tileskip,
                                                    strideA, strideB, strideC);
 }

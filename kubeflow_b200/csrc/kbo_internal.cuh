@@ -80,6 +80,7 @@ struct kbo_handle {
   int last_prefix_survivors = -1;  // candidates whose prefix upper bound reached the calibration rows' best value (-1: pass not run)
   DevBuf pr_list, pr_x, pr_mu, pr_var;   // pruning pass: survivor indices, their gathered rows, their ranking-pass mean / variance
   DevBuf cal_mu_rk, cal_var_rk;          // the ranking arithmetic on the calibration rows
+  DevBuf mu_part;                  // FP64 K* kernel with the trial tiles split over blockIdx.y: partial means [split][row]
   DevBuf cal_idx, cal_x, cal_mu;   // stratified calibration rows of the ranking pass: indices, gathered rows, FP64-path mean
   float last_rank_mu_err = 0.f;    // largest |μ̃ − μ| (normalised units) on the calibration rows of the last ranking sweep
   int last_unrefined = 0;          // 1: the last tensor-core sweep could not decide in FP64 (more near-ties than the cap)

@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(256, KBO_CM_MINB)
 cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* __restrict__ inv_ls, int n_ls,
                   const double* __restrict__ XsT, int ldx, const double* __restrict__ nx, int N, const double* __restrict__ alpha, int kind,
                   double amp, double* __restrict__ Ks64, int ldks, __half* __restrict__ Ksh,
-                  __half* __restrict__ Ksl, int Npad, MT* __restrict__ mun) {
+                  __half* __restrict__ Ksl, int Npad, MT* __restrict__ mun, double* __restrict__ mu_part) {
+  // gridDim.y > 1: the trial tiles are split over blockIdx.y (few candidate rows — the calibration rows — would otherwise leave
+  // half of the SMs idle); each split writes its partial mean to mu_part[split][row], summed in split order by mu_parts_kernel
   extern __shared__ __align__(16) unsigned char smraw[];
   const int Dp = (D + CM_DC - 1) / CM_DC * CM_DC;
   double* As = reinterpret_cast<double*>(smraw);        // [Dp][130]
@@ -52,12 +54,14 @@ cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* 
   }
   const int nd = Dp / CM_DC;
   const int ntiles = (N + CM_BN - 1) / CM_BN;
-  const int total = ntiles * nd;
+  const int tps = (ntiles + gridDim.y - 1) / gridDim.y;
+  const int tile0 = blockIdx.y * tps, tile1 = min(ntiles, tile0 + tps);
+  const int total = max(0, tile1 - tile0) * nd;
   double pf[8];
   double pf_nx = 0.0, pf_al = 0.0;
   // slab `it` = (tile it / nd, dims [ (it % nd)·32, +32 ) ): thread loads n = tid & 63, dd = (tid >> 6) + 4q
   auto prefetch = [&](int it) {
-    const int n0 = (it / nd) * CM_BN, d0 = (it % nd) * CM_DC;
+    const int n0 = (tile0 + it / nd) * CM_BN, d0 = (it % nd) * CM_DC;
     const int n = n0 + (tid & 63);
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -89,7 +93,7 @@ cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* 
   }
   __syncthreads();
   for (int it = 0; it < total; it++) {
-    const int tile = it / nd, dchunk = it % nd;
+    const int tile = tile0 + it / nd, dchunk = it % nd;
     if (dchunk == 0) {
 #pragma unroll
       for (int i = 0; i < 8; i++)
@@ -117,7 +121,7 @@ cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* 
       // branch-free epilogue: all 32 kernel values are computed unconditionally (inputs are always finite), so the whole
       // block is one scheduling region with 32 independent FP64 dependency chains to interleave.  Interior tiles (the
       // overwhelming majority) skip the row/column masks altogether; edge tiles mask the results at the end.
-      const int n0 = tile * CM_BN, tb = tile & 1;
+      const int n0 = tile * CM_BN, tb = (it / nd) & 1;
       double nxv[4], alv[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -160,7 +164,7 @@ cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* 
     if (it + 1 < total) commit(it + 1);
     __syncthreads();
   }
-  if (MODE == 1) {  // zero the padding columns [ntiles·64, Npad) of this CTA's rows (W is zero there, but 0·NaN must not happen)
+  if (MODE == 1 && blockIdx.y == gridDim.y - 1) {  // zero the padding columns [ntiles·64, Npad) of this CTA's rows (W is zero there, but 0·NaN must not happen)
     const int c0 = ntiles * CM_BN, w = Npad - c0;
     if (w > 0) {
       const int segs = w / 8;
@@ -178,8 +182,21 @@ cross_mean_kernel(const XT* __restrict__ Xc, int64_t rows, int D, const double* 
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const int64_t gm = m0 + ty + 16 * i;
-    if (tx == 0 && gm < rows) mun[gm] = (MT)s;
+    if (tx == 0 && gm < rows) {
+      if (gridDim.y > 1)
+        mu_part[(size_t)blockIdx.y * rows + gm] = s;
+      else
+        mun[gm] = (MT)s;
+    }
   }
+}
+template <typename MT>
+__global__ void mu_parts_kernel(const double* __restrict__ part, int64_t rows, int nsplit, MT* __restrict__ mun) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  double s = 0.0;
+  for (int j = 0; j < nsplit; j++) s += part[(size_t)j * rows + m];
+  mun[m] = (MT)s;
 }
 
 __global__ void var_from_parts_kernel(const double* __restrict__ part, int64_t rows, int njt, double amp, double* __restrict__ varn) {
@@ -688,10 +705,25 @@ static int launch_cross(kbo_handle* h, const XT* Xc, int64_t rows, int64_t rows_
                         cudaStream_t s) {
   const size_t smem = cross_smem_bytes(h->D, MODE);
   KBO_CUDA(h, cudaFuncSetAttribute(cross_mean_kernel<XT, MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cross_mean_kernel<XT, MT, MODE><<<(unsigned)((rows_grid + CM_BM - 1) / CM_BM), 256, smem, s>>>(
+  const unsigned gx = (unsigned)((rows_grid + CM_BM - 1) / CM_BM);
+  // fewer CTAs than one wave (two per SM): split the trial tiles so every SM works — the 74 CTAs of the calibration rows left half
+  // of the GPU idle for 1.5 ms
+  const int ntiles = (h->N + CM_BN - 1) / CM_BN;
+  int nsplit = 1;
+  if (gx < 2u * h->sm_count) nsplit = (int)min((unsigned)min(ntiles, 16), max(1u, 2u * h->sm_count / gx));
+  double* part = nullptr;
+  if (nsplit > 1) {
+    KBO_TRY(kbo_reserve(h, h->mu_part, sizeof(double) * (size_t)nsplit * rows));
+    part = (double*)h->mu_part.p;
+  }
+  cross_mean_kernel<XT, MT, MODE><<<dim3(gx, nsplit), 256, smem, s>>>(
       Xc, rows, h->D, (const double*)h->d_inv_ls.p, (int)h->inv_ls.size(), (const double*)h->XsT.p, h->ld, (const double*)h->nx.p, h->N,
-      (const double*)h->alpha.p, h->prm.kernel, h->prm.amplitude, Ks64, ldks, Ksh, Ksl, h->Npad, mun);
+      (const double*)h->alpha.p, h->prm.kernel, h->prm.amplitude, Ks64, ldks, Ksh, Ksl, h->Npad, mun, part);
   KBO_LAUNCH_CHECK(h);
+  if (nsplit > 1) {
+    mu_parts_kernel<MT><<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(part, rows, nsplit, mun);
+    KBO_LAUNCH_CHECK(h);
+  }
   return KBO_OK;
 }
 

@@ -55,9 +55,9 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ float rsqrt_ftz(float x) {
+__device__ __forceinline__ float sqrt_abs_ftz(float x) {   // MUFU.SQRT |x|: one instruction where max + rsqrt + multiply were three
   float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("{ .reg .f32 t; abs.ftz.f32 t, %1; sqrt.approx.ftz.f32 %0, t; }" : "=f"(r) : "f"(x));
   return r;
 }
 // kernel value from the dot product: KIND 0 = RBF (coordinates pre-scaled by 1/√2: k = exp(−d2)), 1 = Matérn-5/2 (pre-scaled by
@@ -69,8 +69,7 @@ __device__ __forceinline__ float ks_kernel_value(float dot, float nsum, float lo
     d2 = fmaxf(d2, 0.f);
     return ex2_ftz(fmaf(d2, -1.4426950408889634f, log2amp));
   }
-  d2 = fmaxf(d2, 1e-30f);
-  const float s = d2 * rsqrt_ftz(d2);
+  const float s = sqrt_abs_ftz(d2);   // d2 < 0 only by rounding (|d2| tiny): its magnitude is as good an estimate as 0
   const float p = fmaf(fmaf(s, 0.33333334f, 1.f), s, 1.f);
   return p * ex2_ftz(fmaf(s, -1.4426950408889634f, log2amp));
 }
@@ -193,20 +192,23 @@ tc_kstar_kernel(const __grid_constant__ CUtensorMap tmCh, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * KS_BN + cg * 64;
       const int n_base = t * KS_BN + cg * 64;
       const bool edge = n_base + 64 > N;   // warp-uniform: only the last tile(s) mask trials >= N
+      uint32_t rr[2][16];
+      tmem_ld16(taddr, rr[0]);
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        uint32_t r[16];
-        tmem_ld16(taddr + q * 16, r);
+        uint32_t(&r)[16] = rr[q & 1];
         tmem_ld_wait();
+        if (q < 3) tmem_ld16(taddr + (q + 1) * 16, rr[(q + 1) & 1]);   // the next 16 columns travel while these are evaluated
         if (q == 3) {   // everything this warp needs from the accumulator is in registers: hand it back to the MMA thread
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&S->tmem_empty[buf]));
         }
         uint32_t o[8];
+        float macc[4];   // four independent fp32 chains of four trials each, summed in FP64 once per 16 trials
 #pragma unroll
-        for (int g = 0; g < 4; g++) {   // groups of four trials: fp32 FMAs inside, FP64 across groups
-          float macc = 0.f;
+        for (int g = 0; g < 4; g++) {
+          macc[g] = 0.f;
 #pragma unroll
           for (int e = 0; e < 4; e += 2) {
             const int i = g * 4 + e;
@@ -217,13 +219,13 @@ tc_kstar_kernel(const __grid_constant__ CUtensorMap tmCh, const __grid_constant_
               k0 = (n_base + q * 16 + i < N) ? k0 : 0.f;
               k1 = (n_base + q * 16 + i + 1 < N) ? k1 : 0.f;
             }
-            macc = fmaf(k0, na.y, macc);
-            macc = fmaf(k1, na.w, macc);
+            macc[g] = fmaf(k0, na.y, macc[g]);
+            macc[g] = fmaf(k1, na.w, macc[g]);
             const __half2 h2 = __floats2half2_rn(k0, k1);
             o[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
           }
-          mu_d += (double)macc;
         }
+        mu_d += (double)((macc[0] + macc[1]) + (macc[2] + macc[3]));
         if (t < store_tiles)   // a pruning pass contracts a prefix of the trials only: the mean needs every column, the plane does not
           asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_row + (size_t)t * KS_BN + q * 16), "r"(o[0]), "r"(o[1]),
                        "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])

@@ -175,6 +175,12 @@ class GPEngine:
         1: among the best 4096 by fp32 value (window overflow); 2: not refined (exact ties beyond the cap / refinement off)."""
         return int(self.lib.kbo_last_unrefined(self._h))
 
+    def fp64_peak_tflops(self) -> float:
+        """Test / bench hook: the FP64 tensor-core (DMMA) rate of this GPU, measured on register-resident operands."""
+        out = C.c_double(0.0)
+        L.check(self.lib, self._h, self.lib.kbo_debug_fp64_peak(self._h, C.byref(out)))
+        return float(out.value)
+
     def rank_pass(self, Xc, mode: int, want_plane: bool = False):
         """Test hook: the ranking pass alone (mode 0: FP64 K* + one-product cluster kernel, 1: tensor-core K* + cta_group::2
         kernel) -> normalised mean, normalised variance (float32 CUDA tensors) and optionally the fp16 K* hi plane."""

@@ -685,7 +685,9 @@ def test_tensor_core_ranking_pass_returns_the_fp64_suggestion(N, M, D, kind, acq
     assert _same(bn, bo) and _same(bn, bs) and (bo.index, bo.value, bo.mu, bo.std) == (bs.index, bs.value, bs.mu, bs.std)
     assert bn.index == b6.index and abs(bn.value - b6.value) <= 1e-10 * max(1.0, abs(b6.value))
     assert new.last_unrefined() == 0 and 1 <= new.last_contenders() <= 4096
-    assert 0 < new.last_rank_mu_error() < 1e-2 and old.last_rank_mu_error() == 0.0
+    # the round-1 ranking pass takes its mean from the FP64 K* kernel, as the calibration rows do: they differ only by the summation
+    # order of the trial-tile split the kernel uses when it has few rows
+    assert 0 < new.last_rank_mu_error() < 1e-2 and old.last_rank_mu_error() < 1e-8
     if acq == "ei":
         assert new.last_prefix_survivors() <= 16384     # EI is decided by the mean: the prefix bound prunes (PI, bounded by 1 wherever
                                                         # the improvement is positive, may not — it then takes the full pass, or three products)
