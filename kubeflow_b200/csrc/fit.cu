@@ -681,6 +681,7 @@ static int fit_partition(kbo_handle* h) {
               d.GreenCtxCreate(&gc, dc, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
     ok = ok && d.GreenCtxCreate(&gr, dr, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
     ok = ok && d.GreenCtxStreamCreate((CUstream*)&h->s3_chain, gc, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
+         d.GreenCtxStreamCreate((CUstream*)&h->s3_near, gc, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
          d.GreenCtxStreamCreate((CUstream*)&h->s3_solve, gr, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
          d.GreenCtxStreamCreate((CUstream*)&h->s3_upd, gr, CU_STREAM_NON_BLOCKING, mid) == CUDA_SUCCESS &&
          d.GreenCtxStreamCreate((CUstream*)&h->s3_inv, gr, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS;
@@ -692,7 +693,7 @@ static int fit_partition(kbo_handle* h) {
       if (trace) fprintf(stderr, "[kbo fit] SM partition: chain %u SMs, rest %u SMs\n", chain.sm.smCount, rest.sm.smCount);
       return KBO_OK;
     }
-    for (cudaStream_t* st : {&h->s3_chain, &h->s3_solve, &h->s3_upd, &h->s3_inv})
+    for (cudaStream_t* st : {&h->s3_chain, &h->s3_near, &h->s3_solve, &h->s3_upd, &h->s3_inv})
       if (*st) {
         cudaStreamDestroy(*st);
         *st = nullptr;
@@ -702,13 +703,14 @@ static int fit_partition(kbo_handle* h) {
     cudaGetLastError();
   }
   KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_chain, cudaStreamNonBlocking, hi));
+  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_near, cudaStreamNonBlocking, hi));
   KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_solve, cudaStreamNonBlocking, hi));
   KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_upd, cudaStreamNonBlocking, mid));
   KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_inv, cudaStreamNonBlocking, lo));
   return KBO_OK;
 }
 void kbo_i_fit_partition_free(kbo_handle* h) {
-  for (cudaStream_t* st : {&h->s3_chain, &h->s3_solve, &h->s3_upd, &h->s3_inv})
+  for (cudaStream_t* st : {&h->s3_chain, &h->s3_near, &h->s3_solve, &h->s3_upd, &h->s3_inv})
     if (*st) {
       cudaStreamDestroy(*st);
       *st = nullptr;
@@ -719,11 +721,13 @@ void kbo_i_fit_partition_free(kbo_handle* h) {
 }
 
 static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s, int lead) {
-  const int OW = 256, NB = KBO_NB, n_panels = (N + OW - 1) / OW;
-  KBO_TRY(fit_streams(h, 3 * n_panels + 16));
+  // panel width: 256 (four 64-blocks per panel), or KBO_FIT_OW=512 (eight): wider panels make the trailing updates K = 512 GEMMs
+  static const int ow_env = getenv("KBO_FIT_OW") ? atoi(getenv("KBO_FIT_OW")) : 0;
+  const int OW = ow_env == 512 ? 512 : 256, NB = KBO_NB, n_panels = (N + OW - 1) / OW;
+  KBO_TRY(fit_streams(h, 6 * n_panels + 32));
   KBO_TRY(fit_partition(h));
   KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
-  KBO_TRY(kbo_reserve(h, h->Linv4, sizeof(double) * 4 * NB * NB));
+  KBO_TRY(kbo_reserve(h, h->Linv4, sizeof(double) * 8 * NB * NB));
   const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
   if (!h->attr_fit) {
     KBO_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -733,12 +737,15 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   }
   double* T = (double*)h->T.p;
   double* Linv4 = (double*)h->Linv4.p;
-  cudaStream_t sc = h->s3_chain, ss = h->s3_solve, su = h->s3_upd, si = h->s3_inv;
-  cudaEvent_t* ev_solve = h->ev_panel.data();                    // [n_panels]     panel's rows below the diagonal block are L
-  cudaEvent_t* ev_col = h->ev_panel.data() + n_panels;           // [n_panels + 1] column block P carries every earlier panel's update
-  cudaEvent_t* ev_chain = h->ev_panel.data() + 2 * n_panels + 1; // [n_panels]     diagonal block factored, its 64-block inverses in W
-  cudaEvent_t* ev_x = h->ev_panel.data() + 3 * n_panels + 1;     // pf[4], tr[4], start, 4 joins
-  cudaEvent_t *ev_pf = ev_x, *ev_tr = ev_x + 4, e_start = ev_x[8], *e_join = ev_x + 9;
+  cudaStream_t sc = h->s3_chain, sn = h->s3_near, ss = h->s3_solve, su = h->s3_upd, si = h->s3_inv;
+  cudaEvent_t* ev_solve = h->ev_panel.data();                     // [n_panels]     the FAR rows below the diagonal block (past the next block) are L
+  cudaEvent_t* ev_col = h->ev_panel.data() + n_panels;            // [n_panels + 1] column block P, rows below its diagonal block, carries every earlier update
+  cudaEvent_t* ev_chain = h->ev_panel.data() + 2 * n_panels + 1;  // [n_panels]     diagonal block factored, its 64-block inverses in W
+  cudaEvent_t* ev_near = h->ev_panel.data() + 3 * n_panels + 1;   // [n_panels + 1] diagonal block P carries every earlier update: the chain may start
+  cudaEvent_t* ev_nsolve = h->ev_panel.data() + 4 * n_panels + 2; // [n_panels]     the NEAR rows (the next diagonal block's rows) of panel P are L
+  cudaEvent_t* ev_rest = h->ev_panel.data() + 5 * n_panels + 2;   // [n_panels]     trailing update of panel P done
+  cudaEvent_t* ev_x = h->ev_panel.data() + 6 * n_panels + 2;      // pf[8], tr[8], start, 5 joins
+  cudaEvent_t *ev_pf = ev_x, *ev_tr = ev_x + 8, e_start = ev_x[16], *e_join = ev_x + 17;
   static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
   cudaEvent_t tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> tp;   // per panel on the chain stream: enqueued | column block ready | diagonal block done
@@ -756,7 +763,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));   // on the caller's stream: all SMs, not the chain's 8
   KBO_CUDA(h, cudaEventRecord(e_start, s));
-  for (cudaStream_t st : {sc, ss, su, si}) KBO_CUDA(h, cudaStreamWaitEvent(st, e_start, 0));
+  for (cudaStream_t st : {sc, sn, ss, su, si}) KBO_CUDA(h, cudaStreamWaitEvent(st, e_start, 0));
   const int RW = 512;
   int rp0 = 0;
   auto body = [&]() -> int {
@@ -764,7 +771,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
       const int Wd = min(OW, N - K0), rows_t = N - (K0 + Wd);
       const int nblk = (Wd + NB - 1) / NB;
       mark();
-      if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(sc, ev_col[P], 0));
+      if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(sc, ev_near[P], 0));
       mark();
       // ---- the chain (own SMs): the diagonal block only ------------------------------------------------------------------
       for (int b = 0; b < nblk; b++) {
@@ -786,36 +793,50 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
       }
       mark();
       KBO_CUDA(h, cudaEventRecord(ev_chain[P], sc));
-      // ---- the shadow: rows below the diagonal block, one 64-column block behind the chain --------------------------------------
+      // ---- the shadows: rows below the diagonal block, one 64-column block behind the chain.  NEAR = the rows of the next diagonal
+      // block (on the chain's SMs: 4-CTA kernels that must not queue behind GEMM blocks) — all the next panel's chain waits for is
+      // their solve and the 256×256 update of its diagonal block; FAR = the rest, on the big partition ------------------------------
       if (rows_t > 0) {
-        if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(ss, ev_col[P], 0));   // these rows of the column block carry the earlier updates too
-        for (int b = 0; b < nblk; b++) {
-          const int k = K0 + b * NB, jb = min(NB, N - k);
-          KBO_CUDA(h, cudaStreamWaitEvent(ss, ev_pf[b], 0));
-          double* Xb = A + (size_t)(K0 + Wd) * lda + k;
-          trsm_panel_kernel<<<(rows_t + 63) / 64, 256, smem, ss>>>(Xb, lda, rows_t, jb, Linv4 + (size_t)b * NB * NB, info_dev);
-          KBO_LAUNCH_CHECK(h);
-          const int ncols = K0 + Wd - (k + jb);   // the panel's columns right of this block
-          if (ncols > 0) {
-            KBO_CUDA(h, cudaStreamWaitEvent(ss, ev_tr[b], 0));   // L of the diagonal block's rows in this column block (the chain's trsm)
-            dgemm64_launch<true, EPI_STORE>(ss, rows_t, ncols, jb, Xb, lda, A + (size_t)(k + jb) * lda + k, lda, Xb + jb, lda, -1.0, 1.0, KM_FULL, 0, TS_NONE);
+        const int n_near = min(OW, rows_t), n_far = rows_t - n_near;
+        auto shadow = [&](cudaStream_t st, int r0, int nrows) -> int {
+          if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(st, ev_col[P], 0));   // these rows of the column block carry the earlier updates too
+          for (int b = 0; b < nblk; b++) {
+            const int k = K0 + b * NB, jb = min(NB, N - k);
+            KBO_CUDA(h, cudaStreamWaitEvent(st, ev_pf[b], 0));
+            double* Xb = A + (size_t)r0 * lda + k;
+            trsm_panel_kernel<<<(nrows + 63) / 64, 256, smem, st>>>(Xb, lda, nrows, jb, Linv4 + (size_t)b * NB * NB, info_dev);
             KBO_LAUNCH_CHECK(h);
+            const int ncols = K0 + Wd - (k + jb);   // the panel's columns right of this block
+            if (ncols > 0) {
+              KBO_CUDA(h, cudaStreamWaitEvent(st, ev_tr[b], 0));   // L of the diagonal block's rows in this column block (the chain's trsm)
+              dgemm64_launch<true, EPI_STORE>(st, nrows, ncols, jb, Xb, lda, A + (size_t)(k + jb) * lda + k, lda, Xb + jb, lda, -1.0, 1.0, KM_FULL, 0, TS_NONE);
+              KBO_LAUNCH_CHECK(h);
+            }
           }
-        }
-        KBO_CUDA(h, cudaEventRecord(ev_solve[P], ss));
-        // ---- trailing update: next column block first (the next panel's chain and shadow wait for it), then the rest --------------
-        KBO_CUDA(h, cudaStreamWaitEvent(su, ev_solve[P], 0));
-        const double* Pp = A + (size_t)(K0 + Wd) * lda + K0;
-        const int nb = min(OW, rows_t);
-        dgemm64_launch<true, EPI_STORE>(su, rows_t, nb, Wd, Pp, lda, Pp, lda, A + (size_t)(K0 + Wd) * lda + (K0 + Wd), lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+          return KBO_OK;
+        };
+        const int rn = K0 + Wd, rf = rn + n_near;
+        KBO_TRY(shadow(sn, rn, n_near));
+        KBO_CUDA(h, cudaEventRecord(ev_nsolve[P], sn));
+        // the next diagonal block's own update (after the previous panel's trailing update, which wrote the same block)
+        if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(sn, ev_rest[P - 1], 0));
+        const double* Ln = A + (size_t)rn * lda + K0;
+        dgemm64_launch<true, EPI_STORE>(sn, n_near, n_near, Wd, Ln, lda, Ln, lda, A + (size_t)rn * lda + rn, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
         KBO_LAUNCH_CHECK(h);
-        KBO_CUDA(h, cudaEventRecord(ev_col[P + 1], su));
-        const int rows_r = rows_t - nb;
-        if (rows_r > 0) {
-          const double* Pr = Pp + (size_t)nb * lda;
-          dgemm64_launch<true, EPI_STORE>(su, rows_r, rows_r, Wd, Pr, lda, Pr, lda, A + (size_t)(K0 + Wd + nb) * lda + (K0 + Wd + nb), lda, -1.0, 1.0,
-                                          KM_FULL, 0, TS_LOWER);
+        KBO_CUDA(h, cudaEventRecord(ev_near[P + 1], sn));
+        if (n_far > 0) {
+          KBO_TRY(shadow(ss, rf, n_far));
+          KBO_CUDA(h, cudaEventRecord(ev_solve[P], ss));
+          // ---- trailing update: the next column block below its diagonal block first (the next panel's shadows wait for it), then the rest
+          KBO_CUDA(h, cudaStreamWaitEvent(su, ev_solve[P], 0));
+          KBO_CUDA(h, cudaStreamWaitEvent(su, ev_nsolve[P], 0));
+          const double* Lf = A + (size_t)rf * lda + K0;
+          dgemm64_launch<true, EPI_STORE>(su, n_far, n_near, Wd, Lf, lda, Ln, lda, A + (size_t)rf * lda + rn, lda, -1.0, 1.0, KM_FULL, 0, TS_NONE);
           KBO_LAUNCH_CHECK(h);
+          KBO_CUDA(h, cudaEventRecord(ev_col[P + 1], su));
+          dgemm64_launch<true, EPI_STORE>(su, n_far, n_far, Wd, Lf, lda, Lf, lda, A + (size_t)rf * lda + rf, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+          KBO_LAUNCH_CHECK(h);
+          KBO_CUDA(h, cudaEventRecord(ev_rest[P], su));
         }
       }
       // ---- inverse stream: W_PP = L_PP⁻¹ by recursive doubling from the 64-block inverses, then the row panels of L⁻¹ -------------
@@ -839,7 +860,10 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
       if (rp0 < lead && (done - rp0 >= RW || done >= N)) {
         const int P0 = rp0, Pw = done - rp0;
         rp0 = done;
-        if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(si, ev_solve[P - 1], 0));   // rows [P0, done) of L left of this panel: the earlier shadows
+        if (P > 0) {   // rows [P0, done) of L left of this panel: the earlier panels' shadows
+          KBO_CUDA(h, cudaStreamWaitEvent(si, ev_solve[P - 1], 0));
+          KBO_CUDA(h, cudaStreamWaitEvent(si, ev_nsolve[P - 1], 0));
+        }
         double* Wrp = W + (size_t)P0 * ldw + P0;
         const double* Lrp = A + (size_t)P0 * lda + P0;
         for (int b = OW; b < Pw; b *= 2)
@@ -867,7 +891,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   const int rc = body();
   {
     int j = 0;
-    for (cudaStream_t st : {sc, ss, su, si}) {
+    for (cudaStream_t st : {sc, sn, ss, su, si}) {
       cudaEventRecord(e_join[j], st);
       cudaStreamWaitEvent(s, e_join[j], 0);
       j++;
@@ -876,7 +900,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   if (tr[0]) {
     int j = 1;
     for (cudaStream_t st : {sc, ss, su, si}) cudaEventRecord(tr[j++], st);
-    for (cudaStream_t st : {sc, ss, su, si}) cudaStreamSynchronize(st);
+    for (cudaStream_t st : {sc, sn, ss, su, si}) cudaStreamSynchronize(st);
     float t[5] = {0, 0, 0, 0, 0};
     for (int i = 1; i < 5; i++) cudaEventElapsedTime(&t[i], tr[0], tr[i]);
     fprintf(stderr, "[kbo fit v3 N=%d%s] chain stream done at %.3f ms, shadow %.3f, update %.3f, inverse %.3f ms\n", N, h->part_ok ? ", partitioned" : "", t[1],
