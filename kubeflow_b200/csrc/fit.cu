@@ -661,15 +661,33 @@ const DrvApi& drv() {
 }
 }  // namespace
 
-static int fit_partition(kbo_handle* h) {
-  if (h->part_tried) return KBO_OK;
-  h->part_tried = true;
+// ncu / nsys cannot instrument kernels launched into a green context ("Failed to prepare kernel for profiling" ends the process),
+// compute-sanitizer can: with a profiler's injection library mapped the fit keeps the plain streams.
+static bool profiler_attached() {
+  static const bool attached = [] {
+    FILE* f = fopen("/proc/self/maps", "r");
+    if (!f) return false;
+    char line[1024];
+    bool hit = false;
+    while (!hit && fgets(line, sizeof line, f))
+      hit = strstr(line, "nsight-compute") || strstr(line, "libcuda-injection") || strstr(line, "libnvperf_") || strstr(line, "nsight-systems") ||
+            strstr(line, "ToolsInjection");
+    fclose(f);
+    return hit;
+  }();
+  return attached;
+}
+
+// The five streams of the v3 factorisation: {chain, near shadow, far shadow, update, inverse}.  partitioned = true asks for the
+// green-context set (created once; falls back to the plain set if the driver cannot split the device).
+static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[5]) {
   int lo = 0, hi = 0;
   KBO_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
   const int mid = (lo + hi) / 2;
   static const bool off = getenv("KBO_FIT_NO_PARTITION") != nullptr;
   const DrvApi& d = drv();
-  if (!off && d.ok) {
+  if (partitioned && !h->part_tried && !off && d.ok && !profiler_attached()) {
+    h->part_tried = true;
     CUdevice dev;
     CUdevResource all, chain, rest;
     unsigned int nb = 1;
@@ -691,26 +709,30 @@ static int fit_partition(kbo_handle* h) {
       h->part_ok = true;
       static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
       if (trace) fprintf(stderr, "[kbo fit] SM partition: chain %u SMs, rest %u SMs\n", chain.sm.smCount, rest.sm.smCount);
-      return KBO_OK;
+    } else {
+      for (cudaStream_t* st : {&h->s3_chain, &h->s3_near, &h->s3_solve, &h->s3_upd, &h->s3_inv})
+        if (*st) {
+          cudaStreamDestroy(*st);
+          *st = nullptr;
+        }
+      if (gc) d.GreenCtxDestroy(gc);
+      if (gr) d.GreenCtxDestroy(gr);
+      cudaGetLastError();
     }
-    for (cudaStream_t* st : {&h->s3_chain, &h->s3_near, &h->s3_solve, &h->s3_upd, &h->s3_inv})
-      if (*st) {
-        cudaStreamDestroy(*st);
-        *st = nullptr;
-      }
-    if (gc) d.GreenCtxDestroy(gc);
-    if (gr) d.GreenCtxDestroy(gr);
-    cudaGetLastError();
   }
-  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_chain, cudaStreamNonBlocking, hi));
-  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_near, cudaStreamNonBlocking, hi));
-  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_solve, cudaStreamNonBlocking, hi));
-  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_upd, cudaStreamNonBlocking, mid));
-  KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3_inv, cudaStreamNonBlocking, lo));
+  if (partitioned && h->part_ok) {
+    out[0] = h->s3_chain, out[1] = h->s3_near, out[2] = h->s3_solve, out[3] = h->s3_upd, out[4] = h->s3_inv;
+    return KBO_OK;
+  }
+  if (!h->s3p[0]) {
+    const int prio[5] = {hi, hi, hi, mid, lo};
+    for (int i = 0; i < 5; i++) KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3p[i], cudaStreamNonBlocking, prio[i]));
+  }
+  for (int i = 0; i < 5; i++) out[i] = h->s3p[i];
   return KBO_OK;
 }
 void kbo_i_fit_partition_free(kbo_handle* h) {
-  for (cudaStream_t* st : {&h->s3_chain, &h->s3_near, &h->s3_solve, &h->s3_upd, &h->s3_inv})
+  for (cudaStream_t* st : {&h->s3_chain, &h->s3_near, &h->s3_solve, &h->s3_upd, &h->s3_inv, &h->s3p[0], &h->s3p[1], &h->s3p[2], &h->s3p[3], &h->s3p[4]})
     if (*st) {
       cudaStreamDestroy(*st);
       *st = nullptr;
@@ -725,7 +747,11 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   static const int ow_env = getenv("KBO_FIT_OW") ? atoi(getenv("KBO_FIT_OW")) : 0;
   const int OW = ow_env == 512 ? 512 : 256, NB = KBO_NB, n_panels = (N + OW - 1) / OW;
   KBO_TRY(fit_streams(h, 6 * n_panels + 32));
-  KBO_TRY(fit_partition(h));
+  // the SM partition pays when trailing updates big enough to fill the GPU run beside the chain; small factorisations (and any
+  // process a profiler is attached to) use plain priority streams
+  cudaStream_t st5[5];
+  KBO_TRY(fit_partition(h, N >= 2048, st5));
+  const bool partitioned = st5[0] == h->s3_chain && h->part_ok;
   KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
   KBO_TRY(kbo_reserve(h, h->Linv4, sizeof(double) * 8 * NB * NB));
   const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
@@ -737,7 +763,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   }
   double* T = (double*)h->T.p;
   double* Linv4 = (double*)h->Linv4.p;
-  cudaStream_t sc = h->s3_chain, sn = h->s3_near, ss = h->s3_solve, su = h->s3_upd, si = h->s3_inv;
+  cudaStream_t sc = st5[0], sn = st5[1], ss = st5[2], su = st5[3], si = st5[4];
   cudaEvent_t* ev_solve = h->ev_panel.data();                     // [n_panels]     the FAR rows below the diagonal block (past the next block) are L
   cudaEvent_t* ev_col = h->ev_panel.data() + n_panels;            // [n_panels + 1] column block P, rows below its diagonal block, carries every earlier update
   cudaEvent_t* ev_chain = h->ev_panel.data() + 2 * n_panels + 1;  // [n_panels]     diagonal block factored, its 64-block inverses in W
@@ -903,7 +929,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
     for (cudaStream_t st : {sc, sn, ss, su, si}) cudaStreamSynchronize(st);
     float t[5] = {0, 0, 0, 0, 0};
     for (int i = 1; i < 5; i++) cudaEventElapsedTime(&t[i], tr[0], tr[i]);
-    fprintf(stderr, "[kbo fit v3 N=%d%s] chain stream done at %.3f ms, shadow %.3f, update %.3f, inverse %.3f ms\n", N, h->part_ok ? ", partitioned" : "", t[1],
+    fprintf(stderr, "[kbo fit v3 N=%d%s] chain stream done at %.3f ms, shadow %.3f, update %.3f, inverse %.3f ms\n", N, partitioned ? ", partitioned" : "", t[1],
             t[2], t[3], t[4]);
     double sum[2] = {0, 0};
     for (size_t i = 0; i + 2 < tp.size(); i += 3) {

@@ -869,3 +869,50 @@ def test_lazy_inverse_sweep_matches_the_full_fit(N, M, D, kind, acq):
     assert b2l.index == b2e.index and abs(b2l.value - b2e.value) <= 1e-9
     for e in (lazy, eager, e64):
         e.close()
+
+
+@pytest.mark.parametrize("N,M,D,mode", [(700, 5000, 5, "tc"), (2304, 20000, 16, "tc"), (1500, 4000, 7, "f64")])
+def test_fit_variants_agree(N, M, D, mode, tmp_path):
+    """The factorisation's schedules — v3 (default: diagonal-block chain on its own SM partition, shadow panel solve), the same
+    without the partition, v2 (look-ahead, one-GEMM panel solve), the one-stream sequence — are the same arithmetic up to the
+    order the trailing updates are applied in: L, W, alpha, LML and the suggestion agree to FP64 rounding, and all of them with
+    the oracle's Cholesky."""
+    import os, subprocess, sys
+    runs = {}
+    for name, env in (("v3", {}), ("v3-unpartitioned", {"KBO_FIT_NO_PARTITION": "1"}), ("v2", {"KBO_FIT_V2": "1"}), ("serial", {"KBO_FIT_SERIAL": "1"}),
+                      ("v3-512", {"KBO_FIT_OW": "512"})):
+        out = str(tmp_path / f"{name}.npz")
+        subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_fit_variant.py"), str(N), str(M), str(D), mode, out],
+                       check=True, env={**os.environ, **env}, timeout=300)
+        runs[name] = np.load(out)
+    X, y, _ = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    fit = O.gp_fit(X, y, kind="matern52", length_scale=th["length_scale"], amplitude=th["amplitude"], noise=th["noise"])
+    ref = runs["serial"]
+    scale = np.abs(fit["L"]).max()
+    assert np.abs(np.tril(ref["L"]) - fit["L"]).max() <= 1e-11 * scale
+    for name, r in runs.items():
+        assert np.abs(np.tril(r["L"]) - np.tril(ref["L"])).max() <= 1e-12 * scale, name
+        assert np.abs(r["W"] - ref["W"]).max() <= 1e-9 * np.abs(ref["W"]).max(), name
+        np.testing.assert_allclose(r["alpha"], ref["alpha"], rtol=0, atol=1e-9 * np.abs(ref["alpha"]).max(), err_msg=name)
+        assert abs(float(r["lml"]) - float(ref["lml"])) <= 1e-10 * abs(float(ref["lml"])), name
+        assert int(r["index"]) == int(ref["index"]) and abs(float(r["value"]) - float(ref["value"])) <= 1e-10 * max(1.0, abs(float(ref["value"]))), name
+
+
+def test_fp64_kstar_kernel_gives_the_same_mean_for_few_and_many_rows():
+    """With fewer CTAs than one wave the FP64 K* kernel splits the trial tiles over blockIdx.y and sums the partial means in split
+    order: a candidate's mean must not depend (beyond FP64 rounding) on how many rows were swept with it."""
+    N, M, D = 1500, 40000, 9
+    X, y, Xc = O.synthetic(N, M, D)
+    g = dict(kind="matern52", acq="ei", **O.theta_of_record(D))
+    e = _engine(g, "f64"); e.tell(X, y)
+    _, mu_all, sd_all, _ = e.ask(Xc, return_arrays=True)
+    for rows in (1, 130, 3000):
+        _, mu, sd, _ = e.ask(Xc[:rows], return_arrays=True)
+        np.testing.assert_allclose(mu.cpu().numpy(), mu_all.cpu().numpy()[:rows], rtol=0, atol=1e-12 * max(1.0, float(mu_all.abs().max())))
+        np.testing.assert_allclose(sd.cpu().numpy(), sd_all.cpu().numpy()[:rows], rtol=0, atol=1e-10)
+    fit = O.gp_fit(X, y, kind="matern52", length_scale=g["length_scale"], amplitude=g["amplitude"], noise=g["noise"])
+    mu_ref, _ = O.gp_predict(fit, Xc[:130])
+    _, mu, _, _ = e.ask(Xc[:130], return_arrays=True)
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_ref, rtol=0, atol=1e-8)
+    e.close()

@@ -19,7 +19,8 @@ def theta_of_record(D):
     return dict(length_scale=0.3 * np.sqrt(D), amplitude=1.0, noise=1e-3, xi=0.01, kappa=1.96)
 
 
-for N, M, D, mode in ((70, 300, 3, "f64"), (135, 515, 5, "tc"), (300, 700, 33, "tc"), (700, 1900, 40, "tc")):   # the last: 2 tile pairs -> pruning pass
+for N, M, D, mode in ((70, 300, 3, "f64"), (135, 515, 5, "tc"), (300, 700, 33, "tc"), (700, 1900, 40, "tc"),   # 700: 2 tile pairs -> pruning pass
+                      (1100, 2500, 12, "tc")):   # 1100: lazy inverse (leading 512 rows of W), alpha and survivors by the cooperative panel solves, 5 panels of the look-ahead factorisation
     X, y, Xc = synthetic(N, M, D)
     th = theta_of_record(D)
     e = GPEngine(0, kernel="matern52", acq="ei", var_mode=mode, **th)
