@@ -40,17 +40,19 @@ __device__ __forceinline__ void sv_grid_barrier(unsigned* ctr, unsigned& target)
 //   (b) B_>P −= L_>P,P·V_P — one warp per row below, grid-strided, V_P in shared memory as [rhs][k] (conflict-free).
 // Fixed-order butterfly reductions: a right-hand side's result does not depend on the grid size or on what rides beside it.
 __global__ void __launch_bounds__(256)
-sv_forward_kernel(const double* __restrict__ L, const double* __restrict__ W, int N, int ld, double* B, double* V, unsigned* bar) {
-  __shared__ double vs[SV_R * SV_P];
+sv_forward_kernel(const double* __restrict__ L, const double* __restrict__ W, int N, int ld, double* B, double* V, unsigned* bar, int G, size_t gstride) {
+  // G groups of 8 right-hand sides ride one launch (group g at B + g·gstride): the rows of L and W_PP are loaded once and every group
+  // goes through the arithmetic of a single-group solve, so a right-hand side's result does not depend on G either
+  extern __shared__ double vs_all[];   // [G][SV_R][SV_P]
   unsigned target = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
   for (int K0 = 0; K0 < N; K0 += SV_P) {
     const int Wd = min(SV_P, N - K0);
     if (blockIdx.x * 8 < Wd) {   // (a)
-      for (int e = threadIdx.x; e < SV_P * SV_R; e += 256) {
-        const int k = e / SV_R, q = e % SV_R;
-        vs[q * SV_P + k] = k < Wd ? __ldcg(B + (size_t)(K0 + k) * SV_R + q) : 0.0;
+      for (int e = threadIdx.x; e < G * SV_P * SV_R; e += 256) {
+        const int g = e / (SV_P * SV_R), k = (e / SV_R) % SV_P, q = e % SV_R;
+        vs_all[(size_t)g * SV_R * SV_P + q * SV_P + k] = k < Wd ? __ldcg(B + g * gstride + (size_t)(K0 + k) * SV_R + q) : 0.0;
       }
       __syncthreads();
       const int r = gwarp;
@@ -59,28 +61,31 @@ sv_forward_kernel(const double* __restrict__ L, const double* __restrict__ W, in
         double wv[SV_P / 32];
 #pragma unroll
         for (int i = 0; i < SV_P / 32; i++) wv[i] = lane + 32 * i <= r ? w[lane + 32 * i] : 0.0;
-        double acc[SV_R];
+        for (int g = 0; g < G; g++) {
+          const double* vs = vs_all + (size_t)g * SV_R * SV_P;
+          double acc[SV_R];
 #pragma unroll
-        for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
+          for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
 #pragma unroll
-        for (int i = 0; i < SV_P / 32; i++)
+          for (int i = 0; i < SV_P / 32; i++)
 #pragma unroll
-          for (int q = 0; q < SV_R; q++) acc[q] = fma(wv[i], vs[q * SV_P + lane + 32 * i], acc[q]);
+            for (int q = 0; q < SV_R; q++) acc[q] = fma(wv[i], vs[q * SV_P + lane + 32 * i], acc[q]);
 #pragma unroll
-        for (int q = 0; q < SV_R; q++) {
-          double v = acc[q];
+          for (int q = 0; q < SV_R; q++) {
+            double v = acc[q];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) V[(size_t)(K0 + r) * SV_R + q] = v;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) V[g * gstride + (size_t)(K0 + r) * SV_R + q] = v;
+          }
         }
       }
     }
     sv_grid_barrier(bar, target);
     const int below = N - (K0 + Wd);
     if (below > 0) {   // (b)
-      for (int e = threadIdx.x; e < SV_P * SV_R; e += 256) {
-        const int k = e / SV_R, q = e % SV_R;
-        vs[q * SV_P + k] = k < Wd ? __ldcg(V + (size_t)(K0 + k) * SV_R + q) : 0.0;
+      for (int e = threadIdx.x; e < G * SV_P * SV_R; e += 256) {
+        const int g = e / (SV_P * SV_R), k = (e / SV_R) % SV_P, q = e % SV_R;
+        vs_all[(size_t)g * SV_R * SV_P + q * SV_P + k] = k < Wd ? __ldcg(V + g * gstride + (size_t)(K0 + k) * SV_R + q) : 0.0;
       }
       __syncthreads();
       for (int r = gwarp; r < below; r += nwarps) {
@@ -88,21 +93,24 @@ sv_forward_kernel(const double* __restrict__ L, const double* __restrict__ W, in
         double lv[SV_P / 32];
 #pragma unroll
         for (int i = 0; i < SV_P / 32; i++) lv[i] = lane + 32 * i < Wd ? l[lane + 32 * i] : 0.0;
-        double acc[SV_R];
+        for (int g = 0; g < G; g++) {
+          const double* vs = vs_all + (size_t)g * SV_R * SV_P;
+          double acc[SV_R];
 #pragma unroll
-        for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
+          for (int q = 0; q < SV_R; q++) acc[q] = 0.0;
 #pragma unroll
-        for (int i = 0; i < SV_P / 32; i++)
+          for (int i = 0; i < SV_P / 32; i++)
 #pragma unroll
-          for (int q = 0; q < SV_R; q++) acc[q] = fma(lv[i], vs[q * SV_P + lane + 32 * i], acc[q]);
+            for (int q = 0; q < SV_R; q++) acc[q] = fma(lv[i], vs[q * SV_P + lane + 32 * i], acc[q]);
 #pragma unroll
-        for (int q = 0; q < SV_R; q++) {
-          double v = acc[q];
+          for (int q = 0; q < SV_R; q++) {
+            double v = acc[q];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) {
-            double* o = B + (size_t)(K0 + Wd + r) * SV_R + q;
-            *o = __ldcg(o) - v;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) {
+              double* o = B + g * gstride + (size_t)(K0 + Wd + r) * SV_R + q;
+              *o = __ldcg(o) - v;
+            }
           }
         }
       }
@@ -210,21 +218,40 @@ __global__ void sv_col_kernel(const double* __restrict__ src, int N, int stride_
 
 }  // namespace
 
-static int sv_coop_launch(kbo_handle* h, const void* fn, double* X0, double* X1, cudaStream_t s) {
+#define SV_GMAX 8   // groups of 8 right-hand sides per forward launch (16 KB of shared memory each)
+static int sv_bar_reset(kbo_handle* h, cudaStream_t s) {
   KBO_TRY(kbo_reserve(h, h->sv_bar, 256));
   KBO_CUDA(h, cudaMemsetAsync(h->sv_bar.p, 0, sizeof(unsigned), s));
+  return KBO_OK;
+}
+// B (G groups of N × 8, overwritten: scratch) -> V = L⁻¹·B.  Needs the diagonal-block inverses in W's diagonal 256-blocks.
+int kbo_i_solve_fwd(kbo_handle* h, double* B, double* V, cudaStream_t s, int G, size_t gstride) {
+  KBO_TRY(sv_bar_reset(h, s));
   const double* L = (const double*)h->K.p;
   const double* W = (const double*)h->W.p;
   int N = h->N, ld = h->ld;
   unsigned* bar = (unsigned*)h->sv_bar.p;
-  void* args[] = {(void*)&L, (void*)&W, (void*)&N, (void*)&ld, (void*)&X0, (void*)&X1, (void*)&bar};
-  KBO_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(h->sm_count), dim3(256), args, 0, s));   // one CTA per SM: co-resident by construction
+  const size_t smem = sizeof(double) * (size_t)G * SV_R * SV_P;
+  static bool attr = false;
+  if (!attr) {
+    KBO_CUDA(h, cudaFuncSetAttribute(sv_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * SV_GMAX * SV_R * SV_P)));
+    attr = true;
+  }
+  void* args[] = {(void*)&L, (void*)&W, (void*)&N, (void*)&ld, (void*)&B, (void*)&V, (void*)&bar, (void*)&G, (void*)&gstride};
+  KBO_CUDA(h, cudaLaunchCooperativeKernel((const void*)sv_forward_kernel, dim3(h->sm_count), dim3(256), args, smem, s));   // one CTA per SM: co-resident
   return KBO_OK;
 }
-// B (N × 8, overwritten: scratch) -> V = L⁻¹·B (N × 8).  Needs the diagonal-block inverses in W's diagonal 256-blocks.
-int kbo_i_solve_fwd(kbo_handle* h, double* B, double* V, cudaStream_t s) { return sv_coop_launch(h, (const void*)sv_forward_kernel, B, V, s); }
 // Z (N × 8, overwritten) -> A = L⁻ᵀ·Z (N × 8)
-int kbo_i_solve_bwd(kbo_handle* h, double* Z, double* A, cudaStream_t s) { return sv_coop_launch(h, (const void*)sv_backward_kernel, Z, A, s); }
+int kbo_i_solve_bwd(kbo_handle* h, double* Z, double* A, cudaStream_t s) {
+  KBO_TRY(sv_bar_reset(h, s));
+  const double* L = (const double*)h->K.p;
+  const double* W = (const double*)h->W.p;
+  int N = h->N, ld = h->ld;
+  unsigned* bar = (unsigned*)h->sv_bar.p;
+  void* args[] = {(void*)&L, (void*)&W, (void*)&N, (void*)&ld, (void*)&Z, (void*)&A, (void*)&bar};
+  KBO_CUDA(h, cudaLaunchCooperativeKernel((const void*)sv_backward_kernel, dim3(h->sm_count), dim3(256), args, 0, s));
+  return KBO_OK;
+}
 
 // alpha = L⁻ᵀ(L⁻¹·yn) into h->alpha (what fit_finish computes as Wᵀ(W·yn) when W is formed)
 int kbo_i_alpha_by_solves(kbo_handle* h, cudaStream_t s) {
@@ -236,27 +263,34 @@ int kbo_i_alpha_by_solves(kbo_handle* h, cudaStream_t s) {
   KBO_CUDA(h, cudaMemsetAsync(B, 0, sizeof(double) * (size_t)N * SV_R, s));
   sv_col_kernel<<<(N + 255) / 256, 256, 0, s>>>((const double*)h->yn.p, N, 1, B, SV_R);
   KBO_LAUNCH_CHECK(h);
-  KBO_TRY(kbo_i_solve_fwd(h, B, V, s));      // V[:,0] = z
+  KBO_TRY(kbo_i_solve_fwd(h, B, V, s, 1, 0));      // V[:,0] = z
   KBO_TRY(kbo_i_solve_bwd(h, V, B, s));      // B[:,0] = alpha (V is consumed)
   sv_col_kernel<<<(N + 255) / 256, 256, 0, s>>>(B, N, SV_R, (double*)h->alpha.p, 1);
   KBO_LAUNCH_CHECK(h);
   return KBO_OK;
 }
 
-// varn64[c] = amp − ‖L⁻¹ k*_c‖² for the n rows of Ks (n × ld, FP64 K*), groups of 8
+// varn64[c] = amp − ‖L⁻¹ k*_c‖² for the n rows of Ks (n × ld, FP64 K*): up to 64 right-hand sides (8 groups of 8) per forward solve
 int kbo_i_variance_by_solves(kbo_handle* h, const double* Ks, int n, double* varn64, cudaStream_t s) {
   const int N = h->N, ld = h->ld;
-  KBO_TRY(kbo_reserve(h, h->sv_B, sizeof(double) * (size_t)(N + SV_P) * SV_R));
-  KBO_TRY(kbo_reserve(h, h->sv_V, sizeof(double) * (size_t)(N + SV_P) * SV_R));
+  const size_t gstride = (size_t)(N + SV_P) * SV_R;
+  KBO_TRY(kbo_reserve(h, h->sv_B, sizeof(double) * gstride * SV_GMAX));
+  KBO_TRY(kbo_reserve(h, h->sv_V, sizeof(double) * gstride * SV_GMAX));
   double* B = (double*)h->sv_B.p;
   double* V = (double*)h->sv_V.p;
-  for (int c0 = 0; c0 < n; c0 += SV_R) {
-    const int nq = n - c0 < SV_R ? n - c0 : SV_R;
-    sv_pack_kernel<<<(N + 255) / 256, 256, 0, s>>>(Ks, ld, N, c0, nq, B);
-    KBO_LAUNCH_CHECK(h);
-    KBO_TRY(kbo_i_solve_fwd(h, B, V, s));
-    sv_sumsq_kernel<<<nq, 256, 0, s>>>(V, N, h->prm.amplitude, varn64 + c0);
-    KBO_LAUNCH_CHECK(h);
+  for (int c0 = 0; c0 < n; c0 += SV_R * SV_GMAX) {
+    const int nc = n - c0 < SV_R * SV_GMAX ? n - c0 : SV_R * SV_GMAX, G = (nc + SV_R - 1) / SV_R;
+    for (int g = 0; g < G; g++) {
+      const int nq = nc - g * SV_R < SV_R ? nc - g * SV_R : SV_R;
+      sv_pack_kernel<<<(N + 255) / 256, 256, 0, s>>>(Ks, ld, N, c0 + g * SV_R, nq, B + g * gstride);
+      KBO_LAUNCH_CHECK(h);
+    }
+    KBO_TRY(kbo_i_solve_fwd(h, B, V, s, G, gstride));
+    for (int g = 0; g < G; g++) {
+      const int nq = nc - g * SV_R < SV_R ? nc - g * SV_R : SV_R;
+      sv_sumsq_kernel<<<nq, 256, 0, s>>>(V + g * gstride, N, h->prm.amplitude, varn64 + c0 + g * SV_R);
+      KBO_LAUNCH_CHECK(h);
+    }
   }
   return KBO_OK;
 }

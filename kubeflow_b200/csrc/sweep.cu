@@ -746,6 +746,7 @@ static cudaEvent_t* ev_pair(kbo_handle* h, std::vector<std::pair<cudaEvent_t, cu
   if (_ev) cudaEventRecord((&_ev[0])[1], s);
 
 // FP64 evaluation of the n contenders in list (sorted here) and the first-index argmax over them -> best_dev
+#define KBO_SOLVE_CAP 256   // survivors a lazy fit evaluates by triangular solves with L before it forms the rest of L⁻¹ instead
 static int refine_evaluate(kbo_handle* h, const void* Xc, int xc_dtype, int n, int* list, int* count, int64_t goff, kbo_best* best_dev, cudaStream_t s);
 
 static int refine_suggestion(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, kbo_best* best_dev, cudaStream_t s) {
@@ -805,7 +806,7 @@ static int refine_evaluate(kbo_handle* h, const void* Xc, int xc_dtype, int n, i
   KBO_LAUNCH_CHECK(h);
   refine_mu_kernel<<<n, 256, 0, s>>>((const double*)h->Ks64.p, ld, N, (const double*)h->alpha.p, mun64);
   KBO_LAUNCH_CHECK(h);
-  if (!h->w_full && n <= 64) {
+  if (!h->w_full && n <= KBO_SOLVE_CAP) {
     // lazy inverse: ‖L⁻¹k*‖² by panel solves with the factor itself (solve.cu) — no W
     KBO_TRY(kbo_i_variance_by_solves(h, (const double*)h->Ks64.p, n, varn64, s));
   } else {
@@ -1075,13 +1076,12 @@ calib_prefix_kernel(const float* __restrict__ v_rk, const float* __restrict__ v_
 }
 
 #define KBO_PRUNE_CAP 16384
-#define KBO_SOLVE_CAP 64
 // The pruning sweep of a LAZY fit (only the leading rows of W exist): everything it touches is the factor L, alpha, and the
 // leading block of W.  Calibration: exact mean (FP64 K* kernel) and exact PREFIX variance (three products over the prefix's
 // tiles) against the ranking arithmetic over the same prefix -> E, Emu.  Lower bound on the maximum: the sigma -> 0 limit of
 // the acquisition function over the whole grid (for EI: the largest predicted improvement) — free.  Candidates whose prefix
 // upper bound reaches it (normally a handful) are evaluated EXACTLY in FP64 by panel solves with L and the first-index
-// argmax is taken over those values: no ranking pass, no interval test.  *pruned = 0 (more than 64 such candidates, or no
+// argmax is taken over those values: no ranking pass, no interval test.  *pruned = 0 (more than 256 such candidates, or no
 // usable lower bound): the caller forms the rest of W and runs the sweep of a full fit.
 static int prune_sweep_lead(kbo_handle* h, const void* Xc, int xc_dtype, int64_t M, int64_t goff, int64_t chunk, kbo_best* best_dev, int* pruned,
                             cudaStream_t s) {

@@ -916,3 +916,30 @@ def test_fp64_kstar_kernel_gives_the_same_mean_for_few_and_many_rows():
     _, mu, _, _ = e.ask(Xc[:130], return_arrays=True)
     np.testing.assert_allclose(mu.cpu().numpy(), mu_ref, rtol=0, atol=1e-8)
     e.close()
+
+
+def test_lazy_fit_decides_among_hundreds_of_survivors_by_triangular_solves():
+    """A lazy fit evaluates up to 256 survivors of the prefix bound in FP64 by cooperative panel solves with L (up to 64 right-hand
+    sides per launch) instead of forming the rest of L^-1.  LCB with a growing kappa loosens the prefix bound: whatever the
+    number of survivors — a handful, hundreds, or more than the cap (then the eager path runs) — the suggestion is the FP64
+    engine's, and a candidate's value does not depend on how many survivors it was evaluated with (sharded asks are bit-equal)."""
+    N, M, D = 2048, 30000, 32
+    X, y, Xc = O.synthetic(N, M, D)
+    th = O.theta_of_record(D)
+    seen = []
+    for kappa in (1.96, 6.0, 12.0, 20.0, 40.0):
+        kw = dict(kind="matern52", acq="lcb", **{**th, "kappa": kappa})
+        lazy = _engine(kw, "tc"); lazy.tell(X, y)
+        e64 = _engine(kw, "f64"); e64.tell(X, y)
+        bl, b6 = lazy.ask(Xc), e64.ask(Xc)
+        seen.append(lazy.last_prefix_survivors())
+        assert bl.index == b6.index and abs(bl.value - b6.value) <= 1e-10 * max(1.0, abs(b6.value)), (kappa, seen)
+        assert lazy.last_unrefined() == 0
+        if 1 <= seen[-1] <= 256:
+            lazy.tell(X, y)     # a fresh lazy fit: the sharded asks below must not inherit a W formed by a fallback
+            parts = [lazy.ask(Xc[s0:s0 + 10000], global_offset=s0) for s0 in range(0, M, 10000)]
+            win = max(parts, key=lambda b: (b.value, -b.index))
+            assert (win.index, win.value) == (bl.index, bl.value), (kappa, seen)
+        lazy.close(); e64.close()
+    print(f"\nprefix survivors by kappa: {seen}")
+    assert any(64 < n <= 256 for n in seen), seen
