@@ -152,6 +152,7 @@ __device__ __forceinline__ void tri_inverse_64(double (*S)[KBO_NB + 1], double (
   }
 }
 
+#include <chrono>
 #include "potf2.cuh"
 
 // batched inverse of the 64×64 diagonal blocks of a lower-triangular L (for kbo_trtri); one CTA per block
@@ -308,17 +309,7 @@ int kbo_i_trtri(kbo_handle* h, const double* L, int N, int ldl, double* W, int l
 }
 
 // ------------------------------------------------------------------------------------------------
-// L = chol(K) and W = L⁻¹ TOGETHER.  The Cholesky of N = 8192 is a chain of 128 single-CTA diagonal blocks (67 µs each) with
-// small panel kernels in between: most of the GPU idles for a third of its 23 ms, and the recursive-doubling inverse (10 ms,
-// at the FP64 ceiling) could only start afterwards — three quarters of its flops sit in the top level, which needs the last
-// panel.  The inverse is therefore computed by ROW PANELS instead:   W_ii = L_ii⁻¹,   W_i,<i = −W_ii · (L_i,<i · W_<i,<i),
-// and row panel i needs nothing but the rows of L in panel i — final as soon as the Cholesky has factored that panel — and
-// the rows of W above it.  Same N³/3 flops, but panel i's share (growing with i) runs on a second stream while the Cholesky
-// works on the panels after it (whose trailing updates shrink with i): only the last row panel is exposed.
-// The Cholesky chain runs on a high-priority stream so its small kernels are scheduled ahead of the inverse's GEMM blocks.
-// Measured (KBO_FIT_TRACE timeline, profiles/README.md): 34.7 -> 33.7 ms at N = 8192 — the two share one FP64 pipe, the
-// Cholesky's own GEMMs run at ~13 of the ~18 TFLOP/s ceiling, and the chain slows to 28 ms under the contention, so the
-// overlap buys 3 %, not the 10 ms the idle SMs suggested.  KBO_FIT_SERIAL=1 selects the one-stream sequence for A/B runs.
+// Streams and events of the multi-stream factorisations below.
 static int fit_streams(kbo_handle* h, int n_panels) {
   if (!h->s_hi) {
     int lo = 0, hi = 0;
@@ -334,109 +325,13 @@ static int fit_streams(kbo_handle* h, int n_panels) {
   return KBO_OK;
 }
 
-static int factor_and_invert(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s) {
-  const int OW = 256, n_panels = (N + OW - 1) / OW;
-  KBO_TRY(fit_streams(h, n_panels));
-  KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
-  const int smem = 2 * KBO_NB * (KBO_NB + 1) * (int)sizeof(double);
-  KBO_CUDA(h, cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  double* T = (double*)h->T.p;
-  cudaEvent_t e_start = h->ev_panel[n_panels], e_hi = h->ev_panel[n_panels + 1], e_lo = h->ev_panel[n_panels + 2];
-  cudaStream_t shi = h->s_hi, slo = h->s_lo;
-  static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
-  cudaEvent_t trace_ev[3] = {nullptr, nullptr, nullptr};
-  std::vector<cudaEvent_t> trace_rp;
-  if (trace) {
-    for (auto& e : trace_ev) cudaEventCreate(&e);
-    cudaEventRecord(trace_ev[0], s);
-  }
-  KBO_CUDA(h, cudaEventRecord(e_start, s));            // the Gram matrix is complete; earlier readers of W / T on s are done
-  KBO_CUDA(h, cudaStreamWaitEvent(shi, e_start, 0));
-  KBO_CUDA(h, cudaStreamWaitEvent(slo, e_start, 0));
-  KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, slo));
-  // Row panels of the inverse are 512 wide (two Cholesky panels): M = 512 gives the triangular GEMM below 4 × K0/64 tiles —
-  // several waves, longest K ranges first — where a 256-row panel had too few tiles to balance their unequal K ranges.
-  const int RW = 512;
-  int rp0 = 0;   // first column of the row panel being collected
-  int rc = potrf_impl(h, A, N, lda, info_dev, shi, [&](int K0, int Wd) -> int {
-    const int done = K0 + Wd;
-    if (done - rp0 < RW && done < N) return KBO_OK;
-    const int P0 = rp0, Pw = done - rp0;
-    rp0 = done;
-    cudaEvent_t ev = h->ev_panel[K0 / OW];
-    KBO_CUDA(h, cudaEventRecord(ev, shi));
-    KBO_CUDA(h, cudaStreamWaitEvent(slo, ev, 0));
-    if (trace) {
-      cudaEvent_t e;
-      cudaEventCreate(&e);
-      cudaEventRecord(e, slo);
-      trace_rp.push_back(e);
-    }
-    const double* L = A;
-    // W_PP = L_PP⁻¹: the 64-blocks' inverses, then recursive doubling inside the panel
-    double* Wpp = W + (size_t)P0 * ldw + P0;
-    const double* Lpp = L + (size_t)P0 * lda + P0;
-    diag_inv_kernel<<<(Pw + KBO_NB - 1) / KBO_NB, 1024, smem, slo>>>(Lpp, Pw, lda, Wpp, ldw);
-    KBO_LAUNCH_CHECK(h);
-    for (int b = KBO_NB; b < Pw; b *= 2)
-      for (int r0 = 0; r0 + b < Pw; r0 += 2 * b) {
-        const int rows2 = min(b, Pw - (r0 + b));
-        double* T21 = T + (size_t)(P0 + r0 + b) * ldw + P0 + r0;
-        dgemm64_launch<false, EPI_STORE>(slo, rows2, b, b, Lpp + (size_t)(r0 + b) * lda + r0, lda, Wpp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
-                                         KM_FROM_N, 0, TS_NONE);
-        KBO_LAUNCH_CHECK(h);
-        dgemm64_launch<false, EPI_STORE>(slo, rows2, b, rows2, Wpp + (size_t)(r0 + b) * ldw + r0 + b, ldw, T21, ldw, Wpp + (size_t)(r0 + b) * ldw + r0,
-                                         ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
-        KBO_LAUNCH_CHECK(h);
-      }
-    if (P0 > 0) {
-      double* Trow = T + (size_t)P0 * ldw;
-      // T_P,<P = L_P,<P · W_<P,<P   (W lower triangular: k >= n)
-      dgemm64_launch<false, EPI_STORE>(slo, Pw, P0, P0, L + (size_t)P0 * lda, lda, W, ldw, Trow, ldw, 1.0, 0.0, KM_FROM_N, 0, TS_NONE);
-      KBO_LAUNCH_CHECK(h);
-      // W_P,<P = −W_PP · T_P,<P     (W_PP lower triangular: k <= m)
-      dgemm64_launch<false, EPI_STORE>(slo, Pw, P0, Pw, Wpp, ldw, Trow, ldw, W + (size_t)P0 * ldw, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
-      KBO_LAUNCH_CHECK(h);
-    }
-    if (trace) {
-      cudaEvent_t e;
-      cudaEventCreate(&e);
-      cudaEventRecord(e, slo);
-      trace_rp.push_back(e);
-    }
-    return KBO_OK;
-  });
-  // join both streams back into the caller's, also on the error path (the launches already enqueued must not outlive the call's ordering)
-  cudaEventRecord(e_hi, shi);
-  cudaEventRecord(e_lo, slo);
-  cudaStreamWaitEvent(s, e_hi, 0);
-  cudaStreamWaitEvent(s, e_lo, 0);
-  if (trace_ev[0]) {   // KBO_FIT_TRACE: when each stream finished and when each row panel of the inverse began / ended
-    cudaEventRecord(trace_ev[1], shi);
-    cudaEventRecord(trace_ev[2], slo);
-    cudaStreamSynchronize(shi);
-    cudaStreamSynchronize(slo);
-    float a_ms = 0.f, b_ms = 0.f;
-    cudaEventElapsedTime(&a_ms, trace_ev[0], trace_ev[1]);
-    cudaEventElapsedTime(&b_ms, trace_ev[0], trace_ev[2]);
-    fprintf(stderr, "[kbo fit N=%d] cholesky stream done at %.3f ms, inverse stream done at %.3f ms; inverse row panels (begin-end ms):", N, a_ms, b_ms);
-    for (size_t i = 0; i + 1 < trace_rp.size(); i += 2) {
-      float x = 0.f, y = 0.f;
-      cudaEventElapsedTime(&x, trace_ev[0], trace_rp[i]);
-      cudaEventElapsedTime(&y, trace_ev[0], trace_rp[i + 1]);
-      fprintf(stderr, " %.2f-%.2f", x, y);
-    }
-    fprintf(stderr, "\n");
-    for (auto& e : trace_ev) cudaEventDestroy(e);
-    for (auto& e : trace_rp) cudaEventDestroy(e);
-  }
-  return rc;
-}
-
 // ------------------------------------------------------------------------------------------------
-// Version 2 of the joint factorisation: LOOK-AHEAD.  In potrf_impl every 64-block step touches all N−k rows below it (panel
-// solve + in-panel update: ~125 CTAs each), so when a trailing update runs beside the chain those kernels queue for SM slots
-// behind 70 µs GEMM blocks and the chain doubles in length (round 1's look-ahead attempt: no gain).  Here the dependent chain
+// L = chol(K) and (rows of) W = L⁻¹ TOGETHER, version 2: LOOK-AHEAD on three streams (kept for A/B runs: KBO_FIT_V2=1; version 3
+// below is the default).  The Cholesky of N = 8192 is a chain of 128 single-CTA diagonal blocks with small panel kernels in
+// between — most of the GPU idles — and the inverse W_i,<i = −W_ii·(L_i,<i·W_<i,<i) of row panel i needs only the rows of L the
+// Cholesky has already finished, so it runs on another stream under the chain.  In potrf_impl every 64-block step touches all
+// N−k rows below it (panel solve + in-panel update: ~125 CTAs each), so when a trailing update runs beside the chain those kernels
+// queue for SM slots behind 70 µs GEMM blocks and the chain doubles in length.  Here the dependent chain
 // of a 256-column panel works on its 256×256 DIAGONAL block only — four single-CTA factorisations, ≤ 3-CTA solves, ≤ 9-CTA
 // updates — then inverts that block (needed for L⁻¹ anyway) and solves the whole panel below it with ONE GEMM against the
 // inverse.  The trailing update is issued on a second stream as [next column block | rest]: the next panel's chain starts as
@@ -678,12 +573,17 @@ static bool profiler_attached() {
   return attached;
 }
 
-// The five streams of the v3 factorisation: {chain, near shadow, far shadow, update, inverse}.  partitioned = true asks for the
-// green-context set (created once; falls back to the plain set if the driver cannot split the device).
-static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[5]) {
+// The streams of the v3 factorisation (roles: kbo_internal.cuh).  partitioned = true asks for the green-context set (created once;
+// falls back to the plain set if the driver cannot split the device).
+#define FIT_NSTREAMS 11
+static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[FIT_NSTREAMS]) {
   int lo = 0, hi = 0;
   KBO_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  const int mid = (lo + hi) / 2;
+  int prio[FIT_NSTREAMS];   // numerically lower = more urgent
+  prio[0] = prio[1] = prio[2] = prio[3] = hi;
+  for (int k = 2; k <= 6; k++) prio[2 + k] = min(lo, hi + (k - 1));
+  prio[9] = max(hi, lo - 1);
+  prio[10] = lo;
   static const bool off = getenv("KBO_FIT_NO_PARTITION") != nullptr;
   const DrvApi& d = drv();
   if (partitioned && !h->part_tried && !off && d.ok && !profiler_attached()) {
@@ -698,11 +598,8 @@ static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[5]
               d.DevResourceGenerateDesc(&dc, &chain, 1) == CUDA_SUCCESS && d.DevResourceGenerateDesc(&dr, &rest, 1) == CUDA_SUCCESS &&
               d.GreenCtxCreate(&gc, dc, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
     ok = ok && d.GreenCtxCreate(&gr, dr, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
-    ok = ok && d.GreenCtxStreamCreate((CUstream*)&h->s3_chain, gc, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
-         d.GreenCtxStreamCreate((CUstream*)&h->s3_near, gc, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
-         d.GreenCtxStreamCreate((CUstream*)&h->s3_solve, gr, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
-         d.GreenCtxStreamCreate((CUstream*)&h->s3_upd, gr, CU_STREAM_NON_BLOCKING, mid) == CUDA_SUCCESS &&
-         d.GreenCtxStreamCreate((CUstream*)&h->s3_inv, gr, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS;
+    for (int i = 0; ok && i < FIT_NSTREAMS; i++)
+      ok = d.GreenCtxStreamCreate((CUstream*)&h->s3g[i], i < 2 ? gc : gr, CU_STREAM_NON_BLOCKING, prio[i]) == CUDA_SUCCESS;
     if (ok) {
       h->gctx_chain = gc;
       h->gctx_rest = gr;
@@ -710,10 +607,10 @@ static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[5]
       static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
       if (trace) fprintf(stderr, "[kbo fit] SM partition: chain %u SMs, rest %u SMs\n", chain.sm.smCount, rest.sm.smCount);
     } else {
-      for (cudaStream_t* st : {&h->s3_chain, &h->s3_near, &h->s3_solve, &h->s3_upd, &h->s3_inv})
-        if (*st) {
-          cudaStreamDestroy(*st);
-          *st = nullptr;
+      for (auto& st : h->s3g)
+        if (st) {
+          cudaStreamDestroy(st);
+          st = nullptr;
         }
       if (gc) d.GreenCtxDestroy(gc);
       if (gr) d.GreenCtxDestroy(gr);
@@ -721,22 +618,21 @@ static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[5]
     }
   }
   if (partitioned && h->part_ok) {
-    out[0] = h->s3_chain, out[1] = h->s3_near, out[2] = h->s3_solve, out[3] = h->s3_upd, out[4] = h->s3_inv;
+    for (int i = 0; i < FIT_NSTREAMS; i++) out[i] = h->s3g[i];
     return KBO_OK;
   }
-  if (!h->s3p[0]) {
-    const int prio[5] = {hi, hi, hi, mid, lo};
-    for (int i = 0; i < 5; i++) KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3p[i], cudaStreamNonBlocking, prio[i]));
-  }
-  for (int i = 0; i < 5; i++) out[i] = h->s3p[i];
+  if (!h->s3p[0])
+    for (int i = 0; i < FIT_NSTREAMS; i++) KBO_CUDA(h, cudaStreamCreateWithPriority(&h->s3p[i], cudaStreamNonBlocking, prio[i]));
+  for (int i = 0; i < FIT_NSTREAMS; i++) out[i] = h->s3p[i];
   return KBO_OK;
 }
 void kbo_i_fit_partition_free(kbo_handle* h) {
-  for (cudaStream_t* st : {&h->s3_chain, &h->s3_near, &h->s3_solve, &h->s3_upd, &h->s3_inv, &h->s3p[0], &h->s3p[1], &h->s3p[2], &h->s3p[3], &h->s3p[4]})
-    if (*st) {
-      cudaStreamDestroy(*st);
-      *st = nullptr;
-    }
+  for (auto* set : {&h->s3g, &h->s3p})
+    for (auto& st : *set)
+      if (st) {
+        cudaStreamDestroy(st);
+        st = nullptr;
+      }
   if (h->gctx_chain) drv().GreenCtxDestroy((CUgreenCtx)h->gctx_chain);
   if (h->gctx_rest) drv().GreenCtxDestroy((CUgreenCtx)h->gctx_rest);
   h->gctx_chain = h->gctx_rest = nullptr;
@@ -746,14 +642,18 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   // panel width: 256 (four 64-blocks per panel), or KBO_FIT_OW=512 (eight): wider panels make the trailing updates K = 512 GEMMs
   static const int ow_env = getenv("KBO_FIT_OW") ? atoi(getenv("KBO_FIT_OW")) : 0;
   const int OW = ow_env == 512 ? 512 : 256, NB = KBO_NB, n_panels = (N + OW - 1) / OW;
-  KBO_TRY(fit_streams(h, 6 * n_panels + 32));
+  // look-ahead depth: column blocks at distance 1..depth from the panel get their own GEMM (and stream) per panel, the bulk of the
+  // trailing update covers the rest — the chain can run `depth` − 1 panels ahead of the bulk (KBO_FIT_DEPTH=1: [next block | rest])
+  static const int depth_env = getenv("KBO_FIT_DEPTH") ? atoi(getenv("KBO_FIT_DEPTH")) : 0;
+  const int Dn = OW == 256 ? (depth_env >= 1 && depth_env <= 6 ? depth_env : 3) : 1;
+  KBO_TRY(fit_streams(h, (7 + Dn) * n_panels + 8 * Dn + 64));
   // the SM partition pays when trailing updates big enough to fill the GPU run beside the chain; small factorisations (and any
   // process a profiler is attached to) use plain priority streams
-  cudaStream_t st5[5];
+  cudaStream_t st5[FIT_NSTREAMS];
   KBO_TRY(fit_partition(h, N >= 2048, st5));
-  const bool partitioned = st5[0] == h->s3_chain && h->part_ok;
+  const bool partitioned = st5[0] == h->s3g[0] && h->part_ok;
   KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
-  KBO_TRY(kbo_reserve(h, h->Linv4, sizeof(double) * 8 * NB * NB));
+  KBO_TRY(kbo_reserve(h, h->Linv4, sizeof(double) * 2 * 8 * NB * NB));
   const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
   if (!h->attr_fit) {
     KBO_CUDA(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -762,16 +662,23 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
     h->attr_fit = true;
   }
   double* T = (double*)h->T.p;
-  double* Linv4 = (double*)h->Linv4.p;
-  cudaStream_t sc = st5[0], sn = st5[1], ss = st5[2], su = st5[3], si = st5[4];
+  // the 64×64 inverses of a panel's diagonal blocks, two sets: the chain of panel P+1 starts when the NEAR shadow of panel P is done,
+  // the far shadow of panel P may still be reading its set (it is done before the chain of panel P+2 can start: that one waits for
+  // the near shadow of P+1, which waits for the distance-1 update of P, which waits for the far shadow of P)
+  double* Linv_sets = (double*)h->Linv4.p;
+  cudaStream_t sc = st5[0], sn = st5[1], ss = st5[2], su = st5[3], sb = st5[9], si = st5[10];
+  cudaStream_t* colS = st5 + 2;   // colS[k]: column-block updates at distance k (colS[1] == su)
   cudaEvent_t* ev_solve = h->ev_panel.data();                     // [n_panels]     the FAR rows below the diagonal block (past the next block) are L
   cudaEvent_t* ev_col = h->ev_panel.data() + n_panels;            // [n_panels + 1] column block P, rows below its diagonal block, carries every earlier update
   cudaEvent_t* ev_chain = h->ev_panel.data() + 2 * n_panels + 1;  // [n_panels]     diagonal block factored, its 64-block inverses in W
   cudaEvent_t* ev_near = h->ev_panel.data() + 3 * n_panels + 1;   // [n_panels + 1] diagonal block P carries every earlier update: the chain may start
   cudaEvent_t* ev_nsolve = h->ev_panel.data() + 4 * n_panels + 2; // [n_panels]     the NEAR rows (the next diagonal block's rows) of panel P are L
   cudaEvent_t* ev_rest = h->ev_panel.data() + 5 * n_panels + 2;   // [n_panels]     trailing update of panel P done
-  cudaEvent_t* ev_x = h->ev_panel.data() + 6 * n_panels + 2;      // pf[8], tr[8], start, 5 joins
+  cudaEvent_t* ev_cb = h->ev_panel.data() + 6 * n_panels + 2;     // [(n_panels + 8) × (Dn + 1)] column block j updated through distance k
+  cudaEvent_t* ev_x = ev_cb + (size_t)(n_panels + 8) * (Dn + 1);  // pf[8], tr[8], start, joins
   cudaEvent_t *ev_pf = ev_x, *ev_tr = ev_x + 8, e_start = ev_x[16], *e_join = ev_x + 17;
+  std::vector<cudaStream_t> all_streams = {sc, sn, ss, sb, si};
+  for (int k = 1; k <= Dn; k++) all_streams.push_back(colS[k]);
   static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
   cudaEvent_t tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> tp;   // per panel on the chain stream: enqueued | column block ready | diagonal block done
@@ -789,13 +696,14 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));   // on the caller's stream: all SMs, not the chain's 8
   KBO_CUDA(h, cudaEventRecord(e_start, s));
-  for (cudaStream_t st : {sc, sn, ss, su, si}) KBO_CUDA(h, cudaStreamWaitEvent(st, e_start, 0));
+  for (cudaStream_t st : all_streams) KBO_CUDA(h, cudaStreamWaitEvent(st, e_start, 0));
   const int RW = 512;
   int rp0 = 0;
   auto body = [&]() -> int {
     for (int K0 = 0, P = 0; K0 < N; K0 += OW, P++) {
       const int Wd = min(OW, N - K0), rows_t = N - (K0 + Wd);
       const int nblk = (Wd + NB - 1) / NB;
+      double* Linv4 = Linv_sets + (size_t)(P & 1) * 8 * NB * NB;
       mark();
       if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(sc, ev_near[P], 0));
       mark();
@@ -844,8 +752,10 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
         const int rn = K0 + Wd, rf = rn + n_near;
         KBO_TRY(shadow(sn, rn, n_near));
         KBO_CUDA(h, cudaEventRecord(ev_nsolve[P], sn));
-        // the next diagonal block's own update (after the previous panel's trailing update, which wrote the same block)
-        if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(sn, ev_rest[P - 1], 0));
+        // What was added to column block P+1 last before this panel: the distance-2 update of panel P−1, or (depth 1) its bulk
+        cudaEvent_t pred1 = P > 0 ? (Dn >= 2 ? ev_cb[(size_t)(P + 1) * (Dn + 1) + 2] : ev_rest[P - 1]) : nullptr;
+        // the next diagonal block's own update
+        if (pred1) KBO_CUDA(h, cudaStreamWaitEvent(sn, pred1, 0));
         const double* Ln = A + (size_t)rn * lda + K0;
         dgemm64_launch<true, EPI_STORE>(sn, n_near, n_near, Wd, Ln, lda, Ln, lda, A + (size_t)rn * lda + rn, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
         KBO_LAUNCH_CHECK(h);
@@ -853,16 +763,36 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
         if (n_far > 0) {
           KBO_TRY(shadow(ss, rf, n_far));
           KBO_CUDA(h, cudaEventRecord(ev_solve[P], ss));
-          // ---- trailing update: the next column block below its diagonal block first (the next panel's shadows wait for it), then the rest
+          // ---- trailing update.  Distance 1: the next column block below its diagonal block (the next panel's shadows wait for it)
           KBO_CUDA(h, cudaStreamWaitEvent(su, ev_solve[P], 0));
           KBO_CUDA(h, cudaStreamWaitEvent(su, ev_nsolve[P], 0));
+          if (pred1) KBO_CUDA(h, cudaStreamWaitEvent(su, pred1, 0));
           const double* Lf = A + (size_t)rf * lda + K0;
           dgemm64_launch<true, EPI_STORE>(su, n_far, n_near, Wd, Lf, lda, Ln, lda, A + (size_t)rf * lda + rn, lda, -1.0, 1.0, KM_FULL, 0, TS_NONE);
           KBO_LAUNCH_CHECK(h);
           KBO_CUDA(h, cudaEventRecord(ev_col[P + 1], su));
-          dgemm64_launch<true, EPI_STORE>(su, n_far, n_far, Wd, Lf, lda, Lf, lda, A + (size_t)rf * lda + rf, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
-          KBO_LAUNCH_CHECK(h);
-          KBO_CUDA(h, cudaEventRecord(ev_rest[P], su));
+          // distances 2..Dn: column block j = P + k, rows from its diagonal block down; each after what was added to that block before
+          // (distance k + 1 of the previous panel, or — the farthest — the previous panel's bulk)
+          for (int k = 2; k <= Dn; k++) {
+            const int j = P + k, c0 = j * OW;
+            if (c0 >= N) break;
+            cudaStream_t st = colS[k];
+            KBO_CUDA(h, cudaStreamWaitEvent(st, ev_solve[P], 0));
+            if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(st, k < Dn ? ev_cb[(size_t)j * (Dn + 1) + k + 1] : ev_rest[P - 1], 0));
+            const double* Lc = A + (size_t)c0 * lda + K0;
+            dgemm64_launch<true, EPI_STORE>(st, N - c0, min(OW, N - c0), Wd, Lc, lda, Lc, lda, A + (size_t)c0 * lda + c0, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+            KBO_LAUNCH_CHECK(h);
+            KBO_CUDA(h, cudaEventRecord(ev_cb[(size_t)j * (Dn + 1) + k], st));
+          }
+          // the bulk: every column block farther than Dn
+          const int cB = (P + Dn + 1) * OW;
+          if (cB < N) {
+            KBO_CUDA(h, cudaStreamWaitEvent(sb, ev_solve[P], 0));
+            const double* Lb = A + (size_t)cB * lda + K0;
+            dgemm64_launch<true, EPI_STORE>(sb, N - cB, N - cB, Wd, Lb, lda, Lb, lda, A + (size_t)cB * lda + cB, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+            KBO_LAUNCH_CHECK(h);
+            KBO_CUDA(h, cudaEventRecord(ev_rest[P], sb));
+          }
         }
       }
       // ---- inverse stream: W_PP = L_PP⁻¹ by recursive doubling from the 64-block inverses, then the row panels of L⁻¹ -------------
@@ -914,10 +844,12 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
     }
     return KBO_OK;
   };
+  const auto host_t0 = std::chrono::steady_clock::now();
   const int rc = body();
+  const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   {
     int j = 0;
-    for (cudaStream_t st : {sc, sn, ss, su, si}) {
+    for (cudaStream_t st : all_streams) {
       cudaEventRecord(e_join[j], st);
       cudaStreamWaitEvent(s, e_join[j], 0);
       j++;
@@ -925,11 +857,11 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   }
   if (tr[0]) {
     int j = 1;
-    for (cudaStream_t st : {sc, ss, su, si}) cudaEventRecord(tr[j++], st);
-    for (cudaStream_t st : {sc, sn, ss, su, si}) cudaStreamSynchronize(st);
+    for (cudaStream_t st : {sc, ss, sb, si}) cudaEventRecord(tr[j++], st);
+    for (cudaStream_t st : all_streams) cudaStreamSynchronize(st);
     float t[5] = {0, 0, 0, 0, 0};
     for (int i = 1; i < 5; i++) cudaEventElapsedTime(&t[i], tr[0], tr[i]);
-    fprintf(stderr, "[kbo fit v3 N=%d%s] chain stream done at %.3f ms, shadow %.3f, update %.3f, inverse %.3f ms\n", N, partitioned ? ", partitioned" : "", t[1],
+    fprintf(stderr, "[kbo fit v3 N=%d%s] chain stream done at %.3f ms, shadow %.3f, bulk update %.3f, inverse %.3f ms\n", N, partitioned ? ", partitioned" : "", t[1],
             t[2], t[3], t[4]);
     double sum[2] = {0, 0};
     for (size_t i = 0; i + 2 < tp.size(); i += 3) {
@@ -940,10 +872,12 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
       sum[1] += d;
       if ((i / 3) % 8 == 0) fprintf(stderr, "   panel %2d: wait for column block %.3f | diagonal block %.3f ms\n", (int)(i / 3), w, d);
     }
-    fprintf(stderr, "   chain totals: waiting %.3f | diagonal blocks %.3f ms\n", sum[0], sum[1]);
+    fprintf(stderr, "   chain totals: waiting %.3f | diagonal blocks %.3f ms; host enqueue of the whole factorisation %.3f ms (depth %d)\n", sum[0], sum[1],
+            host_ms, Dn);
     for (auto& e : tr) cudaEventDestroy(e);
     for (auto& e : tp) cudaEventDestroy(e);
   }
+  (void)host_ms;
   return rc;
 }
 
@@ -1174,10 +1108,7 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
     if (trace) cudaEventRecord(te[2], s);
     KBO_TRY(kbo_i_trtri(h, (const double*)h->K.p, N, ld, (double*)h->W.p, ld, s));
   } else {
-    static const bool v1 = getenv("KBO_FIT_V1") != nullptr;   // A/B: the interleaved inverse without the look-ahead restructuring
-    if (v1)
-      KBO_TRY(factor_and_invert(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s));
-    else {
+    {
       // Lazy inverse: a tensor-core fit whose sweeps will prune (kbo_set_rank_prefix) forms only the rows of W the pruning pass
       // contracts with — the first 512·P1 — and leaves the rest to kbo_i_ensure_w, which runs if something asks for all of W.
       int lead = N;

@@ -90,8 +90,10 @@ struct kbo_handle {
   // v3: the chain runs on its own SM partition (green contexts); shadow panel solve / trailing update / inverse share the rest
   bool part_tried = false, part_ok = false;
   void *gctx_chain = nullptr, *gctx_rest = nullptr;   // CUgreenCtx
-  cudaStream_t s3_chain = nullptr, s3_near = nullptr, s3_solve = nullptr, s3_upd = nullptr, s3_inv = nullptr;   // partitioned set
-  cudaStream_t s3p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // the same five roles as plain priority streams (small N, profilers, no green contexts)
+  // stream roles: 0 chain, 1 near shadow (both on the chain's partition), 2 far shadow, 3..8 column-block updates at distance 1..6,
+  // 9 bulk trailing update, 10 inverse
+  cudaStream_t s3g[11] = {};       // green-context set
+  cudaStream_t s3p[11] = {};       // the same roles as plain priority streams (small N, profilers, no green contexts)
   DevBuf Linv4;                     // the four 64×64 block inverses of the current panel
   std::vector<cudaEvent_t> ev_panel;
   // ---- lazy inverse (fit.cu, solve.cu): the product path never needs all of W = L⁻¹ -----------------------------------------
