@@ -20,6 +20,8 @@
 //   warps 2-17  epilogue: tcgen05.ld 16 columns → d² → kernel → fp16 → one 32-byte store per thread per batch; μ̃ partials
 // Per 128×256 tile the epilogue (~15 instructions and 2 MUFU per element) is the limiter, the MMAs take a quarter of that.
 #include "kbo_internal.cuh"
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 #define KS_BM 128
@@ -57,7 +59,7 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 }
 __device__ __forceinline__ float sqrt_abs_ftz(float x) {   // MUFU.SQRT |x|: one instruction where max + rsqrt + multiply were three
   float r;
-  asm("{ .reg .f32 t; abs.ftz.f32 t, %1; sqrt.approx.ftz.f32 %0, t; }" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(x)));
   return r;
 }
 // kernel value from the dot product: KIND 0 = RBF (coordinates pre-scaled by 1/√2: k = exp(−d2)), 1 = Matérn-5/2 (pre-scaled by
@@ -192,45 +194,54 @@ tc_kstar_kernel(const __grid_constant__ CUtensorMap tmCh, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * KS_BN + cg * 64;
       const int n_base = t * KS_BN + cg * 64;
       const bool edge = n_base + 64 > N;   // warp-uniform: only the last tile(s) mask trials >= N
-      uint32_t rr[2][16];
-      tmem_ld16(taddr, rr[0]);
+      // EDGE: only the last tile(s) mask trials >= N.  Two instantiations behind one warp-uniform branch: as a runtime flag inside the
+      // body the mask compiled to ISETP + FSEL + IADD per element — 3 of 15 instructions on every tile.
+      auto tile_body = [&](auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        uint32_t rr[2][16];
+        tmem_ld16(taddr, rr[0]);
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        uint32_t(&r)[16] = rr[q & 1];
-        tmem_ld_wait();
-        if (q < 3) tmem_ld16(taddr + (q + 1) * 16, rr[(q + 1) & 1]);   // the next 16 columns travel while these are evaluated
-        if (q == 3) {   // everything this warp needs from the accumulator is in registers: hand it back to the MMA thread
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&S->tmem_empty[buf]));
-        }
-        uint32_t o[8];
-        float macc[4];   // four independent fp32 chains of four trials each, summed in FP64 once per 16 trials
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          macc[g] = 0.f;
-#pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const int i = g * 4 + e;
-            const float4 na = sl4[(q * 16 + i) >> 1];   // broadcast: every lane reads the same word
-            float k0 = ks_kernel_value<KIND>(__uint_as_float(r[i]), ncr + na.x, log2amp);
-            float k1 = ks_kernel_value<KIND>(__uint_as_float(r[i + 1]), ncr + na.z, log2amp);
-            if (edge) {
-              k0 = (n_base + q * 16 + i < N) ? k0 : 0.f;
-              k1 = (n_base + q * 16 + i + 1 < N) ? k1 : 0.f;
-            }
-            macc[g] = fmaf(k0, na.y, macc[g]);
-            macc[g] = fmaf(k1, na.w, macc[g]);
-            const __half2 h2 = __floats2half2_rn(k0, k1);
-            o[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+        for (int q = 0; q < 4; q++) {
+          uint32_t(&r)[16] = rr[q & 1];
+          tmem_ld_wait();
+          if (q < 3) tmem_ld16(taddr + (q + 1) * 16, rr[(q + 1) & 1]);   // the next 16 columns travel while these are evaluated
+          if (q == 3) {   // everything this warp needs from the accumulator is in registers: hand it back to the MMA thread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S->tmem_empty[buf]));
           }
+          uint32_t o[8];
+          float macc[4];   // four independent fp32 chains of four trials each, summed in FP64 once per 16 trials
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            macc[g] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const int i = g * 4 + e;
+              const float4 na = sl4[(q * 16 + i) >> 1];   // broadcast: every lane reads the same word
+              float k0 = ks_kernel_value<KIND>(__uint_as_float(r[i]), ncr + na.x, log2amp);
+              float k1 = ks_kernel_value<KIND>(__uint_as_float(r[i + 1]), ncr + na.z, log2amp);
+              if (EDGE) {
+                k0 = (n_base + q * 16 + i < N) ? k0 : 0.f;
+                k1 = (n_base + q * 16 + i + 1 < N) ? k1 : 0.f;
+              }
+              macc[g] = fmaf(k0, na.y, macc[g]);
+              macc[g] = fmaf(k1, na.w, macc[g]);
+              const __half2 h2 = __floats2half2_rn(k0, k1);
+              o[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+          }
+          mu_d += (double)((macc[0] + macc[1]) + (macc[2] + macc[3]));
+          if (t < store_tiles)   // a pruning pass contracts a prefix of the trials only: the mean needs every column, the plane does not
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_row + (size_t)t * KS_BN + q * 16), "r"(o[0]), "r"(o[1]),
+                         "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                         : "memory");
         }
-        mu_d += (double)((macc[0] + macc[1]) + (macc[2] + macc[3]));
-        if (t < store_tiles)   // a pruning pass contracts a prefix of the trials only: the mean needs every column, the plane does not
-          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_row + (size_t)t * KS_BN + q * 16), "r"(o[0]), "r"(o[1]),
-                       "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
-                       : "memory");
-      }
+      };
+      if (edge)
+        tile_body(std::true_type{});
+      else
+        tile_body(std::false_type{});
     }
     musum[cg * KS_BM + row] = mu_d;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * KS_EPI_WARPS) : "memory");
