@@ -46,7 +46,7 @@ void kbo_destroy(kbo_handle* h) {
                     &h->scal, &h->info, &h->stage_X, &h->stage_y, &h->stage_Xc, &h->Ks64, &h->Ksh, &h->Ksl, &h->mun, &h->part, &h->varn,
                     &h->blockbest, &h->best, &h->XsT, &h->refine, &h->refine_x, &h->yraw, &h->lrow, &h->var_cal,
                     &h->ks_center, &h->ks_Xh, &h->ks_Xl, &h->ks_nxal, &h->ks_Ch, &h->ks_Cl, &h->ks_nc, &h->rk_part, &h->cal_idx, &h->cal_x, &h->cal_mu,
-                    &h->comm_buf, &h->T2, &h->Linv4, &h->mu_part, &h->sv_B, &h->sv_V, &h->sv_bar, &h->lml_yn, &h->lml_scal, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
+                    &h->comm_buf, &h->T2, &h->Linv4, &h->mu_part, &h->sv_B, &h->sv_V, &h->sv_bar, &h->zf, &h->lml_yn, &h->lml_scal, &h->rk_sched[0].dev, &h->rk_sched[1].dev, &h->rk_sched[2].dev, &h->rk_sched[3].dev, &h->rk_sched[4].dev, &h->rk_sched[5].dev,
                     &h->rk_sched[6].dev, &h->rk_sched[7].dev, &h->pr_list, &h->pr_x, &h->pr_mu, &h->pr_var, &h->cal_mu_rk, &h->cal_var_rk};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);

@@ -695,6 +695,9 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   }
   KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));   // on the caller's stream: all SMs, not the chain's 8
+  // a lazy fit takes alpha from triangular solves: the forward one (z = L⁻¹·yn) is carried along, one panel behind (solve.cu)
+  const bool zsolve = lead < N && OW == 256 && A == (double*)h->K.p && W == (double*)h->W.p && N == h->N && lda == h->ld;
+  if (zsolve) KBO_TRY(kbo_i_zsolve_begin(h, s));
   KBO_CUDA(h, cudaEventRecord(e_start, s));
   for (cudaStream_t st : all_streams) KBO_CUDA(h, cudaStreamWaitEvent(st, e_start, 0));
   const int RW = 512;
@@ -812,6 +815,14 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
             KBO_LAUNCH_CHECK(h);
           }
       }
+      if (zsolve) {
+        KBO_TRY(kbo_i_zsolve_diag(h, K0, Wd, si));
+        if (rows_t > 0) {
+          KBO_CUDA(h, cudaStreamWaitEvent(si, ev_nsolve[P], 0));
+          if (rows_t > OW) KBO_CUDA(h, cudaStreamWaitEvent(si, ev_solve[P], 0));
+          KBO_TRY(kbo_i_zsolve_update(h, K0, Wd, si));
+        }
+      }
       const int done = K0 + Wd;
       if (rp0 < lead && (done - rp0 >= RW || done >= N)) {
         const int P0 = rp0, Pw = done - rp0;
@@ -878,6 +889,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
     for (auto& e : tp) cudaEventDestroy(e);
   }
   (void)host_ms;
+  if (zsolve && rc == KBO_OK) h->z_ready = true;
   return rc;
 }
 

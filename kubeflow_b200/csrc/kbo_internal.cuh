@@ -102,6 +102,8 @@ struct kbo_handle {
   int w_lead = 0;                  // rows of W formed so far (the diagonal 256-blocks exist for every panel)
   DevBuf sv_B, sv_V;               // N × 8 right-hand sides / solutions of the panel solves
   DevBuf sv_bar;                   // grid-barrier counter of the cooperative solve kernels
+  DevBuf zf;                       // b (consumed) and z = L⁻¹·yn of the forward substitution carried along by the factorisation
+  bool z_ready = false;            // zf holds z of the current factorisation
   // ---- kbo_lml_batch: concurrent factorisations for several θ (fit.cu) --------------------------------------------------
   void* lml_lanes = nullptr;       // std::vector<LmlLane>*
   DevBuf lml_yn, lml_scal;
@@ -173,6 +175,9 @@ int kbo_i_ensure_w(kbo_handle* h, cudaStream_t s);   // form the rest of W and t
 // ---- solve.cu ----------------------------------------------------------------------------------
 int kbo_i_alpha_by_solves(kbo_handle* h, cudaStream_t s);
 int kbo_i_variance_by_solves(kbo_handle* h, const double* Ks, int n, double* varn64, cudaStream_t s);
+int kbo_i_zsolve_begin(kbo_handle* h, cudaStream_t s);
+int kbo_i_zsolve_diag(kbo_handle* h, int K0, int Wd, cudaStream_t s);
+int kbo_i_zsolve_update(kbo_handle* h, int K0, int Wd, cudaStream_t s);
 // ---- sweep.cu ----------------------------------------------------------------------------------
 int kbo_i_sweep(kbo_handle* h, const void* Xc_dev, int xc_dtype, int64_t M, int64_t goff, double* mu_out, double* std_out,
                 double* acq_out, kbo_best* best_dev, cudaStream_t s);

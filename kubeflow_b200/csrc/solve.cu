@@ -253,6 +253,68 @@ int kbo_i_solve_bwd(kbo_handle* h, double* Z, double* A, cudaStream_t s) {
   return KBO_OK;
 }
 
+// ---- z = L⁻¹·yn one panel behind the factorisation (fit.cu, lazy fits): the forward half of alpha rides in the factorisation's
+// shadow — a panel's step needs W_PP and the rows of L below the panel, both final as soon as that panel is — so fit_finish pays
+// for the backward half only.  One right-hand side, plain vectors b (consumed) and z.
+namespace {
+__global__ void __launch_bounds__(256) sv_zdiag_kernel(const double* __restrict__ Wpp, int ldw, int Wd, const double* __restrict__ b, double* __restrict__ z) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= Wd) return;
+  const double* w = Wpp + (size_t)r * ldw;
+  double a = 0.0;
+#pragma unroll
+  for (int i = 0; i < SV_P / 32; i++) {
+    const int k = lane + 32 * i;
+    if (k <= r) a = fma(w[k], b[k], a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) z[r] = a;
+}
+__global__ void __launch_bounds__(256) sv_zupdate_kernel(const double* __restrict__ Lp, int ldl, int rows, int Wd, const double* __restrict__ zP,
+                                                         double* __restrict__ b) {
+  __shared__ double zs[SV_P];
+  for (int k = threadIdx.x; k < SV_P; k += 256) zs[k] = k < Wd ? zP[k] : 0.0;
+  __syncthreads();
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const double* l = Lp + (size_t)r * ldl;
+  double lv[SV_P / 32];
+#pragma unroll
+  for (int i = 0; i < SV_P / 32; i++) lv[i] = lane + 32 * i < Wd ? l[lane + 32 * i] : 0.0;
+  double a = 0.0;
+#pragma unroll
+  for (int i = 0; i < SV_P / 32; i++) a = fma(lv[i], zs[lane + 32 * i], a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) b[r] -= a;
+}
+}  // namespace
+int kbo_i_zsolve_begin(kbo_handle* h, cudaStream_t s) {
+  KBO_TRY(kbo_reserve(h, h->zf, sizeof(double) * 2 * (size_t)(h->N + SV_P)));
+  KBO_CUDA(h, cudaMemcpyAsync(h->zf.p, h->yn.p, sizeof(double) * h->N, cudaMemcpyDeviceToDevice, s));
+  h->z_ready = false;
+  return KBO_OK;
+}
+// panel [K0, K0 + Wd): z_P = W_PP·b_P (needs W's diagonal 256-block) ...
+int kbo_i_zsolve_diag(kbo_handle* h, int K0, int Wd, cudaStream_t s) {
+  double* b = (double*)h->zf.p;
+  double* z = b + h->N + SV_P;
+  sv_zdiag_kernel<<<(Wd + 7) / 8, 256, 0, s>>>((const double*)h->W.p + (size_t)K0 * h->ld + K0, h->ld, Wd, b + K0, z + K0);
+  KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
+// ... then b_>P −= L_>P,P·z_P (needs the rows of L below the panel)
+int kbo_i_zsolve_update(kbo_handle* h, int K0, int Wd, cudaStream_t s) {
+  const int N = h->N, rows = N - (K0 + Wd);
+  if (rows <= 0) return KBO_OK;
+  double* b = (double*)h->zf.p;
+  double* z = b + N + SV_P;
+  sv_zupdate_kernel<<<(rows + 7) / 8, 256, 0, s>>>((const double*)h->K.p + (size_t)(K0 + Wd) * h->ld + K0, h->ld, rows, Wd, z + K0, b + K0 + Wd);
+  KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
+
 // alpha = L⁻ᵀ(L⁻¹·yn) into h->alpha (what fit_finish computes as Wᵀ(W·yn) when W is formed)
 int kbo_i_alpha_by_solves(kbo_handle* h, cudaStream_t s) {
   const int N = h->N;
@@ -260,10 +322,17 @@ int kbo_i_alpha_by_solves(kbo_handle* h, cudaStream_t s) {
   KBO_TRY(kbo_reserve(h, h->sv_V, sizeof(double) * (size_t)(N + SV_P) * SV_R));
   double* B = (double*)h->sv_B.p;
   double* V = (double*)h->sv_V.p;
-  KBO_CUDA(h, cudaMemsetAsync(B, 0, sizeof(double) * (size_t)N * SV_R, s));
-  sv_col_kernel<<<(N + 255) / 256, 256, 0, s>>>((const double*)h->yn.p, N, 1, B, SV_R);
-  KBO_LAUNCH_CHECK(h);
-  KBO_TRY(kbo_i_solve_fwd(h, B, V, s, 1, 0));      // V[:,0] = z
+  if (h->z_ready) {   // the factorisation already carried z = L⁻¹·yn along (kbo_i_zsolve_*)
+    KBO_CUDA(h, cudaMemsetAsync(V, 0, sizeof(double) * (size_t)N * SV_R, s));
+    sv_col_kernel<<<(N + 255) / 256, 256, 0, s>>>((const double*)h->zf.p + N + SV_P, N, 1, V, SV_R);
+    KBO_LAUNCH_CHECK(h);
+    h->z_ready = false;
+  } else {
+    KBO_CUDA(h, cudaMemsetAsync(B, 0, sizeof(double) * (size_t)N * SV_R, s));
+    sv_col_kernel<<<(N + 255) / 256, 256, 0, s>>>((const double*)h->yn.p, N, 1, B, SV_R);
+    KBO_LAUNCH_CHECK(h);
+    KBO_TRY(kbo_i_solve_fwd(h, B, V, s, 1, 0));      // V[:,0] = z
+  }
   KBO_TRY(kbo_i_solve_bwd(h, V, B, s));      // B[:,0] = alpha (V is consumed)
   sv_col_kernel<<<(N + 255) / 256, 256, 0, s>>>(B, N, SV_R, (double*)h->alpha.p, 1);
   KBO_LAUNCH_CHECK(h);
