@@ -152,6 +152,7 @@ __device__ __forceinline__ void tri_inverse_64(double (*S)[KBO_NB + 1], double (
   }
 }
 
+#include <algorithm>
 #include <chrono>
 #include "potf2.cuh"
 
@@ -575,7 +576,7 @@ static bool profiler_attached() {
 
 // The streams of the v3 factorisation (roles: kbo_internal.cuh).  partitioned = true asks for the green-context set (created once;
 // falls back to the plain set if the driver cannot split the device).
-#define FIT_NSTREAMS 11
+#define FIT_NSTREAMS 13
 static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[FIT_NSTREAMS]) {
   int lo = 0, hi = 0;
   KBO_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -584,6 +585,7 @@ static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[FI
   for (int k = 2; k <= 6; k++) prio[2 + k] = min(lo, hi + (k - 1));
   prio[9] = max(hi, lo - 1);
   prio[10] = lo;
+  prio[11] = prio[12] = hi;
   static const bool off = getenv("KBO_FIT_NO_PARTITION") != nullptr;
   const DrvApi& d = drv();
   if (partitioned && !h->part_tried && !off && d.ok && !profiler_attached()) {
@@ -599,7 +601,7 @@ static int fit_partition(kbo_handle* h, bool partitioned, cudaStream_t (&out)[FI
               d.GreenCtxCreate(&gc, dc, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
     ok = ok && d.GreenCtxCreate(&gr, dr, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
     for (int i = 0; ok && i < FIT_NSTREAMS; i++)
-      ok = d.GreenCtxStreamCreate((CUstream*)&h->s3g[i], i < 2 ? gc : gr, CU_STREAM_NON_BLOCKING, prio[i]) == CUDA_SUCCESS;
+      ok = d.GreenCtxStreamCreate((CUstream*)&h->s3g[i], (i < 2 || i >= 11) ? gc : gr, CU_STREAM_NON_BLOCKING, prio[i]) == CUDA_SUCCESS;
     if (ok) {
       h->gctx_chain = gc;
       h->gctx_rest = gr;
@@ -646,13 +648,20 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   // trailing update covers the rest — the chain can run `depth` − 1 panels ahead of the bulk (KBO_FIT_DEPTH=1: [next block | rest])
   static const int depth_env = getenv("KBO_FIT_DEPTH") ? atoi(getenv("KBO_FIT_DEPTH")) : 0;
   const int Dn = OW == 256 ? (depth_env >= 1 && depth_env <= 6 ? depth_env : 3) : 1;
-  KBO_TRY(fit_streams(h, (7 + Dn) * n_panels + 8 * Dn + 64));
+  // merged bulks: the bulk updates of panels (P, P+1), P even, run as ONE K = 512 GEMM after panel P+1 (26 instead of 24 TFLOP/s, half
+  // the passes over the trailing matrix); the even panel covers the column block the merged region misses with one more distance GEMM
+  static const bool pair_env = !(getenv("KBO_FIT_PAIR") && atoi(getenv("KBO_FIT_PAIR")) == 0);
+  const bool pairs = pair_env && OW == 256 && Dn >= 2 && Dn <= 5;
+  auto kmax_of = [&](int P) { return pairs && (P % 2 == 0) ? Dn + 1 : Dn; };
+  const int CBW = Dn + 2;   // events per column block: distances 1..Dn+1
+  KBO_TRY(fit_streams(h, (12 + Dn) * n_panels + 8 * CBW + 80));
   // the SM partition pays when trailing updates big enough to fill the GPU run beside the chain; small factorisations (and any
   // process a profiler is attached to) use plain priority streams
   cudaStream_t st5[FIT_NSTREAMS];
   KBO_TRY(fit_partition(h, N >= 2048, st5));
   const bool partitioned = st5[0] == h->s3g[0] && h->part_ok;
   KBO_TRY(kbo_reserve(h, h->T, sizeof(double) * (size_t)N * ldw));
+  KBO_TRY(kbo_reserve(h, h->T2, sizeof(double) * (size_t)N * OW));
   KBO_TRY(kbo_reserve(h, h->Linv4, sizeof(double) * 2 * 8 * NB * NB));
   const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
   if (!h->attr_fit) {
@@ -662,11 +671,12 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
     h->attr_fit = true;
   }
   double* T = (double*)h->T.p;
+  double* T2 = (double*)h->T2.p;
   // the 64×64 inverses of a panel's diagonal blocks, two sets: the chain of panel P+1 starts when the NEAR shadow of panel P is done,
   // the far shadow of panel P may still be reading its set (it is done before the chain of panel P+2 can start: that one waits for
   // the near shadow of P+1, which waits for the distance-1 update of P, which waits for the far shadow of P)
   double* Linv_sets = (double*)h->Linv4.p;
-  cudaStream_t sc = st5[0], sn = st5[1], ss = st5[2], su = st5[3], sb = st5[9], si = st5[10];
+  cudaStream_t sc = st5[0], sn = st5[1], ss = st5[2], su = st5[3], sb = st5[9], si = st5[10], sw = st5[11], sm = st5[12];
   cudaStream_t* colS = st5 + 2;   // colS[k]: column-block updates at distance k (colS[1] == su)
   cudaEvent_t* ev_solve = h->ev_panel.data();                     // [n_panels]     the FAR rows below the diagonal block (past the next block) are L
   cudaEvent_t* ev_col = h->ev_panel.data() + n_panels;            // [n_panels + 1] column block P, rows below its diagonal block, carries every earlier update
@@ -675,10 +685,19 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
   cudaEvent_t* ev_nsolve = h->ev_panel.data() + 4 * n_panels + 2; // [n_panels]     the NEAR rows (the next diagonal block's rows) of panel P are L
   cudaEvent_t* ev_rest = h->ev_panel.data() + 5 * n_panels + 2;   // [n_panels]     trailing update of panel P done
   cudaEvent_t* ev_cb = h->ev_panel.data() + 6 * n_panels + 2;     // [(n_panels + 8) × (Dn + 1)] column block j updated through distance k
-  cudaEvent_t* ev_x = ev_cb + (size_t)(n_panels + 8) * (Dn + 1);  // pf[8], tr[8], start, joins
+  cudaEvent_t* ev_x = ev_cb + (size_t)(n_panels + 8) * CBW;  // pf[8], tr[8], start, joins
   cudaEvent_t *ev_pf = ev_x, *ev_tr = ev_x + 8, e_start = ev_x[16], *e_join = ev_x + 17;
-  std::vector<cudaStream_t> all_streams = {sc, sn, ss, sb, si};
-  for (int k = 1; k <= Dn; k++) all_streams.push_back(colS[k]);
+  std::vector<cudaStream_t> all_streams = {sc, sn, ss, sb, si, sw, sm};
+  cudaEvent_t* ev_wpp = ev_x + 32;   // [n_panels] W_PP complete
+  cudaEvent_t *ev_mid = ev_wpp + n_panels, *ev_t1 = ev_mid + n_panels, *ev_t2 = ev_t1 + n_panels;   // MID rows solved; their two 256×256 updates done
+  // MID rows (KBO_FIT_MID=1, off by default) = the second block below the diagonal block, solved against W_PP on the chain's partition
+  // together with their updates of blocks (P+2,P+1) and (P+2,P+2), so that the next panel's near shadow and the chain two panels on
+  // do not wait for the FAR shadow and the distance-1 update.  Measured (KBO_FIT_TRACE=2): the dependency does move, the factorisation
+  // does not get faster (12.2 vs 11.7 ms) — the big partition is saturated by the updates (2.2e11 flop in ~11 ms = 18 of the 22 TFLOP/s
+  // its K = 256 GEMM delivers on 140 SMs), so the far GEMMs are slow whichever chain waits for them.  Kept as a tested variant.
+  static const bool mid_env = getenv("KBO_FIT_MID") && atoi(getenv("KBO_FIT_MID")) != 0;
+  const bool midmode = mid_env && OW == 256 && Dn >= 2;
+  for (int k = 1; k <= (pairs ? Dn + 1 : Dn); k++) all_streams.push_back(colS[k]);
   static const bool trace = getenv("KBO_FIT_TRACE") != nullptr;
   cudaEvent_t tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> tp;   // per panel on the chain stream: enqueued | column block ready | diagonal block done
@@ -688,6 +707,17 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
     cudaEventCreate(&e);
     cudaEventRecord(e, sc);
     tp.push_back(e);
+  };
+  // KBO_FIT_TRACE=2: a timeline of one panel in eight (when each piece of the schedule finished, ms after the Gram matrix)
+  static const bool timeline = trace && atoi(getenv("KBO_FIT_TRACE")) >= 2;
+  struct TL { cudaEvent_t e; const char* what; int P; };
+  std::vector<TL> tl;
+  auto tmark = [&](cudaStream_t st, const char* what, int P) {
+    if (!timeline || (P % 8 != 2 && P % 8 != 3)) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tl.push_back({e, what, P});
   };
   if (trace) {
     for (auto& e : tr) cudaEventCreate(&e);
@@ -710,6 +740,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
       mark();
       if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(sc, ev_near[P], 0));
       mark();
+      tmark(sc, "chain starts", P);
       // ---- the chain (own SMs): the diagonal block only ------------------------------------------------------------------
       for (int b = 0; b < nblk; b++) {
         const int k = K0 + b * NB, jb = min(NB, N - k);
@@ -729,14 +760,46 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
         }
       }
       mark();
+      tmark(sc, "chain done", P);
       KBO_CUDA(h, cudaEventRecord(ev_chain[P], sc));
+      // ---- W_PP = L_PP⁻¹ by recursive doubling from the 64-block inverses, on the chain's partition, as the chain produces the blocks:
+      // the first pair and the lower-left product after the second block, the second pair and the last product after the fourth
+      {
+        double* Wpp = W + (size_t)K0 * ldw + K0;
+        const double* Lpp = A + (size_t)K0 * lda + K0;
+        auto level = [&](int bsz, int r0) -> int {   // W21 = −W22·(L21·W11) for the pair of bsz-blocks at r0
+          if (r0 + bsz >= Wd) return KBO_OK;
+          const int rows2 = min(bsz, Wd - (r0 + bsz));
+          double* T21 = T + (size_t)(K0 + r0 + bsz) * ldw + K0 + r0;
+          dgemm64_launch<false, EPI_STORE>(sw, rows2, bsz, bsz, Lpp + (size_t)(r0 + bsz) * lda + r0, lda, Wpp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
+                                           KM_FROM_N, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+          dgemm64_launch<false, EPI_STORE>(sw, rows2, bsz, rows2, Wpp + (size_t)(r0 + bsz) * ldw + r0 + bsz, ldw, T21, ldw,
+                                           Wpp + (size_t)(r0 + bsz) * ldw + r0, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+          return KBO_OK;
+        };
+        if (OW == 256 && nblk == 4) {
+          KBO_CUDA(h, cudaStreamWaitEvent(sw, ev_pf[1], 0));   // blocks 0, 1 factored (and L[1][0] solved before block 1 was)
+          KBO_TRY(level(NB, 0));
+          KBO_CUDA(h, cudaStreamWaitEvent(sw, ev_chain[P], 0));
+          KBO_TRY(level(NB, 2 * NB));
+          KBO_TRY(level(2 * NB, 0));
+        } else {
+          KBO_CUDA(h, cudaStreamWaitEvent(sw, ev_chain[P], 0));
+          for (int bsz = NB; bsz < Wd; bsz *= 2)
+            for (int r0 = 0; r0 + bsz < Wd; r0 += 2 * bsz) KBO_TRY(level(bsz, r0));
+        }
+        KBO_CUDA(h, cudaEventRecord(ev_wpp[P], sw));
+      }
+      KBO_CUDA(h, cudaStreamWaitEvent(si, ev_wpp[P], 0));
       // ---- the shadows: rows below the diagonal block, one 64-column block behind the chain.  NEAR = the rows of the next diagonal
       // block (on the chain's SMs: 4-CTA kernels that must not queue behind GEMM blocks) — all the next panel's chain waits for is
       // their solve and the 256×256 update of its diagonal block; FAR = the rest, on the big partition ------------------------------
       if (rows_t > 0) {
-        const int n_near = min(OW, rows_t), n_far = rows_t - n_near;
-        auto shadow = [&](cudaStream_t st, int r0, int nrows) -> int {
-          if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(st, ev_col[P], 0));   // these rows of the column block carry the earlier updates too
+        const int n_near = min(OW, rows_t), n_mid = midmode ? min(OW, rows_t - n_near) : 0, n_far = rows_t - n_near - n_mid;
+        auto shadow = [&](cudaStream_t st, int r0, int nrows, cudaEvent_t ready) -> int {
+          if (ready) KBO_CUDA(h, cudaStreamWaitEvent(st, ready, 0));   // these rows of the column block carry the earlier updates too
           for (int b = 0; b < nblk; b++) {
             const int k = K0 + b * NB, jb = min(NB, N - k);
             KBO_CUDA(h, cudaStreamWaitEvent(st, ev_pf[b], 0));
@@ -752,21 +815,59 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
           }
           return KBO_OK;
         };
-        const int rn = K0 + Wd, rf = rn + n_near;
-        KBO_TRY(shadow(sn, rn, n_near));
+        const int rn = K0 + Wd, rm = rn + n_near, rf = rm + n_mid;
+        // block (P+1, P) got its last update from the previous panel's MID rows (or, without them, its distance-1 update)
+        KBO_TRY(shadow(sn, rn, n_near, P > 0 ? (midmode ? ev_t1[P - 1] : ev_col[P]) : nullptr));
         KBO_CUDA(h, cudaEventRecord(ev_nsolve[P], sn));
-        // What was added to column block P+1 last before this panel: the distance-2 update of panel P−1, or (depth 1) its bulk
-        cudaEvent_t pred1 = P > 0 ? (Dn >= 2 ? ev_cb[(size_t)(P + 1) * (Dn + 1) + 2] : ev_rest[P - 1]) : nullptr;
-        // the next diagonal block's own update
-        if (pred1) KBO_CUDA(h, cudaStreamWaitEvent(sn, pred1, 0));
+        tmark(sn, "near shadow done", P);
+        // What was added to a column block last before this panel's distance-k update: panel P−1's update at distance k+1 if it made
+        // one, else the last bulk issued (by panel P−1)
+        auto pred_of = [&](int k) -> cudaEvent_t {
+          if (P == 0) return nullptr;
+          return k + 1 <= kmax_of(P - 1) ? ev_cb[(size_t)(P + k) * CBW + k + 1] : ev_rest[P - 1];
+        };
+        cudaEvent_t pred1 = pred_of(1);
+        // the next diagonal block's own update (after the previous panel's MID update of the same block, or the distance-2 update)
+        if (cudaEvent_t pe = midmode ? (P > 0 ? ev_t2[P - 1] : nullptr) : pred1) KBO_CUDA(h, cudaStreamWaitEvent(sn, pe, 0));
         const double* Ln = A + (size_t)rn * lda + K0;
         dgemm64_launch<true, EPI_STORE>(sn, n_near, n_near, Wd, Ln, lda, Ln, lda, A + (size_t)rn * lda + rn, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
         KBO_LAUNCH_CHECK(h);
         KBO_CUDA(h, cudaEventRecord(ev_near[P + 1], sn));
+        tmark(sn, "next diagonal block updated", P);
+        const double* Lm = A + (size_t)rm * lda + K0;
+        if (n_mid > 0) {
+          // MID rows on the chain's partition (their own stream: W_PP of the next panel must not queue behind a wait of theirs): L_mid = A_mid·W_PPᵀ, then blocks (P+2,P+1) and (P+2,P+2)
+          double* T2m = T2 + (size_t)(N - OW) * OW;   // the far GEMM uses at most the first N − 3·256 rows of T2
+          if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(sm, ev_col[P], 0));
+          KBO_CUDA(h, cudaStreamWaitEvent(sm, ev_wpp[P], 0));
+          dgemm64_launch<true, EPI_STORE>(sm, n_mid, Wd, Wd, Lm, lda, W + (size_t)K0 * ldw + K0, ldw, T2m, OW, 1.0, 0.0, KM_UPTO_N, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+          KBO_CUDA(h, cudaMemcpy2DAsync((double*)Lm, sizeof(double) * lda, T2m, sizeof(double) * OW, sizeof(double) * Wd, n_mid, cudaMemcpyDeviceToDevice, sm));
+          KBO_CUDA(h, cudaEventRecord(ev_mid[P], sm));
+          KBO_CUDA(h, cudaStreamWaitEvent(sm, ev_nsolve[P], 0));
+          if (pred1) KBO_CUDA(h, cudaStreamWaitEvent(sm, pred1, 0));
+          dgemm64_launch<true, EPI_STORE>(sm, n_mid, n_near, Wd, Lm, lda, Ln, lda, A + (size_t)rm * lda + rn, lda, -1.0, 1.0, KM_FULL, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+          KBO_CUDA(h, cudaEventRecord(ev_t1[P], sm));
+          if (cudaEvent_t pe = pred_of(2)) KBO_CUDA(h, cudaStreamWaitEvent(sm, pe, 0));
+          dgemm64_launch<true, EPI_STORE>(sm, n_mid, n_mid, Wd, Lm, lda, Lm, lda, A + (size_t)rm * lda + rm, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+          KBO_LAUNCH_CHECK(h);
+          KBO_CUDA(h, cudaEventRecord(ev_t2[P], sm));
+          tmark(sm, "mid rows solved, their two updates done", P);
+        }
         if (n_far > 0) {
-          KBO_TRY(shadow(ss, rf, n_far));
+          // FAR rows: one GEMM against W_PP (L_far = A_far·W_PPᵀ, out of place + copy) instead of seven 64-column steps — under the bulk
+          // updates every small kernel of the big partition waits for SM slots (KBO_FIT_TRACE=2 timeline: 0.44 ms for the seven steps,
+          // 0.2 for this)
+          if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(ss, ev_col[P], 0));
+          KBO_CUDA(h, cudaStreamWaitEvent(ss, ev_wpp[P], 0));
+          double* Pf = A + (size_t)rf * lda + K0;
+          dgemm64_launch<true, EPI_STORE>(ss, n_far, Wd, Wd, Pf, lda, W + (size_t)K0 * ldw + K0, ldw, T2, OW, 1.0, 0.0, KM_UPTO_N, 0, TS_NONE);
+          KBO_LAUNCH_CHECK(h);
+          KBO_CUDA(h, cudaMemcpy2DAsync(Pf, sizeof(double) * lda, T2, sizeof(double) * OW, sizeof(double) * Wd, n_far, cudaMemcpyDeviceToDevice, ss));
           KBO_CUDA(h, cudaEventRecord(ev_solve[P], ss));
-          // ---- trailing update.  Distance 1: the next column block below its diagonal block (the next panel's shadows wait for it)
+          tmark(ss, "far shadow done", P);
+          // ---- trailing update.  Distance 1: the next column block's FAR rows (the next panel's mid and far shadows wait for it)
           KBO_CUDA(h, cudaStreamWaitEvent(su, ev_solve[P], 0));
           KBO_CUDA(h, cudaStreamWaitEvent(su, ev_nsolve[P], 0));
           if (pred1) KBO_CUDA(h, cudaStreamWaitEvent(su, pred1, 0));
@@ -774,52 +875,52 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
           dgemm64_launch<true, EPI_STORE>(su, n_far, n_near, Wd, Lf, lda, Ln, lda, A + (size_t)rf * lda + rn, lda, -1.0, 1.0, KM_FULL, 0, TS_NONE);
           KBO_LAUNCH_CHECK(h);
           KBO_CUDA(h, cudaEventRecord(ev_col[P + 1], su));
+          tmark(su, "distance-1 update done", P);
+          if (n_mid > 0) {   // distance 2, FAR rows: the diagonal block of that column block was the MID rows' second update
+            cudaStream_t st = colS[2];
+            KBO_CUDA(h, cudaStreamWaitEvent(st, ev_solve[P], 0));
+            KBO_CUDA(h, cudaStreamWaitEvent(st, ev_mid[P], 0));
+            if (cudaEvent_t pe = pred_of(2)) KBO_CUDA(h, cudaStreamWaitEvent(st, pe, 0));
+            dgemm64_launch<true, EPI_STORE>(st, n_far, n_mid, Wd, Lf, lda, Lm, lda, A + (size_t)rf * lda + rm, lda, -1.0, 1.0, KM_FULL, 0, TS_NONE);
+            KBO_LAUNCH_CHECK(h);
+            KBO_CUDA(h, cudaEventRecord(ev_cb[(size_t)(P + 2) * CBW + 2], st));
+            tmark(st, "distance-2 update done", P);
+          }
           // distances 2..Dn: column block j = P + k, rows from its diagonal block down; each after what was added to that block before
           // (distance k + 1 of the previous panel, or — the farthest — the previous panel's bulk)
-          for (int k = 2; k <= Dn; k++) {
+          for (int k = n_mid > 0 ? 3 : 2; k <= kmax_of(P); k++) {
             const int j = P + k, c0 = j * OW;
             if (c0 >= N) break;
             cudaStream_t st = colS[k];
             KBO_CUDA(h, cudaStreamWaitEvent(st, ev_solve[P], 0));
-            if (P > 0) KBO_CUDA(h, cudaStreamWaitEvent(st, k < Dn ? ev_cb[(size_t)j * (Dn + 1) + k + 1] : ev_rest[P - 1], 0));
+            if (cudaEvent_t pe = pred_of(k)) KBO_CUDA(h, cudaStreamWaitEvent(st, pe, 0));
             const double* Lc = A + (size_t)c0 * lda + K0;
             dgemm64_launch<true, EPI_STORE>(st, N - c0, min(OW, N - c0), Wd, Lc, lda, Lc, lda, A + (size_t)c0 * lda + c0, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
             KBO_LAUNCH_CHECK(h);
-            KBO_CUDA(h, cudaEventRecord(ev_cb[(size_t)j * (Dn + 1) + k], st));
+            KBO_CUDA(h, cudaEventRecord(ev_cb[(size_t)j * CBW + k], st));
+            tmark(st, k == 2 ? "distance-2 update done" : k == 3 ? "distance-3 update done" : "distance-4+ update done", P);
           }
-          // the bulk: every column block farther than Dn
-          const int cB = (P + Dn + 1) * OW;
-          if (cB < N) {
-            KBO_CUDA(h, cudaStreamWaitEvent(sb, ev_solve[P], 0));
-            const double* Lb = A + (size_t)cB * lda + K0;
-            dgemm64_launch<true, EPI_STORE>(sb, N - cB, N - cB, Wd, Lb, lda, Lb, lda, A + (size_t)cB * lda + cB, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
-            KBO_LAUNCH_CHECK(h);
-            KBO_CUDA(h, cudaEventRecord(ev_rest[P], sb));
+          // the bulk: every column block farther than that — per panel, or (merged) for the pair (P−1, P) after the odd panel
+          if (!pairs || (P % 2 == 1)) {
+            const int Pb = pairs ? P - 1 : P;   // first panel of the bulk
+            const int cB = (Pb + kmax_of(Pb) + 1) * OW, Kb = pairs ? 2 * OW : Wd;
+            if (cB < N) {
+              KBO_CUDA(h, cudaStreamWaitEvent(sb, ev_solve[P], 0));
+              const double* Lb = A + (size_t)cB * lda + (size_t)Pb * OW;
+              dgemm64_launch<true, EPI_STORE>(sb, N - cB, N - cB, Kb, Lb, lda, Lb, lda, A + (size_t)cB * lda + cB, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
+              KBO_LAUNCH_CHECK(h);
+              KBO_CUDA(h, cudaEventRecord(ev_rest[P], sb));
+              tmark(sb, "bulk update done", P);
+            }
           }
         }
-      }
-      // ---- inverse stream: W_PP = L_PP⁻¹ by recursive doubling from the 64-block inverses, then the row panels of L⁻¹ -------------
-      KBO_CUDA(h, cudaStreamWaitEvent(si, ev_chain[P], 0));
-      {
-        double* Wpp = W + (size_t)K0 * ldw + K0;
-        const double* Lpp = A + (size_t)K0 * lda + K0;
-        for (int b = NB; b < Wd; b *= 2)
-          for (int r0 = 0; r0 + b < Wd; r0 += 2 * b) {
-            const int rows2 = min(b, Wd - (r0 + b));
-            double* T21 = T + (size_t)(K0 + r0 + b) * ldw + K0 + r0;
-            dgemm64_launch<false, EPI_STORE>(si, rows2, b, b, Lpp + (size_t)(r0 + b) * lda + r0, lda, Wpp + (size_t)r0 * ldw + r0, ldw, T21, ldw, 1.0, 0.0,
-                                             KM_FROM_N, 0, TS_NONE);
-            KBO_LAUNCH_CHECK(h);
-            dgemm64_launch<false, EPI_STORE>(si, rows2, b, rows2, Wpp + (size_t)(r0 + b) * ldw + r0 + b, ldw, T21, ldw,
-                                             Wpp + (size_t)(r0 + b) * ldw + r0, ldw, -1.0, 0.0, KM_UPTO_M, 0, TS_NONE);
-            KBO_LAUNCH_CHECK(h);
-          }
       }
       if (zsolve) {
         KBO_TRY(kbo_i_zsolve_diag(h, K0, Wd, si));
         if (rows_t > 0) {
           KBO_CUDA(h, cudaStreamWaitEvent(si, ev_nsolve[P], 0));
-          if (rows_t > OW) KBO_CUDA(h, cudaStreamWaitEvent(si, ev_solve[P], 0));
+          if (midmode && rows_t > OW) KBO_CUDA(h, cudaStreamWaitEvent(si, ev_mid[P], 0));
+          if (rows_t > (midmode ? 2 : 1) * OW) KBO_CUDA(h, cudaStreamWaitEvent(si, ev_solve[P], 0));
           KBO_TRY(kbo_i_zsolve_update(h, K0, Wd, si));
         }
       }
@@ -830,6 +931,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
         if (P > 0) {   // rows [P0, done) of L left of this panel: the earlier panels' shadows
           KBO_CUDA(h, cudaStreamWaitEvent(si, ev_solve[P - 1], 0));
           KBO_CUDA(h, cudaStreamWaitEvent(si, ev_nsolve[P - 1], 0));
+          if (midmode) KBO_CUDA(h, cudaStreamWaitEvent(si, ev_mid[P - 1], 0));
         }
         double* Wrp = W + (size_t)P0 * ldw + P0;
         const double* Lrp = A + (size_t)P0 * lda + P0;
@@ -885,6 +987,17 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
     }
     fprintf(stderr, "   chain totals: waiting %.3f | diagonal blocks %.3f ms; host enqueue of the whole factorisation %.3f ms (depth %d)\n", sum[0], sum[1],
             host_ms, Dn);
+    if (!tl.empty()) {
+      std::vector<std::pair<float, size_t>> order;
+      for (size_t i = 0; i < tl.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tr[0], tl[i].e);
+        order.push_back({ms, i});
+      }
+      std::sort(order.begin(), order.end());
+      for (auto& o : order) fprintf(stderr, "   %8.3f ms  panel %2d  %s\n", o.first, tl[o.second].P, tl[o.second].what);
+      for (auto& t : tl) cudaEventDestroy(t.e);
+    }
     for (auto& e : tr) cudaEventDestroy(e);
     for (auto& e : tp) cudaEventDestroy(e);
   }

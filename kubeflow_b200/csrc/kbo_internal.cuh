@@ -91,9 +91,9 @@ struct kbo_handle {
   bool part_tried = false, part_ok = false;
   void *gctx_chain = nullptr, *gctx_rest = nullptr;   // CUgreenCtx
   // stream roles: 0 chain, 1 near shadow (both on the chain's partition), 2 far shadow, 3..8 column-block updates at distance 1..6,
-  // 9 bulk trailing update, 10 inverse
-  cudaStream_t s3g[11] = {};       // green-context set
-  cudaStream_t s3p[11] = {};       // the same roles as plain priority streams (small N, profilers, no green contexts)
+  // 9 bulk trailing update, 10 inverse, 11 W_PP and 12 MID rows (both on the chain's partition)
+  cudaStream_t s3g[13] = {};       // green-context set
+  cudaStream_t s3p[13] = {};       // the same roles as plain priority streams (small N, profilers, no green contexts)
   DevBuf Linv4;                     // the four 64×64 block inverses of the current panel
   std::vector<cudaEvent_t> ev_panel;
   // ---- lazy inverse (fit.cu, solve.cu): the product path never needs all of W = L⁻¹ -----------------------------------------

@@ -873,14 +873,15 @@ def test_lazy_inverse_sweep_matches_the_full_fit(N, M, D, kind, acq):
 
 @pytest.mark.parametrize("N,M,D,mode", [(700, 5000, 5, "tc"), (2304, 20000, 16, "tc"), (1500, 4000, 7, "f64")])
 def test_fit_variants_agree(N, M, D, mode, tmp_path):
-    """The factorisation's schedules — v3 (default: diagonal-block chain on its own SM partition, shadow panel solve), the same
-    without the partition, v2 (look-ahead, one-GEMM panel solve), the one-stream sequence — are the same arithmetic up to the
-    order the trailing updates are applied in: L, W, alpha, LML and the suggestion agree to FP64 rounding, and all of them with
+    """The factorisation's schedules — v3 (default: diagonal-block chain on its own SM partition, near / mid / far shadows, look-ahead
+    depth 3 with merged bulk updates), the same without the partition, with other depths and panel widths, v2 (look-ahead, one-GEMM
+    panel solve), the one-stream sequence — are the same arithmetic up to the order the trailing updates are applied in: L, W, alpha, LML and the suggestion agree to FP64 rounding, and all of them with
     the oracle's Cholesky."""
     import os, subprocess, sys
     runs = {}
     for name, env in (("v3", {}), ("v3-unpartitioned", {"KBO_FIT_NO_PARTITION": "1"}), ("v2", {"KBO_FIT_V2": "1"}), ("serial", {"KBO_FIT_SERIAL": "1"}),
-                      ("v3-512", {"KBO_FIT_OW": "512"})):
+                      ("v3-512", {"KBO_FIT_OW": "512"}), ("v3-depth1", {"KBO_FIT_DEPTH": "1"}), ("v3-depth5-unpaired", {"KBO_FIT_DEPTH": "5", "KBO_FIT_PAIR": "0"}),
+                      ("v3-mid-rows", {"KBO_FIT_MID": "1"})):
         out = str(tmp_path / f"{name}.npz")
         subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_fit_variant.py"), str(N), str(M), str(D), mode, out],
                        check=True, env={**os.environ, **env}, timeout=300)
