@@ -944,3 +944,26 @@ def test_lazy_fit_decides_among_hundreds_of_survivors_by_triangular_solves():
         lazy.close(); e64.close()
     print(f"\nprefix survivors by kappa: {seen}")
     assert any(64 < n <= 256 for n in seen), seen
+
+
+def test_fit_is_bit_reproducible_run_to_run():
+    """The default factorisation runs on a dozen streams ordered by events only; every read-modify-write of a block is ordered, so
+    repeated fits of the same history must give bit-identical L, alpha and suggestion (a missing dependency shows up here as run-to-run
+    differences long before it shows up as a wrong answer)."""
+    N, M, D = 6144, 20000, 24
+    X, y, Xc = O.synthetic(N, M, D)
+    g = dict(kind="matern52", acq="ei", **O.theta_of_record(D))
+    e = _engine(g, "tc")
+    ref = None
+    for it in range(5):
+        e.tell(X, y)
+        b = e.ask(Xc)
+        Lm, _, al = e.state()
+        cur = (Lm.clone(), al.clone(), b.index, b.value)
+        if ref is None:
+            ref = cur
+        else:
+            assert torch.equal(torch.tril(cur[0]), torch.tril(ref[0])), it
+            assert torch.equal(cur[1], ref[1]), it
+            assert (cur[2], cur[3]) == (ref[2], ref[3]), it
+    e.close()
