@@ -53,6 +53,7 @@ void kbo_destroy(kbo_handle* h) {
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& e : h->ev_panel) cudaEventDestroy(e);
+  if (h->ev_gram) cudaEventDestroy(h->ev_gram);
   kbo_i_fit_partition_free(h);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_upd) cudaStreamDestroy(h->s_upd);

@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(1024) prep_y_kernel(const double* __restrict__
 // K = amp·k(Xs,Xs) + noise·I.  Exact pairwise differences (as scipy cdist does), lower tiles computed
 // and mirrored.  64×64 tile, 4×4 per thread, D consumed in chunks of 16 through shared memory.
 __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs, int N, int D, int kind, double amp, double noise,
-                                                   double* __restrict__ K, int ldk) {
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+                                                   double* __restrict__ K, int ldk, int tile0) {
+  const int m0 = blockIdx.y * 64, n0 = (blockIdx.x + tile0) * 64;
   if (n0 > m0) return;
   __shared__ double Xi[16][66], Xj[16][66];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -640,7 +640,10 @@ void kbo_i_fit_partition_free(kbo_handle* h) {
   h->gctx_chain = h->gctx_rest = nullptr;
 }
 
-static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s, int lead) {
+static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double* W, int ldw, int* info_dev, cudaStream_t s, int lead,
+                                cudaEvent_t e_early = nullptr) {
+  // e_early (optional): the first column block of A is complete and info / W are zeroed (the caller did both); the rest of A follows
+  // on s.  The chain-side streams then start on e_early; everything that touches other column blocks waits for the whole matrix.
   // panel width: 256 (four 64-blocks per panel), or KBO_FIT_OW=512 (eight): wider panels make the trailing updates K = 512 GEMMs
   static const int ow_env = getenv("KBO_FIT_OW") ? atoi(getenv("KBO_FIT_OW")) : 0;
   const int OW = ow_env == 512 ? 512 : 256, NB = KBO_NB, n_panels = (N + OW - 1) / OW;
@@ -723,13 +726,18 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
     for (auto& e : tr) cudaEventCreate(&e);
     cudaEventRecord(tr[0], s);
   }
-  KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
-  KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));   // on the caller's stream: all SMs, not the chain's 8
+  if (!e_early) {
+    KBO_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+    KBO_CUDA(h, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)N * ldw, s));   // on the caller's stream: all SMs, not the chain's 8
+  }
   // a lazy fit takes alpha from triangular solves: the forward one (z = L⁻¹·yn) is carried along, one panel behind (solve.cu)
   const bool zsolve = lead < N && OW == 256 && A == (double*)h->K.p && W == (double*)h->W.p && N == h->N && lda == h->ld;
   if (zsolve) KBO_TRY(kbo_i_zsolve_begin(h, s));
   KBO_CUDA(h, cudaEventRecord(e_start, s));
-  for (cudaStream_t st : all_streams) KBO_CUDA(h, cudaStreamWaitEvent(st, e_start, 0));
+  for (cudaStream_t st : all_streams) {
+    const bool chain_side = st == sc || st == sn || st == sw;
+    KBO_CUDA(h, cudaStreamWaitEvent(st, e_early && chain_side ? e_early : e_start, 0));
+  }
   const int RW = 512;
   int rp0 = 0;
   auto body = [&]() -> int {
@@ -828,6 +836,7 @@ static int factor_and_invert_v3(kbo_handle* h, double* A, int N, int lda, double
         };
         cudaEvent_t pred1 = pred_of(1);
         // the next diagonal block's own update (after the previous panel's MID update of the same block, or the distance-2 update)
+        if (P == 0 && e_early) KBO_CUDA(h, cudaStreamWaitEvent(sn, e_start, 0));   // that block is not in the first column block
         if (cudaEvent_t pe = midmode ? (P > 0 ? ev_t2[P - 1] : nullptr) : pred1) KBO_CUDA(h, cudaStreamWaitEvent(sn, pe, 0));
         const double* Ln = A + (size_t)rn * lda + K0;
         dgemm64_launch<true, EPI_STORE>(sn, n_near, n_near, Wd, Ln, lda, Ln, lda, A + (size_t)rn * lda + rn, lda, -1.0, 1.0, KM_FULL, 0, TS_LOWER);
@@ -1106,8 +1115,22 @@ int kbo_i_zero_upper(kbo_handle* h, double* A, int N, int lda, cudaStream_t s) {
 
 int kbo_i_gram(kbo_handle* h, const double* Xs, int N, int D, int kernel, double amp, double noise, double* K, int ldk, cudaStream_t s) {
   dim3 grid((N + 63) / 64, (N + 63) / 64);
-  gram_kernel<<<grid, 256, 0, s>>>(Xs, N, D, kernel, amp, noise, K, ldk);
+  gram_kernel<<<grid, 256, 0, s>>>(Xs, N, D, kernel, amp, noise, K, ldk, 0);
   KBO_LAUNCH_CHECK(h);
+  return KBO_OK;
+}
+// The Gram matrix in two launches: the first `tiles_first` 64-column tiles (all the first panel's chain and shadows read), an event,
+// then the rest — the factorisation starts 0.3 ms earlier (fit.cu: factor_and_invert_v3, e_early).
+static int gram_two_parts(kbo_handle* h, const double* Xs, int N, int D, int kernel, double amp, double noise, double* K, int ldk, int tiles_first,
+                          cudaEvent_t e_first, cudaStream_t s) {
+  const int nt = (N + 63) / 64, t1 = min(tiles_first, nt);
+  gram_kernel<<<dim3(t1, nt), 256, 0, s>>>(Xs, N, D, kernel, amp, noise, K, ldk, 0);
+  KBO_LAUNCH_CHECK(h);
+  KBO_CUDA(h, cudaEventRecord(e_first, s));
+  if (nt > t1) {
+    gram_kernel<<<dim3(nt - t1, nt), 256, 0, s>>>(Xs, N, D, kernel, amp, noise, K, ldk, t1);
+    KBO_LAUNCH_CHECK(h);
+  }
   return KBO_OK;
 }
 
@@ -1223,9 +1246,20 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
   if (trace)
     for (auto& e : te) cudaEventCreate(&e);
   if (trace) cudaEventRecord(te[0], s);
-  KBO_TRY(kbo_i_gram(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, s));
-  if (trace) cudaEventRecord(te[1], s);
   static const bool serial = getenv("KBO_FIT_SERIAL") != nullptr;   // A/B: Cholesky, then recursive-doubling inverse, on one stream
+  static const bool v2_env = getenv("KBO_FIT_V2") != nullptr;
+  static const bool early_env = !(getenv("KBO_FIT_EARLY") && atoi(getenv("KBO_FIT_EARLY")) == 0);
+  const bool early = early_env && !serial && !v2_env && N >= 1024;   // v3 starts on the first column block of the Gram matrix
+  if (early) {
+    KBO_TRY(fit_streams(h, 8));
+    KBO_CUDA(h, cudaMemsetAsync(h->info.p, 0, sizeof(int), s));
+    KBO_CUDA(h, cudaMemsetAsync(h->W.p, 0, sizeof(double) * (size_t)N * ld, s));
+    if (!h->ev_gram) KBO_CUDA(h, cudaEventCreateWithFlags(&h->ev_gram, cudaEventDisableTiming));
+    KBO_TRY(gram_two_parts(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, 8, h->ev_gram, s));
+  } else {
+    KBO_TRY(kbo_i_gram(h, (const double*)h->Xs.p, N, D, p->kernel, p->amplitude, p->noise, (double*)h->K.p, ld, s));
+  }
+  if (trace) cudaEventRecord(te[1], s);
   h->w_full = true;
   h->w_lead = N;
   if (serial) {
@@ -1247,7 +1281,7 @@ int kbo_i_fit(kbo_handle* h, const double* X, const double* y, int N, int D, con
       if (v2)
         KBO_TRY(factor_and_invert_v2(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s, lead));
       else
-        KBO_TRY(factor_and_invert_v3(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s, lead));
+        KBO_TRY(factor_and_invert_v3(h, (double*)h->K.p, N, ld, (double*)h->W.p, ld, (int*)h->info.p, s, lead, early ? h->ev_gram : nullptr));
       h->w_lead = lead < N ? lead : N;
       h->w_full = lead >= N;
     }

@@ -96,6 +96,7 @@ struct kbo_handle {
   cudaStream_t s3p[13] = {};       // the same roles as plain priority streams (small N, profilers, no green contexts)
   DevBuf Linv4;                     // the four 64×64 block inverses of the current panel
   std::vector<cudaEvent_t> ev_panel;
+  cudaEvent_t ev_gram = nullptr;   // the first column block of the Gram matrix is complete (the factorisation starts on it)
   // ---- lazy inverse (fit.cu, solve.cu): the product path never needs all of W = L⁻¹ -----------------------------------------
   bool lazy_w = true;              // kbo_set_lazy_inverse: tensor-core fits form only the leading rows of W the pruning pass reads
   bool w_full = true;              // all rows of W (and the full fp16 planes) exist
