@@ -442,6 +442,12 @@ def main():
                          "traffic": kernel_traffic("tcrank_traffic.json" if rank_tc else "tcvar_traffic.json", rows_per_launch) if (rank_tc or not fast_rank) else None,
                          "launch_ms": var_launch_ms, "launches_per_step": chunks, "flops_per_launch": flops_launch,
                          "launch_note": "variance phase time / chunks (CUDA events inside libkbo around tc_rank_kernel + its 6 µs finish kernel)",
+                         "share_of_step": {"note": "where the product path's step goes (phases_ms / ms_per_step); this object rates the kernel that carries "
+                                                   "the path's M·N² term, which the pruning pass shrinks to 1/64 — the step's largest kernels are rated in "
+                                                   "fit_fp64 (dgemm64_kernel, FP64 DMMA) and kstar_hbm / profiles (tc_kstar_kernel, MUFU-bound)",
+                                           "fit": mean("fit_ms") / ms_step, "kstar_kernel": mean("cross_kernel_ms") / ms_step,
+                                           "prefix_contraction_this_kernel": mean("var_kernel_ms") / ms_step, "calibration": mean("calib_ms") / ms_step,
+                                           "bounds_and_fp64_decision": mean("acq_kernel_ms") / ms_step},
                          "measured_on": ("the full contraction, kbo_set_rank_prefix(h, 0), 3 steps through kbo_suggest_host in this run (%.1f ms per step): the product "
                                          "path above prunes with the same kernel over the first eighth of the trial tiles (%.2f ms per step) and contracts fully only "
                                          "the %d candidates that survive" % (fmean("total_ms"), mean("var_kernel_ms"), prefix_survivors)) if pruned else "the product path"},
