@@ -21,7 +21,7 @@ for line in txt.splitlines():
         flush()
         name, counts, total = m.group(1), collections.Counter(), 0
         continue
-    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z0-9_.]+)", line)
     if m and name:
         total += 1
         op = m.group(1)
