@@ -39,8 +39,10 @@ __device__ __forceinline__ void sv_grid_barrier(unsigned* ctr, unsigned& target)
 //   (a) V_P = W_PP·B_P — one warp per row of the panel (the first 32 CTAs), B_P in shared memory as [rhs][k];
 //   (b) B_>P −= L_>P,P·V_P — one warp per row below, grid-strided, V_P in shared memory as [rhs][k] (conflict-free).
 // Fixed-order butterfly reductions: a right-hand side's result does not depend on the grid size or on what rides beside it.
+template <bool SINGLE>   // SINGLE: one group (the usual case: alpha, one survivor) — the group loops vanish at compile time
 __global__ void __launch_bounds__(256)
-sv_forward_kernel(const double* __restrict__ L, const double* __restrict__ W, int N, int ld, double* B, double* V, unsigned* bar, int G, size_t gstride) {
+sv_forward_kernel(const double* __restrict__ L, const double* __restrict__ W, int N, int ld, double* B, double* V, unsigned* bar, int G_rt, size_t gstride) {
+  const int G = SINGLE ? 1 : G_rt;
   // G groups of 8 right-hand sides ride one launch (group g at B + g·gstride): the rows of L and W_PP are loaded once and every group
   // goes through the arithmetic of a single-group solve, so a right-hand side's result does not depend on G either
   extern __shared__ double vs_all[];   // [G][SV_R][SV_P]
@@ -234,11 +236,12 @@ int kbo_i_solve_fwd(kbo_handle* h, double* B, double* V, cudaStream_t s, int G, 
   const size_t smem = sizeof(double) * (size_t)G * SV_R * SV_P;
   static bool attr = false;
   if (!attr) {
-    KBO_CUDA(h, cudaFuncSetAttribute(sv_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * SV_GMAX * SV_R * SV_P)));
+    KBO_CUDA(h, cudaFuncSetAttribute(sv_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * SV_GMAX * SV_R * SV_P)));
     attr = true;
   }
   void* args[] = {(void*)&L, (void*)&W, (void*)&N, (void*)&ld, (void*)&B, (void*)&V, (void*)&bar, (void*)&G, (void*)&gstride};
-  KBO_CUDA(h, cudaLaunchCooperativeKernel((const void*)sv_forward_kernel, dim3(h->sm_count), dim3(256), args, smem, s));   // one CTA per SM: co-resident
+  const void* fn = G == 1 ? (const void*)sv_forward_kernel<true> : (const void*)sv_forward_kernel<false>;
+  KBO_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(h->sm_count), dim3(256), args, smem, s));   // one CTA per SM: co-resident
   return KBO_OK;
 }
 // Z (N × 8, overwritten) -> A = L⁻ᵀ·Z (N × 8)
