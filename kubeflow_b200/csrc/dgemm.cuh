@@ -26,8 +26,9 @@ enum { TS_NONE = 0, TS_LOWER = 1 };
 #define DG_SMEM_BYTES (2 * DG_STAGE_DOUBLES * 8 + 2 * DG_BM * 8)   // two slabs + the row-sum epilogue's scratch
 
 // FP64 tensor-core MMA (DMMA), warp-level: D(8×8) += A(8×4)·B(4×8).  Fragments (lane = 4g + t): a = A[g][t], b = B[t][g],
-// c/d = C[g][2t], C[g][2t+1].  B200's FP64 tensor rate is about twice its vector DFMA rate, and a fragment load feeds 256
-// FMAs, so the FP64 GEMM-shaped work (potrf/trtri updates, FP64 variance contraction, CMA-ES products) runs here.
+// c/d = C[g][2t], C[g][2t+1].  On B200 DMMA and plain DFMA reach the same 37 TFLOP/s (tests/studies/dmma_probe.cu); the point of
+// the tensor form is that one fragment load feeds 256 FMAs, so the FP64 GEMM-shaped work (potrf / trtri updates, FP64 variance
+// contraction, CMA-ES products) is not bound by shared-memory loads.
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
