@@ -7,9 +7,9 @@
 //                                                              by √5 (Matérn) or 1/√2 (RBF) so the epilogue needs no constant)
 // with c·x on the tensor cores.  Coordinates are split into fp16 hi + lo (|x̂ − hi − lo| ≤ 2⁻²²|x̂|) and all four partial
 // products are accumulated in fp32 TMEM (small ones first), so c·x carries ~1e-7 relative error — the kernel value is then
-// evaluated in fp32 (MUFU rsqrt / ex2) per element by the epilogue warps, written ONCE as the fp16 hi plane the ranking kernel
-// consumes (no lo plane, no FP64), and the normalised mean μ̃ = Σ_n K̃*[m,n]·alpha[n] is accumulated on the fly (fp32 FMAs in
-// groups of four, groups added in FP64).  Both μ̃ and the variance built from this plane are only used to RANK: their error
+// evaluated in fp32 (MUFU sqrt / ex2) per element by the epilogue warps, written ONCE as the fp16 hi plane the ranking kernel
+// consumes (no lo plane, no FP64), and the normalised mean μ̃ = Σ_n K̃*[m,n]·alpha[n] is accumulated on the fly (four fp32 FMA
+// chains of four trials, summed and added in FP64 once per 16 trials).  Both μ̃ and the variance built from this plane are only used to RANK: their error
 // is measured per sweep on stratified calibration rows against the FP64 path and every candidate that could still be the
 // maximum is re-evaluated in FP64 (sweep.cu).
 //
@@ -18,7 +18,8 @@
 //   warp 0      TMA producer
 //   warp 1      MMA issuer (one thread): per (tile, slab) 2 k-steps × 4 products of M128 N256 K16 → one of two TMEM accumulators
 //   warps 2-17  epilogue: tcgen05.ld 16 columns → d² → kernel → fp16 → one 32-byte store per thread per batch; μ̃ partials
-// Per 128×256 tile the epilogue (~15 instructions and 2 MUFU per element) is the limiter, the MMAs take a quarter of that.
+// Per 128×256 tile the epilogue (~12 instructions and 2 MUFU per element: MUFU-bound, profiles/r11_tckstar_cfg3_summary.csv) is the
+// limiter, the MMAs take a sixth of that.
 #include "kbo_internal.cuh"
 #include <type_traits>
 
